@@ -1,0 +1,121 @@
+"""The oracle (oracle/lanczos_oracle.py) is held to the golden vectors produced by the
+live reference (tests/golden/make_golden.py).  Same NumPy ops in the same order =>
+the comparison is bit-for-bit.  CPU only."""
+import hashlib
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import lanczos_oracle as orc
+
+
+def _tri(T):
+    return np.diag(T).copy(), np.diag(T, 1).copy()
+
+
+@pytest.mark.parametrize("N", [2, 3, 5])
+def test_pattern_T7_matches_reference(golden, N):
+    # kron generator == Hamiltonian.create_sparse_T("7") after sort_indices, bit-exact
+    T = orc.laplacian_csr((N, N, N), -6.0 * 1.75, 1.75, periodic=True)
+    assert np.array_equal(T.indptr, golden[f"T7_N{N}_indptr"])
+    assert np.array_equal(T.indices, golden[f"T7_N{N}_indices"])
+    assert np.array_equal(T.data, golden[f"T7_N{N}_data"])
+    # emission-order restatement (COO with duplicates) gives the same matrix
+    T2 = orc.reference_T_csr(N, 1.75)
+    T2.sum_duplicates()
+    T2.sort_indices()
+    assert np.array_equal(T2.indptr, golden[f"T7_N{N}_indptr"])
+    assert np.array_equal(T2.indices, golden[f"T7_N{N}_indices"])
+    assert np.array_equal(T2.data, golden[f"T7_N{N}_data"])
+
+
+@pytest.mark.parametrize("N", [3, 5])
+def test_deuteron_H_matches_reference(golden, N):
+    dx = 25.0 / N
+    g = np.linspace(-12.5, 12.5, N)
+    Z, Y, X = np.meshgrid(g, g, g, indexing="ij")
+    pot = orc.deuteron_potential(X, Y, Z).ravel()
+    H = orc.laplacian_csr((N, N, N), 6.0 * 1.75, -1.75, periodic=True, diag=pot)
+    assert np.array_equal(H.indptr, golden[f"H_N{N}_indptr"])
+    assert np.array_equal(H.indices, golden[f"H_N{N}_indices"])
+    np.testing.assert_allclose(H.data, golden[f"H_N{N}_data"], rtol=1e-15, atol=0)
+
+
+def test_c1_small_bit_exact(golden):
+    H = orc.laplacian_csr((24, 20), 4.0, -1.0, periodic=True)
+    res = orc.lanczos(H, 30, seed=99, vectors=True)
+    assert np.array_equal(res["alpha"], golden["c1s_alpha"])
+    assert np.array_equal(res["beta"], golden["c1s_beta"])
+    assert np.array_equal(res["theta"], golden["c1s_theta"])
+    assert np.array_equal(res["V"][:, :3].T, golden["c1s_V_first3"])
+
+
+@pytest.mark.parametrize("tag,per", [("c1d", False), ("c1p", True)])
+def test_c1_full_bit_exact(golden, tag, per):
+    H = orc.laplacian_csr((200, 200), 4.0, -1.0, periodic=per)
+    res = orc.lanczos(H, 100, seed=99)
+    assert np.array_equal(res["alpha"], golden[f"{tag}_alpha"])
+    assert np.array_equal(res["beta"], golden[f"{tag}_beta"])
+    np.testing.assert_allclose(res["theta"], golden[f"{tag}_theta"], rtol=1e-13, atol=1e-13)
+
+
+def test_c3_small_user_start_vector(golden):
+    H = orc.laplacian_csr((12, 12, 12), 6.0, -1.0, periodic=True)
+    v0 = np.random.RandomState(7).uniform(-1, 1, 12 ** 3)
+    res = orc.lanczos(H, 40, v0=v0)
+    assert np.array_equal(res["alpha"], golden["c3s_alpha"])
+    assert np.array_equal(res["beta"], golden["c3s_beta"])
+
+
+def test_deuteron_bit_exact(golden):
+    H, _, _, _ = orc.deuteron_hamiltonian(16)
+    res = orc.lanczos(H, 120, seed=78)
+    assert np.array_equal(res["alpha"], golden["deut_alpha"])
+    assert np.array_equal(res["beta"], golden["deut_beta"])
+    np.testing.assert_allclose(res["theta"], golden["deut_theta"], rtol=1e-12, atol=1e-10)
+
+
+def test_delaunay_csr_and_csc(golden):
+    L = orc.delaunay_graph_laplacian(3000, seed=0)
+    sha = hashlib.sha256(L.indptr.tobytes() + L.indices.tobytes()).digest()
+    assert np.array_equal(np.frombuffer(sha, dtype=np.uint8), golden["del_indptr_sha"])
+    res = orc.lanczos(L, 50, seed=99)
+    assert np.array_equal(res["alpha"], golden["del_alpha"])
+    assert np.array_equal(res["beta"], golden["del_beta"])
+    res = orc.lanczos(sp.csc_matrix(L), 50, seed=99)
+    assert np.array_equal(res["alpha"], golden["delcsc_alpha"])
+    assert np.array_equal(res["beta"], golden["delcsc_beta"])
+
+
+def test_edge_cases(golden):
+    H = orc.laplacian_csr((6,), 2.0, -1.0, periodic=False)
+    assert np.array_equal(orc.lanczos(H, 2, seed=3)["T"], golden["n2_T"])
+    assert np.array_equal(orc.lanczos(H, 6, seed=3)["T"], golden["nM_T"])
+    with pytest.raises(IndexError):
+        orc.tridiagonalize(H, 1)
+    with pytest.raises(ValueError):
+        orc.tridiagonalize(H, 7)
+
+
+def test_start_vector_discarded():
+    # quirk 1 of SURVEY §0: row 0 of the basis is orthogonal to the user's start vector
+    H = orc.laplacian_csr((30, 30), 4.0, -1.0, periodic=False)
+    v0 = orc.start_vector(900, seed=99)
+    _, _, V = orc.tridiagonalize(H, 5, seed=99)
+    assert abs(np.dot(V[0], v0)) < 1e-14
+
+
+def test_csr_matvec_rows_matches_scipy():
+    H = orc.laplacian_csr((5, 4, 3), 6.0, -1.0, periodic=True)
+    x = np.random.RandomState(1).uniform(-1, 1, 60)
+    y = orc.csr_matvec_rows(H.indptr, H.indices, H.data, x)
+    assert np.array_equal(y, H * x)
+
+
+def test_rgg_laplacian_shape():
+    L = orc.rgg_graph_laplacian(4000, mean_degree=13.0, seed=0)
+    assert L.shape == (4000, 4000)
+    assert abs(L.sum()) < 1e-9
+    assert 9.0 < (L.nnz / 4000.0 - 1.0) < 14.0   # boundary effects lower the mean degree
+    assert (abs(L - L.T)).nnz == 0
