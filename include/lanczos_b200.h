@@ -1,0 +1,165 @@
+/*
+ * lanczos_b200 — C ABI of the B200-native Lanczos tridiagonalization path.
+ *
+ * This is the drop-in boundary for the hot path of jgslunde/Lanczos.  The reference
+ * is pure Python and has no FFI of its own: its seam is the `use_cuda=True` backend
+ * switch inside `Lanczos.execute_Lanczos` (Python/Regular/Lanczos.py:85-91) and
+ * `IrrLanczos.execute_LanczosOld` (Python/Irregular/IrrLanczos.py:203-208), where
+ * NumPy/SciPy objects are swapped for CuPy ones.  Each entry point below names the
+ * reference lines whose work it takes over.  INTEGRATION.md shows the ctypes stub a
+ * reference maintainer would add at that seam.
+ *
+ * Conventions
+ *  - every function returns an int status (LZ_OK == 0); the message of the last
+ *    failure on the calling thread is available from lz_last_error();
+ *  - no exceptions, no longjmp, no torch types: plain pointers and sizes only;
+ *  - pointers named *_dev are CUDA device pointers on the context's device, pointers
+ *    named *_host are ordinary host pointers; the caller owns every buffer it passes;
+ *  - all GPU work is enqueued on the context's stream; functions documented as
+ *    "synchronises" wait for that stream before returning;
+ *  - a context is not thread-safe; different contexts are independent;
+ *  - all arithmetic is IEEE fp64; indices are int32 (as scipy.sparse CSR), sizes int64.
+ */
+#ifndef LANCZOS_B200_H
+#define LANCZOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LZ_ABI_VERSION 1
+
+/* status codes */
+#define LZ_OK               0
+#define LZ_ERR_INVALID      1   /* bad argument (the Python mirror raises ValueError) */
+#define LZ_ERR_CUDA         2   /* a CUDA runtime call failed */
+#define LZ_ERR_NOMEM        3   /* device allocation failed */
+#define LZ_ERR_BREAKDOWN    4   /* beta == 0 or non-finite: Krylov space exhausted */
+#define LZ_ERR_UNSUPPORTED  5
+#define LZ_ERR_PEER         6   /* multi-GPU exchange timed out / peer failure */
+
+/* boundary conditions of a structured-grid operator */
+#define LZ_BC_PERIODIC   0      /* reference convention, Hamiltonian.py:92-97 */
+#define LZ_BC_DIRICHLET  1      /* 1Dbox.py:15-22 */
+
+/* sparse storage used on the device */
+#define LZ_FMT_CSR   0          /* CSR, sub-warp per row */
+#define LZ_FMT_SELL  1          /* SELL-C-sigma, C = 32 */
+
+/* re-orthogonalisation policy */
+#define LZ_REORTH_NONE       0
+#define LZ_REORTH_FULL       1  /* every step, like Lanczos.reorthogonalize (Lanczos.py:233-251) */
+#define LZ_REORTH_SELECTIVE  2  /* omega-recurrence monitor, fires at sqrt(eps) */
+
+typedef struct lz_ctx lz_ctx;   /* one per (device, stream) */
+typedef struct lz_op lz_op;     /* an operator H living on a context */
+typedef struct lz_team lz_team; /* the set of row shards that run one distributed solve */
+
+/* ---- library ---------------------------------------------------------------- */
+int lz_abi_version(void);
+const char* lz_last_error(void);
+int lz_device_count(int* count);
+
+/* ---- context ----------------------------------------------------------------
+ * Replaces: the implicit CuPy device/stream that `import cupy as np` binds at
+ * Lanczos.py:85-88.  `cuda_stream` is a cudaStream_t (NULL = legacy default stream). */
+int lz_ctx_create(int device, void* cuda_stream, lz_ctx** out);
+int lz_ctx_destroy(lz_ctx* ctx);
+int lz_ctx_sync(lz_ctx* ctx);
+
+/* ---- operators --------------------------------------------------------------
+ * lz_op_stencil_create: matrix-free structured-grid operator
+ *     (H x)_i = (center + diag_i) x_i + sum_axis offdiag[axis] (x_{i+e} + x_{i-e}),
+ * index map i = x + nx*(y + ny*z) (Hamiltonian.py:73-84).  Replaces the CSR that
+ * Hamiltonian.create_sparse_T("7") + create_sparse_V build (Hamiltonian.py:35-69) and
+ * that Lanczos.py:88 uploads.  dim in {1,2,3}; shape[dim]; offdiag[dim]; diag_dev may
+ * be NULL, otherwise M doubles on the device (kept by reference, not copied).
+ * An axis with offdiag == 0 is skipped. */
+int lz_op_stencil_create(lz_ctx* ctx, int dim, const int64_t* shape, int bc,
+                         double center, const double* offdiag,
+                         const double* diag_dev, lz_op** out);
+
+/* lz_op_csr_create: general sparse operator from host CSR arrays (scipy layout:
+ * indptr[M+1], indices[nnz], data[nnz]).  Replaces cupyx.scipy.sparse.csr_matrix(H)
+ * at Lanczos.py:88 / csc_matrix(H) at IrrLanczos.py:205.  The arrays are copied
+ * (and, for LZ_FMT_SELL, converted on the device); the caller keeps its own.
+ * sigma = sorting window in rows (multiple of 32; 0 -> library default). */
+int lz_op_csr_create(lz_ctx* ctx, int64_t M, int64_t nnz, const int32_t* indptr_host,
+                     const int32_t* indices_host, const double* data_host,
+                     int fmt, int sigma, lz_op** out);
+
+int lz_op_rows(const lz_op* op, int64_t* M);
+int lz_op_nnz(const lz_op* op, int64_t* nnz_true, int64_t* nnz_stored);
+
+/* y = H x on the device (`H*V[j]`, Lanczos.py:108,116).  Enqueues only. */
+int lz_op_apply(lz_op* op, const double* x_dev, double* y_dev);
+
+/* Export the operator as sorted CSR with duplicates summed (what scipy holds after
+ * `H.sort_indices()`, 3Ddeuteron.py:81) into host arrays, for bit-exact pattern
+ * checks.  Call with indptr_host == NULL to query nnz only.  Synchronises. */
+int lz_op_export_csr(lz_op* op, int64_t* nnz, int32_t* indptr_host,
+                     int32_t* indices_host, double* data_host);
+int lz_op_destroy(lz_op* op);
+
+/* ---- the Lanczos loop ---------------------------------------------------------
+ * Replaces Lanczos.py:100-119 (== IrrLanczos.py:217-238) including reorthogonalize.
+ */
+typedef struct lz_run_opts {
+    int32_t reorth;        /* LZ_REORTH_*                                            */
+    int32_t cgs_passes;    /* 1 or 2 classical Gram-Schmidt sweeps per reorth        */
+    int32_t ref_compat;    /* 1: reproduce the reference loop exactly (pre-step that
+                              discards v0, (2-|v|^2) form of the sweep, beta taken
+                              before the sweep); 0: v0/|v0| is the first basis vector */
+    int32_t reserved;
+    double  breakdown_tol; /* stop when beta <= breakdown_tol * |alpha_0| (0: only 0/NaN) */
+    double  select_tol;    /* selective: orthogonality level that triggers (0 -> sqrt(eps)) */
+} lz_run_opts;
+
+typedef struct lz_run_info {
+    int32_t steps_done;    /* Lanczos steps completed (== n unless breakdown)        */
+    int32_t reorth_count;  /* steps in which the Gram-Schmidt sweeps ran             */
+    int32_t launches;      /* kernels launched by this call                          */
+    int32_t reserved;
+    float   gpu_ms;        /* device time of the loop (CUDA events on the stream)    */
+    float   reserved2;
+} lz_run_info;
+
+/* Runs n steps from v0_dev (M doubles).  Outputs: alpha_host[n], beta_host[n-1]
+ * (reference numbering, Lanczos.py:112: beta[k] couples rows k and k+1);
+ * V_dev (nullable unless reorth != NONE): n rows of ldv >= M doubles, row-major like
+ * the reference's in-loop layout (Lanczos.py:104).  Row j holds the j-th Lanczos
+ * vector up to the factor row_scale_host[j] (nullable): q_j = row_scale[j] * V[j,:].
+ * Rows that went through a Gram-Schmidt sweep are stored normalised (scale 1); the
+ * others are stored un-normalised to keep the step at two passes over HBM.
+ * Use lz_basis_normalize to fold the factors in.  Synchronises. */
+int lz_lanczos_run(lz_ctx* ctx, lz_op* op, const double* v0_dev, int32_t n,
+                   const lz_run_opts* opts, double* alpha_host, double* beta_host,
+                   double* V_dev, int64_t ldv, double* row_scale_host, lz_run_info* info);
+
+/* V[j,:] *= row_scale[j] for every j (skips factors equal to 1).  Enqueues only. */
+int lz_basis_normalize(lz_ctx* ctx, double* V_dev, int64_t ldv, int32_t n, int64_t M,
+                       const double* row_scale_host);
+
+/* One Gram-Schmidt sweep of row j of V against all rows, in place: the staticmethod
+ * Lanczos.reorthogonalize(V, j) (Lanczos.py:233-251, CPU form :247-249;
+ * IrrLanczos.py:448-466).  V is (n x ldv) row-major on the device.  Enqueues only. */
+int lz_reorthogonalize(lz_ctx* ctx, double* V_dev, int64_t ldv, int32_t n, int64_t M, int32_t j);
+
+/* Ritz vectors: Y[c,:] = sum_j S[j,c] * row_scale[j] * V[j,:], c < k.  The lift loop of
+ * get_H_eigs (Lanczos.py:154-156).  S_host is n x k column-major (column c = c-th
+ * eigenvector of H_eff), row_scale_host nullable (all ones), Y_dev is k rows of ldy.
+ * Enqueues only (S is copied before return). */
+int lz_ritz_vectors(lz_ctx* ctx, const double* V_dev, int64_t ldv, int32_t n, int64_t M,
+                    const double* row_scale_host, const double* S_host, int32_t k,
+                    double* Y_dev, int64_t ldy);
+
+/* Deterministic device reductions used by the diagnostics (test_is_normalized,
+ * print_good_eigs: Lanczos.py:166-185, 288-304): result_host[0] = x.y.  Synchronises. */
+int lz_dot(lz_ctx* ctx, const double* x_dev, const double* y_dev, int64_t M, double* result_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LANCZOS_B200_H */

@@ -1,0 +1,91 @@
+// Internal data structures shared by the translation units of liblanczos_b200.
+#pragma once
+#include "common.cuh"
+
+enum lz_op_kind { LZ_OP_STENCIL = 0, LZ_OP_CSR = 1, LZ_OP_SELL = 2 };
+
+struct lz_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sms = 148;
+    double* partials = nullptr;    // 2 * kMaxPartials doubles: CTA partial sums of streaming kernels
+    double* scratch = nullptr;     // 64 doubles of device scratch (lz_dot, lz_reorthogonalize, ...)
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+};
+
+// Geometry of a structured-grid operator as the kernels see it.  `nz` is the number of
+// z-planes held locally; the planes below/above the local slab come from `zlo`/`zhi`
+// offsets (single shard: periodic wrap inside the same vector, or absent for Dirichlet)
+// or from ghost buffers filled by the neighbouring shard.
+struct lz_stencil {
+    int dim = 3;
+    int64_t nx = 1, ny = 1, nz = 1;
+    int bc = LZ_BC_PERIODIC;
+    double center = 0.0, offx = 0.0, offy = 0.0, offz = 0.0;
+    const double* diag = nullptr;
+    // sharded execution: ghost planes (nx*ny doubles each) written by the z-neighbours.
+    // When null, the kernel wraps (periodic) or drops (Dirichlet) the out-of-slab plane.
+    const double* ghost_lo = nullptr;
+    const double* ghost_hi = nullptr;
+    int sharded = 0;
+};
+
+struct lz_csr {
+    int64_t nnz = 0;
+    int32_t* indptr = nullptr;     // device, M+1
+    int32_t* indices = nullptr;    // device, nnz
+    double* data = nullptr;        // device, nnz
+    int lanes_per_row = 8;
+};
+
+struct lz_sell {
+    int64_t nnz_true = 0, nnz_stored = 0;
+    int64_t nchunks = 0;           // chunks of 32 rows
+    int sigma = 0;
+    int64_t* chunk_off = nullptr;  // device, nchunks+1: start of each chunk in col/val (elements)
+    int32_t* col = nullptr;        // device, nnz_stored, column-major inside a chunk
+    double* val = nullptr;         // device, nnz_stored
+    int32_t* row_of = nullptr;     // device, nchunks*32: original row handled by (chunk, lane); -1 = padding row
+};
+
+struct lz_op {
+    lz_ctx* ctx = nullptr;
+    lz_op_kind kind = LZ_OP_STENCIL;
+    int64_t M = 0;
+    lz_stencil st;
+    lz_csr csr;
+    lz_sell sell;
+    // host copy of the CSR arrays is NOT kept; export reads them back from the device.
+};
+
+namespace lz {
+
+// ---- operator apply with fused dot:  y = s * (H x),  partials[cta] = sum y * (s*x) -----
+// `scale_dev` (nullable => 1) points at a device double.  `partials` has room for
+// kMaxPartials doubles; *nparts receives the number written.
+int launch_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
+                     double* partials, int* nparts, int* launches);
+
+// ---- streaming vector kernels (vecops.cu) ------------------------------------------------
+// partials[cta] = sum x*y
+int launch_dot(lz_ctx* ctx, const double* x, const double* y, int64_t M, double* partials, int* nparts);
+// out = w - ca*sa*a - cb*sb*b with ca/sa/cb/sb read from device memory (nullable b),
+// partials[cta] = sum out^2.  In-place (out == w) is allowed.
+int launch_update_norm(lz_ctx* ctx, const double* w, const double* a, const double* b,
+                       const double* ca_dev, const double* sa_dev, const double* cb_dev,
+                       const double* sb_dev, double* out, int64_t M, double* partials, int* nparts);
+int launch_scale(lz_ctx* ctx, double* x, int64_t M, double s);
+
+// ---- Gram-Schmidt block GEMV pair (reorth.cu) --------------------------------------------
+// dots: part[(r * ncg) + g] = partial of V[r,:] . V[j,:]   for r in [0, nrows)   (nrows <= j+1)
+int launch_cgs_dots(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, const double* target,
+                    int64_t M, double* part, int* ncg_out, const int* flag_dev);
+// update: out = cself * target - sum_{r<nrows} coef[r] * V[r,:]   (coef, cself on the device)
+int launch_cgs_update(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, const double* target,
+                      const double* coef_dev, const double* cself_dev, double* out, int64_t M,
+                      const int* flag_dev);
+// Y[c,:] = sum_r S[r + c*n] * V[r,:]  (S on the device, n x k column-major)
+int launch_ritz_lift(lz_ctx* ctx, const double* V, int64_t ldv, int n, int64_t M,
+                     const double* S_dev, int k, double* Y, int64_t ldy);
+
+}  // namespace lz

@@ -1,0 +1,232 @@
+// K1: matrix-free 3-/5-/7-point stencil apply with the Lanczos alpha dot fused in.
+//
+//   y = s * (H x),   partial[cta] = sum_i y_i * (s * x_i)
+//
+// replaces `r = H*V[j]` + `alpha[j] = np.dot(V[j], r)` (Lanczos.py:116,118) for operators
+// with the reference's structured-grid pattern (Hamiltonian.py:73-99).  `s` is the lazy
+// normalisation factor 1/beta_j of the un-normalised Lanczos vector stored in the basis.
+//
+// Layout/algorithm: a CTA of 8 warps owns an xy-tile of (32*VEC) x 8 points and marches
+// through a chunk of z-planes keeping the z-1 / z / z+1 values of its own column in
+// registers (2.5-D register pipeline).  Per plane a thread issues one 128-bit load for
+// the new z+1 values and two for the y-1 / y+1 rows (L1 hits except on the two tile-edge
+// rows); x neighbours travel by warp shuffle, only the two edge lanes load them.  HBM
+// traffic is the compulsory 8 B read + 8 B write per point (+ 2/zc for the chunk halo).
+#include "internal.h"
+
+namespace lz {
+
+struct StencilArgs {
+    int nx, ny, nz;
+    int periodic;
+    int64_t plane;
+    double c, ox, oy, oz;
+    const double* x;
+    double* y;
+    const double* diag;
+    const double* zlo;    // plane below local plane 0 (nullptr: zero)
+    const double* zhi;    // plane above local plane nz-1
+    const double* scale;  // device scalar, nullptr: 1
+    double* partials;
+    int tiles_x, tiles_y, chunks_z, zc;
+    int64_t nitems;
+};
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const double* p, double (&v)[VEC]) {
+    if constexpr (VEC == 2) {
+        double2 t = __ldg(reinterpret_cast<const double2*>(p));
+        v[0] = t.x;
+        v[1] = t.y;
+    } else {
+        v[0] = __ldg(p);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void zero_vec(double (&v)[VEC]) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v[e] = 0.0;
+}
+
+template <int VEC, bool HAS_Y, bool HAS_Z, bool HAS_DIAG>
+__global__ void __launch_bounds__(kThreads)
+stencil_apply_dot_kernel(const StencilArgs a) {
+    __shared__ double red[kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double s = a.scale ? __ldg(a.scale) : 1.0;
+    constexpr int TX = 32 * VEC;
+    double acc_alpha = 0.0;
+
+    for (int64_t item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+        const int tx = (int)(item % a.tiles_x);
+        const int64_t t = item / a.tiles_x;
+        const int ty = (int)(t % a.tiles_y);
+        const int cz = (int)(t / a.tiles_y);
+        const int ix = tx * TX + VEC * lane;
+        const int iy = ty * kWarps + warp;
+        const bool act = (ix < a.nx) && (iy < a.ny);   // nx % VEC == 0 => whole vector in range
+        const int z0 = cz * a.zc;
+        const int z1 = min(z0 + a.zc, a.nz);
+
+        // y neighbours (row offsets inside a plane)
+        int iym = iy - 1, iyp = iy + 1;
+        bool hym = true, hyp = true;
+        if (iym < 0) { if (a.periodic) iym = a.ny - 1; else hym = false; }
+        if (iyp >= a.ny) { if (a.periodic) iyp = 0; else hyp = false; }
+        const int64_t off_c = (int64_t)iy * a.nx + ix;
+        const int64_t off_m = (int64_t)iym * a.nx + ix;
+        const int64_t off_p = (int64_t)iyp * a.nx + ix;
+        // x neighbours that cannot come from a shuffle
+        const bool edge_l = (lane == 0);
+        const bool edge_r = (lane == 31) || (ix + VEC >= a.nx);
+        int ixl = ix - 1, ixr = ix + VEC;
+        bool hxl = true, hxr = true;
+        if (ixl < 0) { if (a.periodic) ixl = a.nx - 1; else hxl = false; }
+        if (ixr >= a.nx) { if (a.periodic) ixr -= a.nx; else hxr = false; }
+        const int64_t off_l = (int64_t)iy * a.nx + ixl;
+        const int64_t off_r = (int64_t)iy * a.nx + ixr;
+
+        const double* pc = a.x + (int64_t)z0 * a.plane;
+        double vm[VEC], vc[VEC], vp[VEC];
+        zero_vec<VEC>(vm);
+        zero_vec<VEC>(vc);
+        if (act) load_vec<VEC>(pc + off_c, vc);
+        if (HAS_Z) {
+            const double* pm = (z0 > 0) ? (pc - a.plane) : a.zlo;
+            if (act && pm) load_vec<VEC>(pm + off_c, vm);
+        }
+
+#pragma unroll 2
+        for (int z = z0; z < z1; ++z) {
+            zero_vec<VEC>(vp);
+            if (HAS_Z) {
+                const double* pp = (z + 1 < a.nz) ? (pc + a.plane) : a.zhi;
+                if (act && pp) load_vec<VEC>(pp + off_c, vp);
+            }
+            double ym[VEC], yp[VEC];
+            zero_vec<VEC>(ym);
+            zero_vec<VEC>(yp);
+            if (HAS_Y) {
+                if (act && hym) load_vec<VEC>(pc + off_m, ym);
+                if (act && hyp) load_vec<VEC>(pc + off_p, yp);
+            }
+            double left = __shfl_up_sync(0xffffffffu, vc[VEC - 1], 1);
+            double right = __shfl_down_sync(0xffffffffu, vc[0], 1);
+            if (edge_l) left = (act && hxl) ? __ldg(pc + off_l) : 0.0;
+            if (edge_r) right = (act && hxr) ? __ldg(pc + off_r) : 0.0;
+            double dg[VEC];
+            zero_vec<VEC>(dg);
+            if (HAS_DIAG) {
+                if (act) load_vec<VEC>(a.diag + (int64_t)z * a.plane + off_c, dg);
+            }
+            if (act) {
+                double out[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    const double xl = (e == 0) ? left : vc[e - 1];
+                    const double xr = (e == VEC - 1) ? right : vc[e + 1];
+                    // ascending column order of the sorted CSR row (interior points)
+                    double r = a.oz * vm[e];
+                    r = fma(a.oy, ym[e], r);
+                    r = fma(a.ox, xl, r);
+                    r = fma(a.c + dg[e], vc[e], r);
+                    r = fma(a.ox, xr, r);
+                    r = fma(a.oy, yp[e], r);
+                    r = fma(a.oz, vp[e], r);
+                    r *= s;
+                    out[e] = r;
+                    acc_alpha = fma(r, s * vc[e], acc_alpha);
+                }
+                double* py = a.y + (int64_t)z * a.plane + off_c;
+                if constexpr (VEC == 2) st_stream2(py, make_double2(out[0], out[1]));
+                else st_stream1(py, out[0]);
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { vm[e] = vc[e]; vc[e] = vp[e]; }
+            pc += a.plane;
+        }
+    }
+    const double tot = block_sum(acc_alpha, red);
+    if (threadIdx.x == 0 && a.partials) a.partials[blockIdx.x] = tot;
+}
+
+template <int VEC, bool HAS_Y, bool HAS_Z>
+static const void* pick_diag(bool has_diag) {
+    if (has_diag) return (const void*)stencil_apply_dot_kernel<VEC, HAS_Y, HAS_Z, true>;
+    return (const void*)stencil_apply_dot_kernel<VEC, HAS_Y, HAS_Z, false>;
+}
+template <int VEC>
+static const void* pick_kernel(bool has_y, bool has_z, bool has_diag) {
+    if (has_y && has_z) return pick_diag<VEC, true, true>(has_diag);
+    if (has_y) return pick_diag<VEC, true, false>(has_diag);
+    if (has_z) return pick_diag<VEC, false, true>(has_diag);
+    return pick_diag<VEC, false, false>(has_diag);
+}
+
+int launch_stencil_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
+                             double* partials, int* nparts) {
+    const lz_stencil& st = op->st;
+    lz_ctx* ctx = op->ctx;
+    StencilArgs a;
+    a.nx = (int)st.nx; a.ny = (int)st.ny; a.nz = (int)st.nz;
+    a.periodic = (st.bc == LZ_BC_PERIODIC);
+    a.plane = st.nx * st.ny;
+    a.c = st.center; a.ox = st.offx; a.oy = st.offy; a.oz = st.offz;
+    a.x = x; a.y = y; a.diag = st.diag;
+    a.scale = scale_dev; a.partials = partials;
+    const bool has_y = (st.offy != 0.0);
+    const bool has_z = (st.offz != 0.0);
+    if (st.sharded) {
+        a.zlo = st.ghost_lo;
+        a.zhi = st.ghost_hi;
+    } else if (a.periodic) {
+        a.zlo = x + (st.nz - 1) * a.plane;
+        a.zhi = x;
+    } else {
+        a.zlo = nullptr;
+        a.zhi = nullptr;
+    }
+    const bool aligned = ((st.nx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(st.diag) & 15) == 0) &&
+                         (!st.sharded || (((reinterpret_cast<uintptr_t>(st.ghost_lo) |
+                                            reinterpret_cast<uintptr_t>(st.ghost_hi)) & 15) == 0));
+    const int vec = aligned ? 2 : 1;
+    const int TX = 32 * vec;
+    a.tiles_x = (int)((st.nx + TX - 1) / TX);
+    a.tiles_y = (int)((st.ny + kWarps - 1) / kWarps);
+    const void* fn = (vec == 2) ? pick_kernel<2>(has_y, has_z, st.diag != nullptr)
+                                : pick_kernel<1>(has_y, has_z, st.diag != nullptr);
+    int per_sm = 0;
+    LZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t gmax = std::min<int64_t>((int64_t)ctx->sms * per_sm, kMaxPartials);
+    // choose the z-chunking: few chunks (small halo overhead 2/zc) but a CTA count that
+    // fills the persistent grid evenly.
+    const int64_t tiles = (int64_t)a.tiles_x * a.tiles_y;
+    int best_chunks = 1;
+    double best_cost = 1e300;
+    const int max_chunks = (int)std::min<int64_t>(st.nz, 4096);
+    for (int ch = 1; ch <= max_chunks; ++ch) {
+        const int zc = (int)((st.nz + ch - 1) / ch);
+        const int chunks = (int)((st.nz + zc - 1) / zc);
+        const int64_t items = tiles * chunks;
+        const int64_t g = std::min<int64_t>(items, gmax);
+        const int64_t rounds = (items + g - 1) / g;
+        // time ~ rounds * zc * (1 + halo), normalised by the ideal items*zc/gmax
+        const double cost = (double)rounds * (zc + (has_z ? 2.0 : 0.0)) / ((double)st.nz * tiles / gmax);
+        if (cost < best_cost - 1e-12) { best_cost = cost; best_chunks = chunks; }
+        if (zc <= 8) break;
+    }
+    a.zc = (int)((st.nz + best_chunks - 1) / best_chunks);
+    a.chunks_z = (int)((st.nz + a.zc - 1) / a.zc);
+    a.nitems = tiles * a.chunks_z;
+    const int grid = (int)std::min<int64_t>(a.nitems, gmax);
+    void* args[] = {(void*)&a};
+    LZ_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, 0, ctx->stream));
+    if (nparts) *nparts = grid;
+    return LZ_OK;
+}
+
+}  // namespace lz

@@ -1,0 +1,244 @@
+"""Shared implementation behind the two drop-in classes (regular.Lanczos, irregular.IrrLanczos).
+
+The public surface (constructor, method names, keyword names and defaults, properties, error
+types and messages) follows the reference classes - Python/Regular/Lanczos.py:11-337 and
+Python/Irregular/IrrLanczos.py:12-554 - while the loop itself runs in liblanczos_b200.so.
+Diagnostics that the reference computes on the host after the loop (ARPACK comparison, the
+n x n eigenproblem, pretty-printing) stay on the host, as north-star item (4) asks.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from . import engine
+from .engine import Context, LanczosBreakdown, StencilOperator, as_device_operator, operator_rows
+
+_NOT_RUN = "Lanczos Algorithm has not been called."      # Lanczos.py:31
+
+
+class LanczosBase:
+    # ---- construction (Lanczos.py:19-26) --------------------------------------------------
+    def __init__(self, H):
+        self.H = H
+        self.M = operator_rows(H)
+        self.Lanczos_has_been_executed = False
+        self.H_eigs_have_been_found = False
+        self.H_exact_eigs_have_been_found = False
+        self._result = None
+        self._V_host = None
+
+    # ---- lazy properties (Lanczos.py:28-66) -----------------------------------------------
+    @property
+    def H_eff(self):
+        if not self.Lanczos_has_been_executed:
+            raise ValueError(_NOT_RUN)
+        return self._H_eff
+
+    @property
+    def V(self):
+        """(M, n) array whose columns are the Lanczos vectors (Lanczos.py:139: `V.T`).  The basis
+        lives in HBM; it is normalised and copied to the host on first access."""
+        if not self.Lanczos_has_been_executed:
+            raise ValueError(_NOT_RUN)
+        if self._V_host is None:
+            self._V_host = self._result.basis_rows_host()
+        return self._V_host.T
+
+    @property
+    def H_eigvecs(self):
+        if not self.H_eigs_have_been_found:
+            self.get_H_eigs()
+        return self._H_eigvecs
+
+    @property
+    def H_eigvals(self):
+        if not self.H_eigs_have_been_found:
+            self.get_H_eigs()
+        return self._H_eigvals
+
+    @property
+    def H_eigvals_actual(self):
+        if not self.H_exact_eigs_have_been_found:
+            self.find_exact_eigs()
+            self.H_exact_eigs_have_been_found = True
+        return self._H_eigvals_actual
+
+    @property
+    def H_eigvecs_actual(self):
+        if not self.H_exact_eigs_have_been_found:
+            self.find_exact_eigs()
+            self.H_exact_eigs_have_been_found = True
+        return self._H_eigvecs_actual
+
+    @property
+    def result(self):
+        """The engine-level result (alpha, beta, device basis, timings)."""
+        if not self.Lanczos_has_been_executed:
+            raise ValueError(_NOT_RUN)
+        return self._result
+
+    # ---- exact eigenpairs for comparison (Lanczos.py:68-71): host ARPACK, a diagnostic -------
+    def find_exact_eigs(self, nr_vecs=20):
+        import scipy.sparse.linalg
+        print("+++ Calculating exact eigs using scipy.sparse.linalg.eigsh.")
+        H = self.H.tocsr() if isinstance(self.H, StencilOperator) else self.H
+        self._H_eigvals_actual, self._H_eigvecs_actual = scipy.sparse.linalg.eigsh(H, k=nr_vecs, which="SM")
+        print("+++ Finished calculating exact eigs.")
+
+    # ---- the loop ---------------------------------------------------------------------------
+    def _execute(self, n, seed, use_cuda, v0, *, reorth, cgs_passes, ref_compat, fmt, sigma,
+                 device, keep_basis, breakdown_tol, select_tol, verbose=True):
+        if n > self.M:
+            raise ValueError("n cannot be larger than M!")                  # Lanczos.py:76-77
+        if ref_compat and n < 2:
+            # the reference writes beta[j-1] into an empty array (Lanczos.py:107,112)
+            raise IndexError("index -1 is out of bounds for axis 0 with size 0")
+        if not use_cuda:
+            warnings.warn("use_cuda=False: lanczos_b200 has no CPU path, the B200 backend is used",
+                          RuntimeWarning, stacklevel=3)
+        if verbose:
+            print("+++ Executing Lanczos algorithm")
+        self.n = n
+        ctx = Context.default(device)
+        op = as_device_operator(self.H, ctx, fmt=fmt, sigma=sigma)
+        torch = engine._torch()
+        if isinstance(v0, torch.Tensor):
+            np.random.seed(seed)                                             # Lanczos.py:93
+            start = v0
+        else:
+            start = engine.start_vector(self.M, seed, v0)
+        self._device_op = op
+        self._result = engine.run_lanczos(op, start, n, reorth=reorth, cgs_passes=cgs_passes,
+                                          ref_compat=ref_compat, keep_basis=keep_basis,
+                                          breakdown_tol=breakdown_tol, select_tol=select_tol)
+        self._H_eff = self._result.tridiagonal()
+        self._V_host = None
+        self.H_eigs_have_been_found = False
+        if verbose:
+            print("+++ Lanczos executed successfully.")
+        self.Lanczos_has_been_executed = True
+
+    # ---- Ritz pairs (Lanczos.py:145-163) ------------------------------------------------------
+    def _ritz(self, check_vectors):
+        if not self.Lanczos_has_been_executed:
+            raise ValueError(_NOT_RUN)
+        print("+++ Converting eigenvectors from H_eff to H basis.")
+        theta, S = np.linalg.eigh(self.H_eff)                   # small n x n problem: host LAPACK
+        Y = self._result.ritz_vectors_dev(S)                    # K5 on the device
+        Yh = np.ascontiguousarray(Y[:, :self.M].cpu().numpy().T)   # (M, n) like the reference
+        if check_vectors:
+            self.test_is_normalized(Yh, tol=0.001)
+            self.test_is_orthogonal(Yh, tol=0.01)
+        self._H_eigvals = theta
+        self._H_eigvecs = Yh
+        print("+++ Finished Converting.")
+        self.H_eigs_have_been_found = True
+
+    def ritz_values(self, k=None):
+        """Lowest-k Ritz values without touching the basis (eigvalsh of H_eff)."""
+        theta = np.linalg.eigvalsh(self.H_eff)
+        return theta if k is None else theta[:k]
+
+    def ritz_vectors(self, k, which="lowest"):
+        """(theta[:k], Y) with Y a CUDA tensor (k, M): only the wanted Ritz vectors are lifted,
+        (n + k) * 8 * M bytes of traffic instead of the reference's full (M, n) product."""
+        theta, S = np.linalg.eigh(self.H_eff)
+        sel = np.arange(k) if which == "lowest" else np.arange(len(theta) - k, len(theta))
+        Y = self._result.ritz_vectors_dev(S[:, sel])
+        return theta[sel], Y[:, :self.M]
+
+    # ---- diagnostics (Lanczos.py:166-222), host-side printing over device products ------------
+    def _residual_cosines(self):
+        H, eigvecs = self.H, self.H_eigvecs
+        inner_prod = np.zeros(self.n)
+        for i in range(self.n):
+            x = eigvecs[:, i]
+            Hx = H * x
+            Hx = Hx / np.linalg.norm(Hx)
+            inner_prod[i] = np.dot(Hx, x) ** 2
+        return inner_prod
+
+    def compare_eigs(self):
+        if not self.Lanczos_has_been_executed:
+            raise ValueError(_NOT_RUN)
+        print("+++ Comparing to exact eigs.")
+        val_a, vec_a = self.H_eigvals_actual, self.H_eigvecs_actual
+        val_e, vec_e = self.H_eigvals, self.H_eigvecs
+        nr = len(val_a)
+        pairs = np.full((nr, 2), np.nan)
+        pairs[:, 0] = val_a
+        overlap = np.full(nr, np.nan)
+        idx_pairs = np.full(nr, np.nan)
+        for i in range(self.n):
+            o = np.dot(vec_e[:, i], vec_a) ** 2
+            k = o.argmax()
+            if np.isnan(overlap[k]) or o[k] > overlap[k]:
+                pairs[k, 1], overlap[k], idx_pairs[k] = val_e[i], o[k], i
+        perc = abs((pairs[:, 0] - pairs[:, 1]) / pairs[:, 1]) * 100
+        print("__________EIGENVALUE AND EIGVENVECTOR COMPARISON__________")
+        print("%6s %6s %20s %20s %14s %14s" % ("Idx1", "Idx2", "Actual", "Lanczos", "% Diff", "Eigvec Prod"))
+        for i in range(nr):
+            print("%6d %6.0f %20.10f %20.10f %14.4f %14.4f" % (i, idx_pairs[i], pairs[i, 0], pairs[i, 1], perc[i], overlap[i]))
+        return pairs, overlap
+
+    # ---- static helpers kept from the reference (Lanczos.py:233-337) ---------------------------
+    @staticmethod
+    def reorthogonalize(V, j, use_cuda=True):
+        """One Gram-Schmidt sweep of row j of V against all rows, in place (CPU form of the
+        reference, Lanczos.py:247-249: V[j] = 2 V[j] - sum_i (V[j].V[i]) V[i]).  V: (n, M) host
+        array or CUDA tensor with rows = Lanczos vectors."""
+        return engine.reorthogonalize_rows(V, j)
+
+    @staticmethod
+    def get_matched_eigs(v, vL, l, lL):
+        n = len(lL)
+        overlap = np.zeros(n)
+        map_vL2v = np.zeros(n, dtype=int)
+        for i in range(n):
+            o = np.dot(vL[:, i], v) ** 2
+            map_vL2v[i] = o.argmax()
+            overlap[i] = o[map_vL2v[i]]
+        order = overlap.argsort()[::-1]
+        return v[:, map_vL2v[order]], vL[:, order], l[map_vL2v[order]], lL[order]
+
+    @staticmethod
+    def test_is_Hermitian(A):
+        import scipy.sparse as sp
+        B = A.tocsr() if isinstance(A, StencilOperator) else A
+        if sp.issparse(B):
+            assert abs(B - B.T).max() == 0, "A IS NOT HERMITIAN!"
+        else:
+            assert (np.asarray(B) == np.asarray(B).T).all(), "A IS NOT HERMITIAN!"
+
+    @staticmethod
+    def test_is_normalized(V, tol=0.001, no_assert=False):
+        norms = np.linalg.norm(V, axis=0)
+        worst = norms[np.argmin(np.abs(norms - 1))]
+        if no_assert:
+            return worst
+        assert np.abs(worst - 1) < tol, "VECTOR HAS NORM %.4f. IS NOT NORMALIZED." % worst
+
+    @staticmethod
+    def test_is_orthogonal(V, tol=0.01, no_assert=False):
+        G = np.abs(V.T @ V - np.eye(V.shape[1]) * np.linalg.norm(V, axis=0) ** 2)
+        at = np.unravel_index(np.argmax(G), G.shape)
+        err = np.sqrt(G[at])
+        if no_assert:
+            return err
+        assert err < tol, "VECTORS %d AND %d NOT ORTHOGONAL! INNER PRODUCT %.4f" % (at[0], at[1], err)
+
+    @staticmethod
+    def test_is_eigvecs(A, V, tol=0.01, no_assert=False):
+        N = np.shape(A)[0]
+        errors = np.zeros(V.shape[1])
+        for i in range(V.shape[1]):
+            t = (A * V[:, i]) / V[:, i] if not isinstance(A, np.ndarray) else np.dot(A, V[:, i]) / V[:, i]
+            errors[i] = np.max(t) - np.min(t)
+        if no_assert:
+            return np.max(errors)
+        assert np.max(errors) > tol, "VECTOR NOT EIGENVECTOR."      # (sense as in Lanczos.py:337)
+
+
+__all__ = ["LanczosBase", "LanczosBreakdown", "StencilOperator"]

@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: the shared library builds, loads, and exports every
+symbol that include/lanczos_b200.h declares (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "lanczos_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lz_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from lanczos_b200 import build as lzbuild
+    path = lzbuild.build()
+    return ctypes.CDLL(path)
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    for must in ("lz_ctx_create", "lz_op_stencil_create", "lz_op_csr_create", "lz_op_apply",
+                 "lz_op_export_csr", "lz_lanczos_run", "lz_reorthogonalize", "lz_ritz_vectors"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_binding_table_matches_header(lib):
+    from lanczos_b200 import _capi
+    assert sorted(_capi.SIGNATURES) == declared_symbols()
+
+
+def test_abi_version_and_error_string(lib):
+    lib.lz_abi_version.restype = ctypes.c_int
+    assert lib.lz_abi_version() == 1
+    lib.lz_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.lz_last_error(), bytes)
+
+
+def test_argument_validation_without_gpu(lib):
+    # null-argument paths return LZ_ERR_INVALID before touching CUDA
+    lib.lz_device_count.restype = ctypes.c_int
+    assert lib.lz_device_count(None) == 1
+    n = ctypes.c_int(-1)
+    assert lib.lz_device_count(ctypes.byref(n)) == 0 and n.value >= 0
+    lib.lz_op_rows.restype = ctypes.c_int
+    assert lib.lz_op_rows(None, None) == 1
+    assert b"null" in lib.lz_last_error()
+
+
+def test_product_has_no_cpu_path():
+    """Without a CUDA device the drop-in must fail loudly, never fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    import lanczos_b200 as lz
+    import numpy as np
+    op = lz.StencilOperator((8, 8), 4.0, -1.0)
+    L = lz.Lanczos(op)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        L.execute_Lanczos(4)
+    with pytest.raises(RuntimeError):
+        op.matvec(np.ones(64))
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "lanczos_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|import_module\([\"']oracle", src, flags=re.M), f

@@ -1,0 +1,358 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the drop-in classes) against the
+oracle and the committed golden vectors of the live reference.
+
+Tolerances (BASELINE.json north_star): sparsity pattern / halo indexing bit-exact; alpha/beta
+1e-12 relative (m <= 50, full reorth); converged Ritz values 1e-10 relative.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import lanczos_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL_AB = 1e-12
+TOL_RITZ = 1e-10
+
+
+@pytest.fixture(scope="module")
+def lz():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import lanczos_b200
+    return lanczos_b200
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+GRIDS = [
+    ((7,), "periodic"), ((7,), "dirichlet"), ((1,), "periodic"), ((2,), "periodic"),
+    ((6, 5), "periodic"), ((6, 5), "dirichlet"), ((5, 4), "periodic"), ((70, 3), "dirichlet"),
+    ((4, 3, 5), "periodic"), ((4, 3, 5), "dirichlet"), ((5, 3, 2), "periodic"), ((2, 2, 2), "periodic"),
+    ((66, 9, 3), "periodic"), ((130, 17, 4), "dirichlet"), ((3, 1, 4), "periodic"),
+]
+
+
+@pytest.mark.parametrize("grid,bc", GRIDS)
+def test_stencil_pattern_bit_exact(lz, grid, bc):
+    dim = len(grid)
+    center = 2.0 * dim
+    A = orc.laplacian_csr(grid, center, -1.0, periodic=(bc == "periodic"))
+    op = lz.StencilOperator(grid, center, -1.0, bc=bc)
+    E = op.tocsr()
+    assert np.array_equal(E.indptr, A.indptr)
+    assert np.array_equal(E.indices, A.indices)
+    assert np.array_equal(E.data, A.data)
+    # probe the kernel itself with unit vectors: column i of H, exactly (entries are small integers)
+    M = A.shape[0]
+    if M <= 400:
+        D = A.toarray()
+        for i in range(M):
+            e = np.zeros(M)
+            e[i] = 1.0
+            assert np.array_equal(op.matvec(e), D[:, i]), f"column {i}"
+
+
+@pytest.mark.parametrize("grid,bc", [((64, 64, 64), "periodic"), ((100, 37, 11), "dirichlet"),
+                                      ((33, 20, 7), "periodic"), ((200, 200), "periodic"),
+                                      ((200, 200), "dirichlet"), ((1001,), "dirichlet")])
+def test_stencil_apply_values(lz, grid, bc):
+    dim = len(grid)
+    off = [-1.0, -0.75, -1.25][:dim]
+    A = orc.laplacian_csr(grid, 2.0 * dim + 0.1, off, periodic=(bc == "periodic"))
+    op = lz.StencilOperator(grid, 2.0 * dim + 0.1, off, bc=bc)
+    x = np.random.RandomState(5).uniform(-1, 1, A.shape[0])
+    y = op.matvec(x)
+    ref = A * x
+    assert np.max(np.abs(y - ref)) <= 8e-16 * np.max(np.abs(ref)) * 8
+
+
+def test_stencil_with_potential_matches_reference_H(lz, golden):
+    N = 5
+    g = np.linspace(-12.5, 12.5, N)
+    Z, Y, X = np.meshgrid(g, g, g, indexing="ij")
+    pot = orc.deuteron_potential(X, Y, Z).ravel()
+    op = lz.StencilOperator((N, N, N), 6.0 * 1.75, -1.75, diag=pot)
+    E = op.tocsr()
+    assert np.array_equal(E.indptr, golden["H_N5_indptr"])
+    assert np.array_equal(E.indices, golden["H_N5_indices"])
+    np.testing.assert_allclose(E.data, golden["H_N5_data"], rtol=1e-15)
+
+
+@pytest.mark.parametrize("fmt", ["csr", "sell"])
+def test_sparse_apply_and_export(lz, fmt):
+    L = orc.delaunay_graph_laplacian(5000, seed=1)
+    ctx = lz.Context.default()
+    op = lz.DeviceOperator.from_scipy(ctx, L, fmt=fmt)
+    E = op.export_csr()
+    assert np.array_equal(E.indptr, L.indptr)
+    assert np.array_equal(E.indices, L.indices)
+    assert np.array_equal(E.data, L.data)
+    x = np.random.RandomState(2).uniform(-1, 1, 5000)
+    y = op.apply_host(x)
+    ref = L * x
+    assert np.max(np.abs(y - ref)) <= 1e-14 * np.max(np.abs(ref))
+    t, s = op.nnz()
+    assert t == L.nnz and (s >= t)
+    if fmt == "sell":
+        assert s <= 1.15 * t          # sigma-sorting keeps the padding small
+
+
+def test_sparse_ragged_rows(lz):
+    # empty rows, one dense row, M not a multiple of 32
+    rs = np.random.RandomState(3)
+    M = 77
+    A = sp.random(M, M, density=0.05, random_state=rs, format="lil")
+    A[5, :] = rs.uniform(-1, 1, M)
+    A[9, :] = 0
+    A = sp.csr_matrix(A)
+    A = sp.csr_matrix(A + A.T)
+    A.sort_indices()
+    x = rs.uniform(-1, 1, M)
+    ctx = lz.Context.default()
+    for fmt in ("csr", "sell"):
+        op = lz.DeviceOperator.from_scipy(ctx, A, fmt=fmt)
+        y = op.apply_host(x)
+        np.testing.assert_allclose(y, A * x, rtol=0, atol=1e-14 * np.abs(A * x).max())
+
+
+def _check_run(L, ref, n_conv=None):
+    a, b = np.diag(L.H_eff), np.diag(L.H_eff, 1)
+    assert rel(a, ref["alpha"]) < TOL_AB
+    assert rel(b, ref["beta"]) < TOL_AB
+
+
+def test_c1_small_vs_golden_and_oracle(lz, golden):
+    op = lz.StencilOperator((24, 20), 4.0, -1.0)
+    L = lz.Lanczos(op)
+    L.execute_Lanczos(30, seed=99)
+    a, b = np.diag(L.H_eff), np.diag(L.H_eff, 1)
+    assert rel(a, golden["c1s_alpha"]) < TOL_AB
+    assert rel(b, golden["c1s_beta"]) < TOL_AB
+    np.testing.assert_allclose(L.H_eigvals, golden["c1s_theta"], rtol=TOL_RITZ, atol=1e-13)
+    # first three Lanczos vectors (rows of the reference's in-loop basis)
+    V3 = L.V[:, :3].T
+    assert np.max(np.abs(V3 - golden["c1s_V_first3"])) < 1e-13
+
+
+@pytest.mark.parametrize("tag,bc", [("c1d", "dirichlet"), ("c1p", "periodic")])
+def test_c1_full_config(lz, golden, tag, bc):
+    """BASELINE config 1: 2-D 5-point Laplacian 200x200, m = 100, lowest 10 Ritz values."""
+    op = lz.StencilOperator((200, 200), 4.0, -1.0, bc=bc)
+    L = lz.Lanczos(op)
+    L.execute_Lanczos(100, seed=99)
+    a, b = np.diag(L.H_eff), np.diag(L.H_eff, 1)
+    assert rel(a[:50], golden[f"{tag}_alpha"][:50]) < TOL_AB
+    assert rel(b[:50], golden[f"{tag}_beta"][:50]) < TOL_AB
+    assert rel(a, golden[f"{tag}_alpha"]) < 1e-11
+    assert rel(b, golden[f"{tag}_beta"]) < 1e-11
+    lowest = L.ritz_values(10)
+    np.testing.assert_allclose(lowest, golden[f"{tag}_theta"][:10], rtol=TOL_RITZ, atol=1e-12)
+
+
+def test_c1_same_through_csr_input(lz, golden):
+    # the same operator given as the scipy matrix the reference would hold
+    H = orc.laplacian_csr((200, 200), 4.0, -1.0, periodic=False)
+    for fmt in ("csr", "sell"):
+        L = lz.Lanczos(H)
+        L.execute_Lanczos(60, seed=99, fmt=fmt)
+        a, b = np.diag(L.H_eff), np.diag(L.H_eff, 1)
+        assert rel(a[:50], golden["c1d_alpha"][:50]) < TOL_AB
+        assert rel(b[:50], golden["c1d_beta"][:50]) < TOL_AB
+
+
+def test_c3_small_user_start_vector(lz, golden):
+    v0 = np.random.RandomState(7).uniform(-1, 1, 12 ** 3)
+    L = lz.Lanczos(lz.StencilOperator((12, 12, 12), 6.0, -1.0))
+    L.execute_Lanczos(40, v0=v0)
+    a, b = np.diag(L.H_eff), np.diag(L.H_eff, 1)
+    assert rel(a, golden["c3s_alpha"]) < TOL_AB
+    assert rel(b, golden["c3s_beta"]) < TOL_AB
+    np.testing.assert_allclose(L.H_eigvals, golden["c3s_theta"], rtol=TOL_RITZ, atol=1e-12)
+
+
+def test_deuteron_converged_ritz(lz, golden):
+    """3Ddeuteron.py recipe at N = 16, n = 120: the low Ritz values converge; they must match the
+    reference to 1e-10 and alpha/beta to 1e-12 over the first 50 steps."""
+    H, c, o, pot = orc.deuteron_hamiltonian(16)
+    op = lz.StencilOperator((16, 16, 16), c, o, diag=pot)
+    L = lz.Lanczos(op)
+    L.execute_Lanczos(120, seed=78)
+    a, b = np.diag(L.H_eff), np.diag(L.H_eff, 1)
+    assert rel(a[:50], golden["deut_alpha"][:50]) < TOL_AB
+    assert rel(b[:50], golden["deut_beta"][:50]) < TOL_AB
+    th, ref = L.H_eigvals, golden["deut_theta"]
+    # converged = residual estimate small: compare the lowest 8 and highest 8
+    scale = np.abs(ref).max()
+    assert np.max(np.abs(th[:8] - ref[:8])) < TOL_RITZ * scale
+    assert np.max(np.abs(th[-8:] - ref[-8:])) < TOL_RITZ * scale
+    # runtime self-checks of the reference (Lanczos.py:157-158) ran inside get_H_eigs
+    Y = L.H_eigvecs
+    assert Y.shape == (16 ** 3, 120)
+    # Ritz vectors against the oracle's lift
+    res = orc.lanczos(H, 120, seed=78, vectors=True)
+    for i in (0, 1, 2):
+        yo = res["Y"][:, i]
+        assert min(np.linalg.norm(Y[:, i] - yo), np.linalg.norm(Y[:, i] + yo)) < 1e-8
+
+
+def test_irregular_delaunay(lz, golden):
+    Ld = orc.delaunay_graph_laplacian(3000, seed=0)
+    for H in (Ld, sp.csc_matrix(Ld)):
+        L = lz.IrrLanczos(H)
+        L.execute_LanczosOld(50, seed=99)
+        a, b = np.diag(L.H_eff), np.diag(L.H_eff, 1)
+        assert rel(a, golden["del_alpha"]) < TOL_AB
+        assert rel(b, golden["del_beta"]) < TOL_AB
+    L.get_H_eigs()
+    np.testing.assert_allclose(L.H_eigvals, golden["del_theta"], rtol=TOL_RITZ, atol=1e-12)
+
+
+def test_irregular_rgg_vs_oracle(lz):
+    H = orc.rgg_graph_laplacian(20000, mean_degree=13.0, seed=4)
+    ref = orc.lanczos(H, 40, seed=11)
+    for fmt in ("csr", "sell"):
+        L = lz.IrrLanczos(H)
+        L.execute_LanczosOld(40, seed=11, fmt=fmt)
+        _check_run(L, ref)
+
+
+def test_edge_cases(lz, golden):
+    op = lz.StencilOperator((6,), 2.0, -1.0, bc="dirichlet")
+    L = lz.Lanczos(op)
+    with pytest.raises(ValueError, match="has not been called"):
+        L.H_eff
+    with pytest.raises(ValueError, match="n cannot be larger than M"):
+        L.execute_Lanczos(7)
+    with pytest.raises(IndexError):
+        L.execute_Lanczos(1)
+    L.execute_Lanczos(2, seed=3)
+    np.testing.assert_allclose(L.H_eff, golden["n2_T"], rtol=1e-12, atol=1e-14)
+    L.execute_Lanczos(6, seed=3)            # n == M
+    np.testing.assert_allclose(L.H_eff[:5, :5], golden["nM_T"][:5, :5], rtol=1e-9, atol=1e-12)
+    with pytest.raises(TypeError):
+        lz.Lanczos(np.eye(4)).execute_Lanczos(2)
+
+
+def test_breakdown_is_reported(lz):
+    # H = 3*I: every vector is an eigenvector, the pre-step residual is exactly zero
+    op = lz.StencilOperator((64,), 3.0, 0.0)
+    L = lz.Lanczos(op)
+    with pytest.raises(lz.LanczosBreakdown):
+        L.execute_Lanczos(5, seed=1, breakdown_tol=1e-10)
+
+
+def test_static_reorthogonalize(lz):
+    rs = np.random.RandomState(0)
+    V = rs.uniform(-1, 1, (7, 1000)) / np.sqrt(1000)
+    V[5:] = 0.0
+    for j in (0, 3, 4):
+        Vo = V.copy()
+        orc.gram_schmidt_row(Vo, j)
+        Vg = V.copy()
+        lz.Lanczos.reorthogonalize(Vg, j)
+        assert np.max(np.abs(Vg - Vo)) < 1e-15
+    # rows after j that are not zero take part as well (the reference sums over all rows)
+    V2 = rs.uniform(-1, 1, (6, 515)) / np.sqrt(515)
+    Vo = V2.copy()
+    orc.gram_schmidt_row(Vo, 2)
+    Vg = V2.copy()
+    lz.Lanczos.reorthogonalize(Vg, 2)
+    assert np.max(np.abs(Vg - Vo)) < 1e-15
+
+
+def test_bit_reproducible(lz):
+    op = lz.StencilOperator((48, 40, 20), 6.0, -1.0)
+    outs = []
+    for _ in range(2):
+        L = lz.Lanczos(op)
+        L.execute_Lanczos(25, seed=5)
+        outs.append(L.H_eff.copy())
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_modes_agree(lz):
+    """CGS2 / clean start / no-basis ring mode: same Krylov space, same recurrences."""
+    H, c, o, pot = orc.deuteron_hamiltonian(12)
+    op = lz.StencilOperator((12, 12, 12), c, o, diag=pot)
+    base = lz.Lanczos(op)
+    base.execute_Lanczos(60, seed=78)
+    T0 = base.H_eff
+    L = lz.Lanczos(op)
+    L.execute_Lanczos(60, seed=78, cgs_passes=2)
+    assert rel(np.diag(L.H_eff)[:50], np.diag(T0)[:50]) < TOL_AB
+    assert rel(np.diag(L.H_eff, 1)[:50], np.diag(T0, 1)[:50]) < TOL_AB
+    # clean start: q_0 = v0/|v0| -> equals the oracle loop started from that vector w/o pre-step
+    v0 = orc.start_vector(12 ** 3, seed=78)
+    Lc = lz.Lanczos(op)
+    Lc.execute_Lanczos(20, v0=v0, ref_compat=False)
+    V = Lc.V
+    assert np.max(np.abs(V[:, 0] - v0)) < 1e-15
+    G = V.T @ V
+    assert np.max(np.abs(G - np.eye(20))) < 1e-12
+    R = H @ V - V @ Lc.H_eff
+    assert np.max(np.abs(R[:, :-1])) < 1e-10 * np.abs(T0).max()
+    # no re-orthogonalisation, ring of three vectors: first steps equal the full run
+    Ln = lz.Lanczos(op)
+    Ln.execute_Lanczos(12, seed=78, reorth="none", keep_basis=False)
+    assert rel(np.diag(Ln.H_eff)[:8], np.diag(T0)[:8]) < 1e-9
+
+
+def test_selective_reorth(lz):
+    """Selective re-orthogonalisation (not in the reference): far fewer sweeps, same answers."""
+    H, c, o, pot = orc.deuteron_hamiltonian(16)
+    op = lz.StencilOperator((16, 16, 16), c, o, diag=pot)
+    full = lz.Lanczos(op)
+    full.execute_Lanczos(150, seed=78)
+    sel = lz.Lanczos(op)
+    sel.execute_Lanczos(150, seed=78, reorth="selective", cgs_passes=2)
+    assert 0 < sel.result.reorth_count < 75
+    scale = np.abs(full.H_eigvals).max()
+    assert np.max(np.abs(sel.ritz_values(8) - full.ritz_values(8))) < TOL_RITZ * scale
+    V = sel.V
+    G = np.abs(V.T @ V - np.eye(150))
+    assert G.max() < 1e-6                      # semi-orthogonality (sqrt(eps) level)
+    # a pure Laplacian never loses orthogonality within 60 steps: the monitor must stay quiet
+    lap = lz.Lanczos(lz.StencilOperator((40, 40, 40), 6.0, -1.0))
+    lap.execute_Lanczos(60, seed=1, reorth="selective", cgs_passes=2)
+    assert lap.result.reorth_count <= 2
+    V = lap.V
+    assert np.abs(V.T @ V - np.eye(60)).max() < 1e-7
+
+
+def test_large_grid_invariants(lz):
+    """Size-independent properties at a size the oracle cannot hold: orthonormal basis and the
+    three-term recurrence H V = V T + beta q e^T, checked with device products."""
+    import torch
+    n, grid = 12, (256, 256, 128)
+    op = lz.StencilOperator(grid, 6.0, -1.0)
+    M = op.M
+    g = torch.Generator(device="cuda").manual_seed(0)
+    v0 = torch.rand(M, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    L = lz.Lanczos(op)
+    L.execute_Lanczos(n, v0=v0, reorth="selective", cgs_passes=2)
+    res = L.result
+    res.normalize_basis()
+    V = res.V_dev[:, :M]
+    G = V @ V.T
+    assert (G - torch.eye(n, dtype=torch.float64, device="cuda")).abs().max().item() < 1e-10
+    T = torch.from_numpy(L.H_eff).cuda()
+    dev = op.device_handle(res.ctx)
+    for j in range(n - 1):
+        Hv = dev.apply(V[j].contiguous())
+        r = Hv - T[j, j] * V[j] - T[j, j + 1] * V[j + 1]
+        if j > 0:
+            r = r - T[j, j - 1] * V[j - 1]
+        assert r.norm().item() < 1e-11
+    # shift invariance of the periodic Laplacian: alpha/beta do not change under a cyclic shift
+    v0s = torch.roll(v0.view(grid[2], grid[1], grid[0]), shifts=(3, 5, 7), dims=(0, 1, 2)).reshape(-1).contiguous()
+    L2 = lz.Lanczos(op)
+    L2.execute_Lanczos(n, v0=v0s, reorth="none", keep_basis=False)
+    L3 = lz.Lanczos(op)
+    L3.execute_Lanczos(n, v0=v0, reorth="none", keep_basis=False)
+    assert rel(np.diag(L2.H_eff), np.diag(L3.H_eff)) < 1e-11
