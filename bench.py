@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py - Lanczos steps/s and achieved HBM GB/s on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1] [--impl reference]
+
+One "step" = one Lanczos step (operator apply + alpha, three-term update + beta, and the
+re-orthogonalisation sweeps the configuration asks for).  The default workload is BASELINE
+config 3 - the 512^3 periodic 7-point Laplacian (134 M unknowns, fp64, selective
+re-orthogonalisation) on which the north-star roofline target is stated; with N > 1 GPUs the
+grid is weak-scaled to 512 x 512 x (512 N), row-sharded in z-slabs (one process per GPU).
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with the start vector resident in HBM;
+`e2e` goes through the drop-in class with a pinned HOST start vector and host results.
+`--impl reference` times the oracle port of the reference's CPU path on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import builtins
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "c3": dict(desc="3D 7-point periodic Laplacian 512x512x(512*gpus) fp64, selective reorth (CGS2 when triggered)",
+               grid=(512, 512, 512), steps=100, reorth="selective", cgs_passes=2),
+    "c3full": dict(desc="3D 7-point periodic Laplacian 512^3 fp64, full reorth (reference form)",
+                   grid=(512, 512, 512), steps=60, reorth="full", cgs_passes=1),
+    "c2": dict(desc="graph Laplacian of a 2D Delaunay mesh, 1M vertices, SELL-32-1024, full reorth",
+               npts=1_000_000, steps=200, reorth="full", cgs_passes=1),
+    "c1": dict(desc="2D 5-point Dirichlet Laplacian 200x200 fp64, full reorth",
+               grid=(200, 200), steps=100, reorth="full", cgs_passes=1),
+}
+METRIC = "lanczos_steps_per_sec"
+UNIT = "steps/s"
+
+
+def quiet_banners():
+    """The drop-in classes print the reference's '+++' banners; keep stdout to the JSON line."""
+    real = builtins.print
+
+    def p(*a, **k):
+        if a and isinstance(a[0], str) and a[0].startswith("+++"):
+            return
+        real(*a, **k)
+    builtins.print = p
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons, pw = [], [], set(), []
+        for t, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clk, cmax = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            inside = (t0 - 0.05) <= t <= (t1 + 0.15)
+            if inside:
+                sm.append(clk)
+                try:
+                    pw.append(float(f[2]))
+                except ValueError:
+                    pass
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            mx.append(cmax)
+        if not sm:   # region shorter than the sampling period: use every sample
+            for t, line in self.lines:
+                try:
+                    sm.append(float(line.split(",")[0]))
+                except ValueError:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "power_w_max": float(max(pw)) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------- CPU baseline
+def cpu_reference_leg(workload: str, budget_s: float = 20.0):
+    """The reference's CPU algorithm (oracle port: same NumPy/SciPy ops as Lanczos.py:100-119 and
+    :247-249) on a bounded sample of the workload, all host threads NumPy/OpenBLAS will use."""
+    from oracle import lanczos_oracle as orc
+    wl = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    if "grid" in wl and len(wl["grid"]) == 3:
+        full_M = int(np.prod(wl["grid"]))
+        side, n = 96, 16
+        H = orc.laplacian_csr((side, side, side), 6.0, -1.0, periodic=True)
+        v0 = np.random.RandomState(99).uniform(-1, 1, side ** 3)
+        t = orc.timed_steps(H, n, v0, reorth=True)
+        # more steps if the box is fast, to land near the budget
+        if t < budget_s / 4:
+            n = 32
+            t = orc.timed_steps(H, n, v0, reorth=True)
+        sample_rate = n / t
+        value = sample_rate * (side ** 3) / full_M           # linear extrapolation in M
+        t2 = orc.timed_steps(H, n, v0, reorth=False)
+        step_only = (n / t2) * (side ** 3) / full_M
+        sample = (f"{side}^3 periodic 7-pt Laplacian, n={n}, full reorth as the reference always does "
+                  f"({sample_rate:.2f} steps/s measured), extrapolated linearly in M to {full_M} unknowns; "
+                  f"its reorth cost also grows with n (all n rows every step), so n={wl['steps']} would be slower still; "
+                  f"step-only (no reorth) extrapolated: {step_only:.3f} steps/s")
+        return dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample,
+                    step_only_value=step_only, numpy=np.__version__)
+    if workload == "c2":
+        npts, n = 100_000, 40
+        H = orc.delaunay_graph_laplacian(npts, seed=0)
+        v0 = np.random.RandomState(99).uniform(-1, 1, npts)
+        t = orc.timed_steps(H, n, v0, reorth=True)
+        value = (n / t) * npts / wl["npts"]
+        return dict(value=value, unit=UNIT, cores=cores, kind="port",
+                    sample=f"Delaunay {npts} vertices, n={n}, full reorth ({n/t:.2f} steps/s), extrapolated linearly in M to {wl['npts']}")
+    grid, n = wl["grid"], wl["steps"]
+    H = orc.laplacian_csr(grid, 4.0, -1.0, periodic=False)
+    v0 = np.random.RandomState(99).uniform(-1, 1, int(np.prod(grid)))
+    t = orc.timed_steps(H, n, v0, reorth=True)
+    return dict(value=n / t, unit=UNIT, cores=cores, kind="port", sample=f"the full config: {grid}, n={n}, full reorth")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 1))):      # one bounded sample per run (each is ~10-30 s)
+        base = cpu_reference_leg(args.workload)
+        vals.append(base["value"])
+    v = float(np.median(vals))
+    base["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v if v > 0 else None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": f"{args.workload}: {wl['desc']}"},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def build_operator(lz, workload, world, rank):
+    wl = WORKLOADS[workload]
+    if "grid" in wl:
+        grid = tuple(wl["grid"])
+        dim = len(grid)
+        if dim == 3 and world > 1:
+            grid = (grid[0], grid[1], grid[2] * world)       # weak scaling in z
+        return lz.StencilOperator(grid, 2.0 * dim, -1.0, bc="periodic" if dim == 3 else "dirichlet"), grid
+    from oracle import lanczos_oracle as orc             # input generator only (test infrastructure)
+    H = orc.delaunay_graph_laplacian(wl["npts"], seed=0)
+    return H, (wl["npts"],)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.steps is None:
+        args.steps = wl["steps"]
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    quiet_banners()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import lanczos_b200 as lz
+
+    K, W = int(args.steps), max(3, int(args.warmup))
+    H, grid = build_operator(lz, args.workload, world, rank)
+    M_total = int(np.prod(grid))
+    opts = dict(reorth=wl["reorth"], cgs_passes=wl["cgs_passes"], ref_compat=True)
+
+    if world > 1:
+        from lanczos_b200 import team as lzteam
+        solver = lzteam.TeamLanczos(H, rank=rank, world=world)
+        M_local = solver.M_local
+    else:
+        solver = lz.Lanczos(H) if "grid" in wl else lz.IrrLanczos(H)
+        M_local = M_total
+    execute = solver.execute_Lanczos if hasattr(solver, "execute_Lanczos") and "grid" in wl else solver.execute_LanczosOld
+
+    # start vector: device-generated for the throughput run, pinned host copy for e2e
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    v0_dev = torch.rand(M_local, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    v0_host = torch.empty(M_local, dtype=torch.float64).pin_memory()
+    v0_host.copy_(v0_dev)
+    torch.cuda.synchronize()
+
+    # basis memory: K rows of 8*M bytes must fit; otherwise split the K steps into several solves
+    free_b, _ = torch.cuda.mem_get_info()
+    row_b = 8 * ((M_local + 63) // 64 * 64)
+    max_rows = max(2, int((free_b * 0.85 - 5 * row_b) // row_b))
+    if wl["reorth"] == "none":
+        max_rows = K
+    chunks = []
+    left = K
+    while left > 0:
+        c = min(left, max_rows)
+        if left - c == 1:          # a 1-step solve is not allowed in ref_compat (n >= 2)
+            c -= 1
+        chunks.append(c)
+        left -= c
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def solve(n, v0, profile=False):
+        execute(n, v0=v0, profile=profile, **opts)
+        return solver.result
+
+    # ---- warm-up: W untimed steps (also sizes the workspace arena and the allocator cache) ----
+    solve(max(W, 2), v0_dev)
+    if len(chunks) == 1:
+        solve(chunks[0], v0_dev)           # allocator + arena warm at the timed size
+    barrier()
+
+    # ---- timed region A: device-resident input, exactly K steps -------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    launches = 0
+    reorths = 0
+    for c in chunks:
+        res = solve(c, v0_dev)
+        launches += res.launches
+        reorths += res.reorth_count
+        del res                       # the result owns the ~100 GB basis; the next solve reuses it
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms_dev = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_dev], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev = float(t.item())
+
+    # ---- region A2: the same K steps again with a CUDA-event pair around every bandwidth kernel
+    # (per-kernel roofline).  Kept out of region A because the event records break up
+    # back-to-back launches and cost several percent of step time.
+    kern = {"apply": [0.0, 0], "update": [0.0, 0], "dots": [0.0, 0], "gs_update": [0.0, 0]}
+    for c in chunks:
+        res = solve(c, v0_dev, profile=True)
+        for k, (ms, cnt) in res.kernel_ms.items():
+            kern[k][0] += ms
+            kern[k][1] += cnt
+        del res
+    barrier()
+    theta = solver.ritz_values(10)
+
+    # ---- timed region B: end to end through the drop-in class, host buffers --------------------
+    barrier()
+    e0 = time.perf_counter()
+    for c in chunks:
+        solve(c, v0_host)
+        T = solver.H_eff                   # host ndarray (alpha/beta came back D2H inside the call)
+        _ = solver.ritz_values(10)
+    torch.cuda.synchronize()
+    e_wall = time.perf_counter() - e0
+    if world > 1:
+        t = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_wall = float(t.item())
+    time.sleep(0.15)
+    sampler.stop()
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    N = M_local
+    is_stencil = "grid" in wl
+    if is_stencil:
+        apply_bytes = 16.0 * N                      # read v_j, write w  (alpha fused)
+    else:
+        nnz_true, _ = solver._device_op.nnz()
+        apply_bytes = 12.0 * nnz_true + 16.0 * N
+    per_kernel = {}
+    alg = {"apply": apply_bytes, "update": 32.0 * N}
+    for k in ("apply", "update"):
+        ms, cnt = kern[k]
+        if cnt:
+            per_kernel[k] = {"launches": cnt, "avg_ms": ms / cnt, "alg_bytes": alg[k],
+                             "achieved_gbs": alg[k] / (ms / cnt) / 1e6}
+    # Gram-Schmidt kernels: bytes depend on the row count of each launch; report the aggregate
+    gs_ms = kern["dots"][0] + kern["gs_update"][0]
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"] * per_kernel[k]["launches"]) if per_kernel else None
+    names = {"apply": "stencil_apply_dot_kernel" if is_stencil else "spmv_sell_dot_kernel",
+             "update": "update_norm_kernel"}
+    roofline = None
+    if dom:
+        pk = per_kernel[dom]
+        roofline = {"kernel": names[dom], "bound": "hbm", "achieved": pk["achieved_gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": pk["achieved_gbs"] / peak, "traffic": None,
+                    "peak_source": peak_src, "alg_bytes_per_launch": pk["alg_bytes"],
+                    "avg_launch_ms": pk["avg_ms"], "launches": pk["launches"],
+                    "timing": "CUDA-event pair around every launch of a second K-step solve on the launching stream",
+                    "frac_of_8TBs_nominal": pk["achieved_gbs"] / 8000.0}
+    step_bytes = apply_bytes + 32.0 * N
+    ms_per_step = ms_dev / K
+    value = K / (ms_dev / 1e3)
+    fused = {"alg_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / ms_per_step / 1e6 if reorths == 0 else None,
+             "frac_of_measured_peak": step_bytes / ms_per_step / 1e6 / peak if reorths == 0 else None,
+             "frac_of_8TBs_nominal": step_bytes / ms_per_step / 1e6 / 8000.0 if reorths == 0 else None,
+             "note": "48*N B/step two-pass fused step (SURVEY 8d); null when Gram-Schmidt sweeps ran"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "grid": list(grid), "unknowns": M_total,
+                   "unknowns_per_gpu": M_local, "lanczos_m": chunks, "reorth": wl["reorth"],
+                   "cgs_passes": wl["cgs_passes"], "l2": "inputs larger than L2 (each vector %.2f GB)" % (8 * M_local / 1e9),
+                   "sharding": "z-slabs, one process per GPU" if world > 1 else "single GPU"},
+        "e2e": {"value": K / e_wall, "unit": UNIT, "h2d_bytes_per_step": 8.0 * M_local * len(chunks) / K,
+                "d2h_bytes_per_step": (sum(3 * (8 * (c + 2) + 512) + 32 for c in chunks)) / K,
+                "wall_s": e_wall},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": per_kernel,
+        "gram_schmidt_ms": gs_ms,
+        "reorth_steps": reorths,
+        "fused_step": fused,
+        "ritz_lowest": [float(x) for x in theta[:4]],
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_reference_leg(args.workload)
+            except Exception as e:      # the baseline is a report, it must not sink the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"failed: {e!r}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

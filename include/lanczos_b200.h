@@ -84,7 +84,7 @@ int lz_op_stencil_create(lz_ctx* ctx, int dim, const int64_t* shape, int bc,
 /* lz_op_csr_create: general sparse operator from host CSR arrays (scipy layout:
  * indptr[M+1], indices[nnz], data[nnz]).  Replaces cupyx.scipy.sparse.csr_matrix(H)
  * at Lanczos.py:88 / csc_matrix(H) at IrrLanczos.py:205.  The arrays are copied
- * (and, for LZ_FMT_SELL, converted on the device); the caller keeps its own.
+ * (and, for LZ_FMT_SELL, converted by the library); the caller keeps its own.
  * sigma = sorting window in rows (multiple of 32; 0 -> library default). */
 int lz_op_csr_create(lz_ctx* ctx, int64_t M, int64_t nnz, const int32_t* indptr_host,
                      const int32_t* indices_host, const double* data_host,
@@ -112,7 +112,8 @@ typedef struct lz_run_opts {
     int32_t ref_compat;    /* 1: reproduce the reference loop exactly (pre-step that
                               discards v0, (2-|v|^2) form of the sweep, beta taken
                               before the sweep); 0: v0/|v0| is the first basis vector */
-    int32_t reserved;
+    int32_t profile;       /* 1: bracket the bandwidth kernels with CUDA events and report
+                              their summed device times in lz_run_info (bench.py roofline) */
     double  breakdown_tol; /* stop when beta <= breakdown_tol * |alpha_0| (0: only 0/NaN) */
     double  select_tol;    /* selective: orthogonality level that triggers (0 -> sqrt(eps)) */
 } lz_run_opts;
@@ -121,9 +122,15 @@ typedef struct lz_run_info {
     int32_t steps_done;    /* Lanczos steps completed (== n unless breakdown)        */
     int32_t reorth_count;  /* steps in which the Gram-Schmidt sweeps ran             */
     int32_t launches;      /* kernels launched by this call                          */
-    int32_t reserved;
+    int32_t apply_launches;   /* profile == 1: launches and summed device ms of ...  */
+    int32_t update_launches;
+    int32_t dots_launches;
+    int32_t gsupd_launches;
     float   gpu_ms;        /* device time of the loop (CUDA events on the stream)    */
-    float   reserved2;
+    float   apply_ms;      /* ... K1/K2 operator apply + alpha dot                   */
+    float   update_ms;     /* ... K3 three-term update + norm                        */
+    float   dots_ms;       /* ... K4a Gram-Schmidt dots                              */
+    float   gsupd_ms;      /* ... K4b Gram-Schmidt update                            */
 } lz_run_info;
 
 /* Runs n steps from v0_dev (M doubles).  Outputs: alpha_host[n], beta_host[n-1]
@@ -144,13 +151,13 @@ int lz_basis_normalize(lz_ctx* ctx, double* V_dev, int64_t ldv, int32_t n, int64
 
 /* One Gram-Schmidt sweep of row j of V against all rows, in place: the staticmethod
  * Lanczos.reorthogonalize(V, j) (Lanczos.py:233-251, CPU form :247-249;
- * IrrLanczos.py:448-466).  V is (n x ldv) row-major on the device.  Enqueues only. */
+ * IrrLanczos.py:448-466).  V is (n x ldv) row-major on the device.  Synchronises. */
 int lz_reorthogonalize(lz_ctx* ctx, double* V_dev, int64_t ldv, int32_t n, int64_t M, int32_t j);
 
 /* Ritz vectors: Y[c,:] = sum_j S[j,c] * row_scale[j] * V[j,:], c < k.  The lift loop of
  * get_H_eigs (Lanczos.py:154-156).  S_host is n x k column-major (column c = c-th
  * eigenvector of H_eff), row_scale_host nullable (all ones), Y_dev is k rows of ldy.
- * Enqueues only (S is copied before return). */
+ * Synchronises. */
 int lz_ritz_vectors(lz_ctx* ctx, const double* V_dev, int64_t ldv, int32_t n, int64_t M,
                     const double* row_scale_host, const double* S_host, int32_t k,
                     double* Y_dev, int64_t ldy);

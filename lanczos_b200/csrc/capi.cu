@@ -111,6 +111,8 @@ int lz_ctx_destroy(lz_ctx* c) {
     cudaSetDevice(c->device);
     if (c->partials) cudaFree(c->partials);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->arena) cudaFree(c->arena);
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     delete c;

@@ -1,5 +1,6 @@
 // Internal data structures shared by the translation units of liblanczos_b200.
 #pragma once
+#include <vector>
 #include "common.cuh"
 
 enum lz_op_kind { LZ_OP_STENCIL = 0, LZ_OP_CSR = 1, LZ_OP_SELL = 2 };
@@ -11,6 +12,9 @@ struct lz_ctx {
     double* partials = nullptr;    // 2 * kMaxPartials doubles: CTA partial sums of streaming kernels
     double* scratch = nullptr;     // 64 doubles of device scratch (lz_dot, lz_reorthogonalize, ...)
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    void* arena = nullptr;         // grow-only device workspace of lz_lanczos_run
+    size_t arena_bytes = 0;
+    std::vector<cudaEvent_t> event_pool;   // profile mode only
 };
 
 // Geometry of a structured-grid operator as the kernels see it.  `nz` is the number of

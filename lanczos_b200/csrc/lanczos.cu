@@ -168,26 +168,65 @@ omega_kernel(RunState st, int j, double* om_cur, double* om_prev, double delta, 
     }
 }
 
-static int alloc_state(RunState* st, int n, std::vector<void*>& owned) {
-    auto alloc = [&](void** p, size_t bytes) -> int {
-        LZ_CUDA(cudaMalloc(p, bytes));
-        owned.push_back(*p);
-        return LZ_OK;
-    };
-    const size_t nd = (size_t)n + 2;
-    LZ_CHECK(alloc((void**)&st->alpha, nd * 8));
-    LZ_CHECK(alloc((void**)&st->beta, nd * 8));
-    LZ_CHECK(alloc((void**)&st->scale, nd * 8));
-    LZ_CHECK(alloc((void**)&st->coef, nd * 8));
-    LZ_CHECK(alloc((void**)&st->cself, 8));
-    LZ_CHECK(alloc((void**)&st->v0scale, 8));
-    LZ_CHECK(alloc((void**)&st->alpha_pre, 8));
-    LZ_CHECK(alloc((void**)&st->omega_a, nd * 8));
-    LZ_CHECK(alloc((void**)&st->omega_b, nd * 8));
-    LZ_CHECK(alloc((void**)&st->anorm, 8));
-    LZ_CHECK(alloc((void**)&st->flags, 8 * sizeof(int)));
+// Carve the run's device workspace out of the context's grow-only arena (no cudaMalloc /
+// cudaFree - and hence no implicit device synchronisation - in steady state).
+struct Carver {
+    char* base;
+    size_t off = 0;
+    template <typename T> T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + off);
+        off += (count * sizeof(T) + 511) & ~(size_t)511;
+        return p;
+    }
+};
+
+int arena_reserve(lz_ctx* ctx, size_t bytes) {
+    if (ctx->arena_bytes >= bytes) return LZ_OK;
+    if (ctx->arena) { LZ_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
+    LZ_CUDA(cudaMalloc(&ctx->arena, bytes));
+    ctx->arena_bytes = bytes;
     return LZ_OK;
 }
+
+// CUDA-event pairs around selected launches, for the per-kernel roofline of bench.py.  Events
+// come from a pool owned by the context (created once, reused by every run).
+struct KernelTimer {
+    lz_ctx* ctx = nullptr;
+    std::vector<int> kind;
+    size_t used = 0;
+    bool on = false;
+    cudaEvent_t next() {
+        if (used == ctx->event_pool.size()) {
+            cudaEvent_t e = nullptr;
+            cudaEventCreate(&e);
+            ctx->event_pool.push_back(e);
+        }
+        return ctx->event_pool[used++];
+    }
+    void begin(int k) {
+        if (!on) return;
+        cudaEventRecord(next(), ctx->stream);
+        kind.push_back(k);
+    }
+    void end() {
+        if (!on) return;
+        cudaEventRecord(next(), ctx->stream);
+        kind.push_back(-1);
+    }
+    void collect(float* ms_by_kind, int* count_by_kind, int nk) {
+        for (int k = 0; k < nk; ++k) { ms_by_kind[k] = 0.f; count_by_kind[k] = 0; }
+        for (size_t i = 0; i + 1 < used; i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->event_pool[i], ctx->event_pool[i + 1]) == cudaSuccess &&
+                kind[i] >= 0 && kind[i] < nk) {
+                ms_by_kind[kind[i]] += ms;
+                count_by_kind[kind[i]] += 1;
+            }
+        }
+        used = 0;
+        kind.clear();
+    }
+};
 
 }  // namespace lz
 
@@ -212,49 +251,43 @@ extern "C" int lz_lanczos_run(lz_ctx* ctx, lz_op* op, const double* v0_dev, int3
     LZ_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
 
-    std::vector<void*> owned;
-    struct Cleanup {
-        std::vector<void*>& v;
-        ~Cleanup() { for (void* p : v) cudaFree(p); }
-    } cleanup{owned};
-
-    RunState st{};
-    LZ_CHECK(alloc_state(&st, n, owned));
+    // ---- workspace ---------------------------------------------------------------------------
     const size_t nd = (size_t)n + 2;
-    LZ_CUDA(cudaMemsetAsync(st.alpha, 0, nd * 8, s));
-    LZ_CUDA(cudaMemsetAsync(st.beta, 0, nd * 8, s));
-    LZ_CUDA(cudaMemsetAsync(st.scale, 0, nd * 8, s));
-    LZ_CUDA(cudaMemsetAsync(st.omega_a, 0, nd * 8, s));
-    LZ_CUDA(cudaMemsetAsync(st.omega_b, 0, nd * 8, s));
+    const int64_t ld_int = (M + 63) & ~(int64_t)63;
+    const size_t vec_bytes = (size_t)ld_int * 8 + 512;
+    size_t need = 16 * 512 + 6 * (nd * 8 + 512) + vec_bytes;
+    if (!V_dev) need += 3 * vec_bytes;
+    if (reorth != LZ_REORTH_NONE) need += (size_t)(n + 1) * kMaxPartials * 8 + 512;
+    LZ_CHECK(arena_reserve(ctx, need));
+    Carver cv{(char*)ctx->arena};
+    RunState st{};
+    st.alpha = cv.take<double>(nd);
+    st.beta = cv.take<double>(nd);
+    st.scale = cv.take<double>(nd);
+    st.coef = cv.take<double>(nd);
+    st.omega_a = cv.take<double>(nd);
+    st.omega_b = cv.take<double>(nd);
+    st.cself = cv.take<double>(1);
+    st.v0scale = cv.take<double>(1);
+    st.alpha_pre = cv.take<double>(1);
+    st.anorm = cv.take<double>(1);
+    st.flags = cv.take<int>(8);
+    double* w = cv.take<double>((size_t)ld_int);
+    double* ring = V_dev ? nullptr : cv.take<double>((size_t)ld_int * 3);
+    double* gs_part = (reorth != LZ_REORTH_NONE) ? cv.take<double>((size_t)(n + 1) * kMaxPartials) : nullptr;
+
+    // alpha .. omega_b are contiguous 512-byte-rounded blocks: one memset clears them all
+    LZ_CUDA(cudaMemsetAsync(st.alpha, 0, (char*)st.cself - (char*)st.alpha, s));
     LZ_CUDA(cudaMemsetAsync(st.anorm, 0, 8, s));
     {
         const double one = 1.0;                       // omega_{0,0} = 1
         LZ_CUDA(cudaMemcpyAsync(st.omega_a, &one, 8, cudaMemcpyHostToDevice, s));
-    }
-    {
         const int h_flags[8] = {-1, reorth == LZ_REORTH_FULL ? 1 : 0, 0, 0, 0, 0, 0, 0};
         LZ_CUDA(cudaMemcpyAsync(st.flags, h_flags, sizeof(h_flags), cudaMemcpyHostToDevice, s));
-    }
-
-    // work vectors: w, and (without a caller basis) a ring of three rows
-    double* w = nullptr;
-    const int64_t ld_int = (M + 63) & ~(int64_t)63;
-    LZ_CUDA(cudaMalloc((void**)&w, (size_t)ld_int * 8));
-    owned.push_back(w);
-    double* ring = nullptr;
-    if (!V_dev) {
-        LZ_CUDA(cudaMalloc((void**)&ring, (size_t)ld_int * 8 * 3));
-        owned.push_back(ring);
     }
     auto row = [&](int j) -> double* {
         return V_dev ? V_dev + (int64_t)j * ldv : ring + (int64_t)(j % 3) * ld_int;
     };
-    // Gram-Schmidt partials: (n+1) rows x ncg
-    double* gs_part = nullptr;
-    if (reorth != LZ_REORTH_NONE) {
-        LZ_CUDA(cudaMalloc((void**)&gs_part, (size_t)(n + 1) * kMaxPartials * 8));
-        owned.push_back(gs_part);
-    }
     double* part = ctx->partials;
     int launches = 0, np = 0;
     const int ref = opts->ref_compat ? 1 : 0;
@@ -262,6 +295,17 @@ extern "C" int lz_lanczos_run(lz_ctx* ctx, lz_op* op, const double* v0_dev, int3
     const double delta = opts->select_tol > 0.0 ? opts->select_tol : sqrt(eps);
     const double eps1 = eps * 1.5;      // noise floor of the omega recurrence
     const double psi = eps * sqrt((double)M);
+    KernelTimer kt;
+    kt.ctx = ctx;
+    kt.on = (opts->profile != 0);
+    if (kt.on) {   // create the pool outside the timed loop
+        while (ctx->event_pool.size() < (size_t)(2 * (2 + 2 * passes) * n + 8)) {
+            cudaEvent_t e = nullptr;
+            LZ_CUDA(cudaEventCreate(&e));
+            ctx->event_pool.push_back(e);
+        }
+    }
+    enum { K_APPLY = 0, K_UPDATE = 1, K_DOTS = 2, K_GSUPD = 3, K_NKINDS = 4 };
 
     LZ_CUDA(cudaEventRecord(ctx->ev_begin, s));
 
@@ -294,22 +338,30 @@ extern "C" int lz_lanczos_run(lz_ctx* ctx, lz_op* op, const double* v0_dev, int3
                 const int nrows = ref_form ? j + 1 : j;      // the reference's sum includes row j itself
                 if (nrows == 0) continue;
                 int ncg = 0;
+                kt.begin(K_DOTS);
                 LZ_CHECK(launch_cgs_dots(ctx, V_dev, ldv, nrows, rj, M, gs_part, &ncg, flag)); ++launches;
+                kt.end();
                 fin_ip_kernel<<<1, kThreads, 0, s>>>(gs_part, ncg, j, ref_form, ref_form, st, flag,
                                                      (p == 0) ? 1 : 0);
                 ++launches;
+                kt.begin(K_GSUPD);
                 LZ_CHECK(launch_cgs_update(ctx, V_dev, ldv, j, rj, st.coef, st.cself, rj, M, flag)); ++launches;
+                kt.end();
             }
         }
         // ---- w = H q_j, alpha_j = q_j . w ------------------------------------------------------
         int l2 = 0;
+        kt.begin(K_APPLY);
         LZ_CHECK(launch_apply_dot(op, rj, st.scale + j, w, part, &np, &l2)); launches += l2;
+        kt.end();
         fin_alpha_kernel<<<1, kThreads, 0, s>>>(part, np, st.alpha + j); ++launches;
         // ---- r = w - alpha_j q_j - beta_j q_{j-1}; beta_{j+1} = |r| --------------------------
         double* out = (j + 1 < n) ? row(j + 1) : w;
+        kt.begin(K_UPDATE);
         LZ_CHECK(launch_update_norm(ctx, w, rj, j > 0 ? row(j - 1) : nullptr, st.alpha + j, st.scale + j,
                                     st.beta + j, j > 0 ? st.scale + j - 1 : nullptr, out, M, part, &np));
         ++launches;
+        kt.end();
         fin_beta_kernel<<<1, kThreads, 0, s>>>(part, np, st, j + 1, opts->breakdown_tol, st.alpha); ++launches;
         if (reorth == LZ_REORTH_SELECTIVE && j + 1 < n) {
             omega_kernel<<<1, kThreads, 0, s>>>(st, j, om_cur, om_prev, delta, eps1, psi); ++launches;
@@ -320,19 +372,25 @@ extern "C" int lz_lanczos_run(lz_ctx* ctx, lz_op* op, const double* v0_dev, int3
     LZ_CUDA(cudaEventRecord(ctx->ev_end, s));
 
     // ---- results ---------------------------------------------------------------------------
-    std::vector<double> h_alpha(nd), h_beta(nd), h_scale(nd);
+    // alpha, beta, scale are adjacent in the arena: one D2H copy
+    const size_t blk = (nd * 8 + 511) & ~(size_t)511;
+    std::vector<char> h_blk(3 * blk);
     int h_flags[8];
-    LZ_CUDA(cudaMemcpyAsync(h_alpha.data(), st.alpha, nd * 8, cudaMemcpyDeviceToHost, s));
-    LZ_CUDA(cudaMemcpyAsync(h_beta.data(), st.beta, nd * 8, cudaMemcpyDeviceToHost, s));
-    LZ_CUDA(cudaMemcpyAsync(h_scale.data(), st.scale, nd * 8, cudaMemcpyDeviceToHost, s));
+    LZ_CUDA(cudaMemcpyAsync(h_blk.data(), st.alpha, 3 * blk, cudaMemcpyDeviceToHost, s));
     LZ_CUDA(cudaMemcpyAsync(h_flags, st.flags, sizeof(h_flags), cudaMemcpyDeviceToHost, s));
     LZ_CUDA(cudaStreamSynchronize(s));
+    const double* h_alpha = reinterpret_cast<const double*>(h_blk.data());
+    const double* h_beta = reinterpret_cast<const double*>(h_blk.data() + blk);
+    const double* h_scale = reinterpret_cast<const double*>(h_blk.data() + 2 * blk);
     for (int j = 0; j < n; ++j) alpha_host[j] = h_alpha[j];
     for (int k = 0; k + 1 < n; ++k) beta_host[k] = h_beta[k + 1];     // Lanczos.py:112 numbering
     if (row_scale_host)
         for (int j = 0; j < n; ++j) row_scale_host[j] = h_scale[j];
     float ms = 0.f;
     LZ_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+    float kms[K_NKINDS];
+    int kcnt[K_NKINDS];
+    kt.collect(kms, kcnt, K_NKINDS);
     int steps_done = n;
     int status = LZ_OK;
     // a breakdown at index jn means row jn could not be normalised: steps 0..jn-1 are valid.
@@ -345,11 +403,13 @@ extern "C" int lz_lanczos_run(lz_ctx* ctx, lz_op* op, const double* v0_dev, int3
     }
     if (info) {
         info->steps_done = steps_done;
-        info->reorth_count = h_flags[2];
+        info->reorth_count = (reorth == LZ_REORTH_FULL) ? (ref ? n : n - 1) : h_flags[2];
         info->launches = launches;
         info->gpu_ms = ms;
-        info->reserved = 0;
-        info->reserved2 = 0.f;
+        info->apply_ms = kms[K_APPLY];   info->apply_launches = kcnt[K_APPLY];
+        info->update_ms = kms[K_UPDATE]; info->update_launches = kcnt[K_UPDATE];
+        info->dots_ms = kms[K_DOTS];     info->dots_launches = kcnt[K_DOTS];
+        info->gsupd_ms = kms[K_GSUPD];   info->gsupd_launches = kcnt[K_GSUPD];
     }
     return status;
 }

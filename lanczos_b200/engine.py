@@ -261,6 +261,11 @@ class LanczosResult:
         self.reorth_count = info.reorth_count
         self.launches = info.launches
         self.gpu_ms = float(info.gpu_ms)
+        # per-kernel device times (only when run with profile=True)
+        self.kernel_ms = {"apply": (float(info.apply_ms), info.apply_launches),
+                          "update": (float(info.update_ms), info.update_launches),
+                          "dots": (float(info.dots_ms), info.dots_launches),
+                          "gs_update": (float(info.gsupd_ms), info.gsupd_launches)}
 
     def tridiagonal(self) -> np.ndarray:
         """Dense H_eff like Lanczos.py:121-130."""
@@ -305,7 +310,8 @@ class LanczosResult:
 
 
 def run_lanczos(op: DeviceOperator, v0, n: int, *, reorth="full", cgs_passes=1, ref_compat=True,
-                keep_basis=True, breakdown_tol=0.0, select_tol=0.0, V_dev=None) -> LanczosResult:
+                keep_basis=True, breakdown_tol=0.0, select_tol=0.0, V_dev=None,
+                profile=False) -> LanczosResult:
     """Enqueue and run the n-step loop (lz_lanczos_run).  `v0` is a host array (copied through
     pinned memory) or a CUDA tensor of M doubles."""
     torch = _torch()
@@ -334,7 +340,8 @@ def run_lanczos(op: DeviceOperator, v0, n: int, *, reorth="full", cgs_passes=1, 
         alpha = np.zeros(n)
         beta = np.zeros(max(n - 1, 0))
         scale = np.ones(n)
-        opts = RunOpts(mode, int(cgs_passes), 1 if ref_compat else 0, 0, float(breakdown_tol), float(select_tol))
+        opts = RunOpts(mode, int(cgs_passes), 1 if ref_compat else 0, 1 if profile else 0,
+                       float(breakdown_tol), float(select_tol))
         info = RunInfo()
         status = ctx.lib.lz_lanczos_run(
             ctx.handle, op.handle, C.c_void_p(v0_dev.data_ptr()), n, C.byref(opts),

@@ -12,12 +12,9 @@ class IrrLanczos(LanczosBase):
     `execute_Lanczos` (:77-187) is an experimental two-sided variant that is broken at HEAD
     (SURVEY.md §2.1); here it runs the same symmetric loop."""
 
-    def execute_LanczosOld(self, n, seed=99, use_cuda=True, v0=None, *, reorth="full", cgs_passes=1,
-                           ref_compat=True, fmt="auto", sigma=0, device=None, keep_basis=True,
-                           breakdown_tol=0.0, select_tol=0.0):
-        self._execute(n, seed, use_cuda, v0, reorth=reorth, cgs_passes=cgs_passes, ref_compat=ref_compat,
-                      fmt=fmt, sigma=sigma, device=device, keep_basis=keep_basis,
-                      breakdown_tol=breakdown_tol, select_tol=select_tol)
+    def execute_LanczosOld(self, n, seed=99, use_cuda=True, v0=None, **options):
+        """IrrLanczos.py:193-260; `options` as in LanczosBase._execute."""
+        self._execute(n, seed, use_cuda, v0, **options)
 
     def execute_Lanczos(self, n, seed=99, use_cuda=True, v0=None, dtype=np.float64, **kw):
         if np.dtype(dtype) != np.float64:

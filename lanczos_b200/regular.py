@@ -11,15 +11,12 @@ class Lanczos(LanczosBase):
     call execute_Lanczos(n), read H_eff / V / H_eigvals / H_eigvecs.  `H` is a scipy.sparse
     matrix (what Hamiltonian.py builds) or a matrix-free lanczos_b200.StencilOperator."""
 
-    def execute_Lanczos(self, n, seed=99, use_cuda=True, v0=None, *, reorth="full", cgs_passes=1,
-                        ref_compat=True, fmt="auto", sigma=0, device=None, keep_basis=True,
-                        breakdown_tol=0.0, select_tol=0.0):
-        """Lanczos.py:75-141.  Positional/keyword arguments as in the reference; the keyword-only
-        extras default to the reference's behaviour (full re-orthogonalisation in the reference's
-        single-sweep form, the v0-discarding pre-step, basis kept)."""
-        self._execute(n, seed, use_cuda, v0, reorth=reorth, cgs_passes=cgs_passes, ref_compat=ref_compat,
-                      fmt=fmt, sigma=sigma, device=device, keep_basis=keep_basis,
-                      breakdown_tol=breakdown_tol, select_tol=select_tol)
+    def execute_Lanczos(self, n, seed=99, use_cuda=True, v0=None, **options):
+        """Lanczos.py:75-141.  Positional/keyword arguments as in the reference; `options` are the
+        keyword-only extras of LanczosBase._execute, which default to the reference's behaviour
+        (full re-orthogonalisation in the reference's single-sweep form, the v0-discarding
+        pre-step, basis kept)."""
+        self._execute(n, seed, use_cuda, v0, **options)
 
     def get_H_eigs(self):
         """Lanczos.py:145-163 (with the normalisation / orthogonality asserts of :157-158)."""
