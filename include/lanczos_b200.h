@@ -162,6 +162,40 @@ int lz_ritz_vectors(lz_ctx* ctx, const double* V_dev, int64_t ldv, int32_t n, in
                     const double* row_scale_host, const double* S_host, int32_t k,
                     double* Y_dev, int64_t ldy);
 
+/* ---- row-sharded (multi-GPU) solves ---------------------------------------------
+ * The reference has no distributed path; this is the multi-GPU form of the same loop
+ * (BASELINE.json north_star): vectors and the Krylov basis are split into contiguous row
+ * blocks, one per GPU (z-slabs of a structured grid).  A "team" is the set of `world` shards;
+ * `nlocal` of them are driven by the calling process (1 under torchrun, one process per GPU;
+ * all of them when a single process drives several shards, e.g. in tests).
+ *
+ * Each rank owns one exchange buffer (lz_comm_alloc) that every other rank maps
+ * (lz_comm_open of its cudaIpc handle, or the same pointer inside one process).  The fused
+ * kernels store halo planes and partial sums straight into the peers' buffers over NVLink;
+ * sums are taken in rank order, so alpha/beta are bit-identical on every rank.
+ */
+int lz_comm_bytes(int world, int32_t max_steps, int64_t plane_elems, int64_t nghost, int64_t* bytes);
+int lz_comm_alloc(lz_ctx* ctx, int64_t bytes, void** dev_ptr, unsigned char* ipc_handle64 /*nullable*/);
+int lz_comm_open(lz_ctx* ctx, const unsigned char* ipc_handle64, void** dev_ptr);
+int lz_comm_close(lz_ctx* ctx, void* dev_ptr);
+int lz_comm_free(lz_ctx* ctx, void* dev_ptr);
+
+/* local_ranks[nlocal], ctxs[nlocal]; global_rows = M of the whole operator; max_steps = largest
+ * n a run will use; plane_elems = nx*ny of a structured grid (0: none); nghost reserved. */
+int lz_team_create(int world, int nlocal, const int* local_ranks, lz_ctx* const* ctxs,
+                   int64_t global_rows, int32_t max_steps, int64_t plane_elems, int64_t nghost,
+                   lz_team** out);
+/* comm_ptrs[world]: exchange buffers of all ranks as mapped in this process; lower/upper = ranks
+ * owning the slab below/above this shard (-1: domain boundary, Dirichlet). */
+int lz_team_attach(lz_team* team, int local_index, void* const* comm_ptrs, int lower_rank, int upper_rank);
+/* As lz_lanczos_run, with one operator / start vector / basis buffer per local shard (the local
+ * slab: an lz_op_stencil_create with the local extents).  alpha/beta are the global values. */
+int lz_team_lanczos_run(lz_team* team, lz_op* const* ops, const double* const* v0_dev, int32_t n,
+                        const lz_run_opts* opts, double* alpha_host, double* beta_host,
+                        double* const* V_dev, const int64_t* ldv, double* row_scale_host,
+                        lz_run_info* info);
+int lz_team_destroy(lz_team* team);
+
 /* Deterministic device reductions used by the diagnostics (test_is_normalized,
  * print_good_eigs: Lanczos.py:166-185, 288-304): result_host[0] = x.y.  Synchronises. */
 int lz_dot(lz_ctx* ctx, const double* x_dev, const double* y_dev, int64_t M, double* result_host);

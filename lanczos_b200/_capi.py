@@ -63,6 +63,15 @@ SIGNATURES = {
     "lz_reorthogonalize": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _i32]),
     "lz_ritz_vectors": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _i32, _vp, _i64]),
     "lz_dot": (C.c_int, [_vp, _vp, _vp, _i64, _P(_dbl)]),
+    "lz_comm_bytes": (C.c_int, [C.c_int, _i32, _i64, _i64, _P(_i64)]),
+    "lz_comm_alloc": (C.c_int, [_vp, _i64, _P(_vp), _vp]),
+    "lz_comm_open": (C.c_int, [_vp, _vp, _P(_vp)]),
+    "lz_comm_close": (C.c_int, [_vp, _vp]),
+    "lz_comm_free": (C.c_int, [_vp, _vp]),
+    "lz_team_create": (C.c_int, [C.c_int, C.c_int, _P(C.c_int), _P(_vp), _i64, _i32, _i64, _i64, _P(_vp)]),
+    "lz_team_attach": (C.c_int, [_vp, C.c_int, _P(_vp), C.c_int, C.c_int]),
+    "lz_team_lanczos_run": (C.c_int, [_vp, _P(_vp), _P(_vp), _i32, _P(RunOpts), _vp, _vp, _P(_vp), _P(_i64), _vp, _P(RunInfo)]),
+    "lz_team_destroy": (C.c_int, [_vp]),
 }
 
 _lib = None

@@ -64,6 +64,14 @@ struct lz_op {
 
 namespace lz {
 
+// Destination of the halo planes of a vector being produced (sharded structured grids): the
+// first `plane` elements go to lo_dst, the last `plane` elements to hi_dst (peer memory).
+struct HaloPush {
+    double* lo_dst = nullptr;
+    double* hi_dst = nullptr;
+    int64_t plane = 0;
+};
+
 // ---- operator apply with fused dot:  y = s * (H x),  partials[cta] = sum y * (s*x) -----
 // `scale_dev` (nullable => 1) points at a device double.  `partials` has room for
 // kMaxPartials doubles; *nparts receives the number written.
@@ -77,7 +85,9 @@ int launch_dot(lz_ctx* ctx, const double* x, const double* y, int64_t M, double*
 // partials[cta] = sum out^2.  In-place (out == w) is allowed.
 int launch_update_norm(lz_ctx* ctx, const double* w, const double* a, const double* b,
                        const double* ca_dev, const double* sa_dev, const double* cb_dev,
-                       const double* sb_dev, double* out, int64_t M, double* partials, int* nparts);
+                       const double* sb_dev, double* out, int64_t M, double* partials, int* nparts,
+                       const HaloPush* halo = nullptr);
+int launch_halo_push(lz_ctx* ctx, const double* x, int64_t M, const HaloPush* halo);
 int launch_scale(lz_ctx* ctx, double* x, int64_t M, double s);
 
 // ---- Gram-Schmidt block GEMV pair (reorth.cu) --------------------------------------------
@@ -87,7 +97,7 @@ int launch_cgs_dots(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, const 
 // update: out = cself * target - sum_{r<nrows} coef[r] * V[r,:]   (coef, cself on the device)
 int launch_cgs_update(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, const double* target,
                       const double* coef_dev, const double* cself_dev, double* out, int64_t M,
-                      const int* flag_dev);
+                      const int* flag_dev, const HaloPush* halo = nullptr);
 // Y[c,:] = sum_r S[r + c*n] * V[r,:]  (S on the device, n x k column-major)
 int launch_ritz_lift(lz_ctx* ctx, const double* V, int64_t ldv, int n, int64_t M,
                      const double* S_dev, int k, double* Y, int64_t ldy);

@@ -1,21 +1,30 @@
 // The Lanczos tridiagonalisation loop: host-side launch sequence plus the single-CTA
-// "scalar" kernels that finish every reduction deterministically on the device and keep
-// alpha, beta, the lazy normalisation factors and the Gram-Schmidt coefficients in HBM, so
-// that the host never synchronises inside the loop.
+// "fin" kernels that finish every reduction deterministically on the device - across CTAs and,
+// in a row-sharded run, across GPUs through NVLink peer memory - and keep alpha, beta, the lazy
+// normalisation factors and the Gram-Schmidt coefficients in HBM, so that the host never
+// synchronises inside the loop.
 //
 // Replaces Lanczos.execute_Lanczos lines 100-119 (Python/Regular/Lanczos.py) and
 // IrrLanczos.execute_LanczosOld lines 217-238 (Python/Irregular/IrrLanczos.py).
 //
-// Per step j (device kernels, one stream):
+// Per step j (device kernels, one stream per shard):
 //   [K4a cgs_dots -> fin_ip -> K4b cgs_update] x passes   (full: every step; selective: predicated)
 //   K1 apply_dot(row j, s_j) -> w, partials            fin_alpha -> alpha[j]
 //   K3 update_norm(w, row j, row j-1) -> row j+1       fin_beta  -> beta[j+1], s_{j+1} = 1/beta
 //   [omega recurrence -> flag for step j+1]             (selective only)
 // Basis rows are stored un-normalised (row j = r_j, q_j = s_j * row j) unless a Gram-Schmidt
 // sweep rewrote them (then s_j = 1): the plain step moves 48*M bytes.
+//
+// Sharded runs (lz_team): every vector and basis row is split into contiguous row blocks, one
+// per GPU (z-slabs of a structured grid).  K3 / K4b store the boundary planes of the vector they
+// produce straight into the neighbours' ghost buffers; the fin kernels push their partial sums
+// to every peer and add the P contributions in rank order (peer.cuh) - that flag also
+// publishes the halo.  No NCCL call, no extra pass over HBM, no extra launch per step.
 #include <math.h>
+#include <string.h>
 #include <vector>
 #include "internal.h"
+#include "peer.cuh"
 
 namespace lz {
 
@@ -32,41 +41,43 @@ struct RunState {          // all device pointers
     double* beta;          // [n+1]  beta[j] = |r_j|  (r_j is what row j stores before any sweep)
     double* scale;         // [n+1]  q_j = scale[j] * row_j
     double* coef;          // [n+1]  Gram-Schmidt coefficients for K4b (already times scale[r])
+    double* omega_a;       // [n+2]  selective monitor, omega_{j,k}
+    double* omega_b;       // [n+2]
     double* cself;         // [1]
     double* v0scale;       // [1]    1/|v0|
     double* alpha_pre;     // [1]    alpha of the pre-step (discarded by the reference)
-    double* omega_a;       // [n+2]  selective monitor, omega_{j,k}
-    double* omega_b;       // [n+2]
     double* anorm;         // [1]    running estimate of |H|
     int* flags;            // [0] first breakdown step (-1: none), [1] reorth flag of the coming step,
-                           // [2] reorth count, [3] force-next flag
+                           // [2] reorth count, [3] force-next flag, [4] peer timeout
 };
 
+enum { FIN_V0NORM = 0, FIN_ALPHA = 1, FIN_BETA = 2 };
+
+// One scalar: CTA partials -> local sum -> (sharded) sum over ranks -> bookkeeping by `kind`.
 __global__ void __launch_bounds__(kThreads)
-fin_v0norm_kernel(const double* __restrict__ partials, int np, RunState st) {
+fin_scalar_kernel(const double* __restrict__ partials, int np, RunState st, PeerComm pc,
+                  unsigned long long seq, int mode, int kind, double* out, int jn, double tol_rel,
+                  const double* __restrict__ magnitude) {
     __shared__ double red[kWarps];
-    const double s = cta_sum_partials(partials, np, red);
-    if (threadIdx.x == 0) {
+    double s = 0.0;
+    if (mode != LZ_XCHG_COMBINE) s = cta_sum_partials(partials, np, red);
+    if (pc.world > 1) {
+        if (mode != LZ_XCHG_COMBINE) {
+            if (threadIdx.x == 0) peer_store(pc, seq, 0, s);
+            peer_publish(pc, seq);
+            if (mode == LZ_XCHG_PUSH) return;
+        }
+        peer_wait(pc, seq);
+        if (threadIdx.x == 0) s = peer_sum(pc, seq, 0);
+    }
+    if (threadIdx.x != 0) return;
+    if (kind == FIN_V0NORM) {
         const double nrm = sqrt(s);
         st.v0scale[0] = (nrm > 0.0) ? 1.0 / nrm : 0.0;
         if (!(nrm > 0.0) && st.flags[0] < 0) st.flags[0] = 0;
-    }
-}
-
-__global__ void __launch_bounds__(kThreads)
-fin_alpha_kernel(const double* __restrict__ partials, int np, double* __restrict__ out) {
-    __shared__ double red[kWarps];
-    const double s = cta_sum_partials(partials, np, red);
-    if (threadIdx.x == 0) out[0] = s;
-}
-
-// beta[jn] = sqrt(sum), scale[jn] = 1/beta; breakdown bookkeeping.
-__global__ void __launch_bounds__(kThreads)
-fin_beta_kernel(const double* __restrict__ partials, int np, RunState st, int jn, double tol_rel,
-                const double* __restrict__ magnitude) {
-    __shared__ double red[kWarps];
-    const double s = cta_sum_partials(partials, np, red);
-    if (threadIdx.x == 0) {
+    } else if (kind == FIN_ALPHA) {
+        out[0] = s;
+    } else {
         const double b = sqrt(s);
         st.beta[jn] = b;
         const double thresh = tol_rel * fabs(magnitude[0]);
@@ -76,7 +87,7 @@ fin_beta_kernel(const double* __restrict__ partials, int np, RunState st, int jn
     }
 }
 
-// Copy for the non-ref start: beta[0] = |v0|, scale[0] = 1/|v0|.
+// Non-ref start: beta[0] = |v0|, scale[0] = 1/|v0|.
 __global__ void init_first_row_kernel(RunState st) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const double s = st.v0scale[0];
@@ -86,34 +97,65 @@ __global__ void init_first_row_kernel(RunState st) {
 }
 
 // Gram-Schmidt coefficients from the dots partials:
-//   ip_r = scale[r] * scale[j] * sum_g part[r*ncg + g]            r < j
+//   ip_r = scale[r] * scale[j] * sum_ranks sum_g part[r*ncg + g]            r < j
 //   coef[r] = ip_r * scale[r]
 //   cself = (ref_form ? 2 - scale[j]^2 * (row_j . row_j) : 1) * scale[j];  scale[j] <- 1
 __global__ void __launch_bounds__(kThreads)
 fin_ip_kernel(const double* __restrict__ part, int ncg, int j, int self_included, int ref_form,
-              RunState st, const int* __restrict__ flag, int count) {
+              RunState st, PeerComm pc, unsigned long long seq, int mode,
+              const int* __restrict__ flag, int count) {
     if (flag && *flag == 0) return;
-    const double sj = st.scale[j];
-    for (int r = threadIdx.x; r < j; r += kThreads) {
-        const double* p = part + (int64_t)r * ncg;
-        double a = 0.0;
-        for (int g = 0; g < ncg; ++g) a += p[g];
-        const double sr = st.scale[r];
-        st.coef[r] = (a * sr * sj) * sr;
+    const int nrows = self_included ? j + 1 : j;
+    const bool sharded = pc.world > 1;
+    __shared__ double s_self;
+    if (threadIdx.x == 0) s_self = 0.0;
+    __syncthreads();
+    if (mode != LZ_XCHG_COMBINE) {
+        const double sj0 = st.scale[j];
+        for (int r = threadIdx.x; r < nrows; r += kThreads) {
+            const double* p = part + (int64_t)r * ncg;
+            double a = 0.0;
+            for (int g = 0; g < ncg; ++g) a += p[g];
+            if (sharded) peer_store(pc, seq, r, a);
+            else if (r < j) { const double sr = st.scale[r]; st.coef[r] = (a * sr * sj0) * sr; }
+            else s_self = a;
+        }
+        if (sharded) {
+            peer_publish(pc, seq);
+            if (mode == LZ_XCHG_PUSH) return;
+        }
+    }
+    if (sharded) {
+        peer_wait(pc, seq);
+        const double sj0 = st.scale[j];
+        for (int r = threadIdx.x; r < nrows; r += kThreads) {
+            const double a = peer_sum(pc, seq, r);
+            if (r < j) { const double sr = st.scale[r]; st.coef[r] = (a * sr * sj0) * sr; }
+            else s_self = a;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        const double sj = st.scale[j];
         double c = 1.0;
-        if (self_included && ref_form) {
-            const double* p = part + (int64_t)j * ncg;
-            double a = 0.0;
-            for (int g = 0; g < ncg; ++g) a += p[g];
-            c = 2.0 - a * sj * sj;
-        }
+        if (self_included && ref_form) c = 2.0 - s_self * sj * sj;
         st.cself[0] = c * sj;
         st.scale[j] = 1.0;           // K4b stores the row normalised
         if (count) st.flags[2] += 1;
     }
+}
+
+// Flag-only exchange: publishes the halo planes that the preceding kernel of this stream stored
+// into the neighbours' ghost buffers, and waits for theirs.
+__global__ void __launch_bounds__(32)
+peer_sync_kernel(PeerComm pc, unsigned long long seq, int mode, const int* __restrict__ flag) {
+    if (flag && *flag == 0) return;
+    if (pc.world <= 1) return;
+    if (mode != LZ_XCHG_COMBINE) {
+        peer_publish(pc, seq);
+        if (mode == LZ_XCHG_PUSH) return;
+    }
+    peer_wait(pc, seq);
 }
 
 // Selective re-orthogonalisation monitor (Simon's omega recurrence in the PROPACK form).
@@ -127,8 +169,7 @@ omega_kernel(RunState st, int j, double* om_cur, double* om_prev, double delta, 
     const double bj1 = st.beta[j + 1];
     const double bj = (j > 0) ? st.beta[j] : 0.0;
     const double aj = st.alpha[j];
-    // the reorth of the coming step was decided by the previous call (flags[1]); if this step's
-    // vector was itself re-orthogonalised, its omegas are at round-off level.
+    // if this step's vector was itself re-orthogonalised, its omegas are at round-off level
     if (st.flags[1]) {
         for (int k = threadIdx.x; k < j; k += kThreads) om_cur[k] = eps1;
         __syncthreads();
@@ -152,7 +193,6 @@ omega_kernel(RunState st, int j, double* om_cur, double* om_prev, double delta, 
         om_prev[k] = t;                      // becomes omega_{j+1,k} after the swap on the host side
         mx = fmax(mx, fabs(t));
     }
-    // block max
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
     __syncthreads();
@@ -182,7 +222,12 @@ struct Carver {
 
 int arena_reserve(lz_ctx* ctx, size_t bytes) {
     if (ctx->arena_bytes >= bytes) return LZ_OK;
-    if (ctx->arena) { LZ_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
+    if (ctx->arena) {
+        LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->arena);
+        ctx->arena = nullptr;
+        ctx->arena_bytes = 0;
+    }
     LZ_CUDA(cudaMalloc(&ctx->arena, bytes));
     ctx->arena_bytes = bytes;
     return LZ_OK;
@@ -232,153 +277,343 @@ struct KernelTimer {
 
 using namespace lz;
 
-extern "C" int lz_lanczos_run(lz_ctx* ctx, lz_op* op, const double* v0_dev, int32_t n,
-                              const lz_run_opts* opts, double* alpha_host, double* beta_host,
-                              double* V_dev, int64_t ldv, double* row_scale_host, lz_run_info* info) {
-    LZ_REQUIRE(ctx && op && v0_dev && opts && alpha_host, "lz_lanczos_run: null argument");
-    LZ_REQUIRE(op->ctx == ctx, "lz_lanczos_run: operator belongs to another context");
-    const int64_t M = op->M;
+// One row shard of a distributed solve, as this process sees it.
+struct lz_shard {
+    lz_ctx* ctx = nullptr;
+    int rank = 0;
+    PeerComm pc;
+    void* comm[kMaxWorld] = {};          // exchange buffers of all ranks, mapped in this process
+    // structured-grid halo: where my boundary planes go / where my neighbours' planes arrive
+    int lower = -1, upper = -1;          // neighbour ranks (-1: none, domain boundary)
+    int64_t plane = 0;
+};
+
+struct lz_team {
+    int world = 1;
+    int nlocal = 1;
+    int kmax = 0;
+    int64_t plane = 0, nghost = 0;
+    int64_t global_rows = 0;             // M of the whole operator (same number on every rank)
+    CommLayout layout{};
+    std::vector<lz_shard> shards;
+    unsigned long long seq = 0;          // sequence number of the last cross-rank exchange
+};
+
+namespace {
+
+struct ShardRun {           // per-shard state of one run
+    lz_ctx* ctx = nullptr;
+    lz_op* op = nullptr;
+    lz_shard* sh = nullptr; // null: single shard, no exchange
+    RunState st{};
+    PeerComm pc;
+    const double* v0 = nullptr;
+    double* V = nullptr;
+    int64_t ldv = 0;
+    int64_t M = 0;
+    double* w = nullptr;
+    double* ring = nullptr;
+    int64_t ld_int = 0;
+    double* gs_part = nullptr;
+    double* om_cur = nullptr;
+    double* om_prev = nullptr;
+    KernelTimer kt;
+    int np = 0;
+    int ncg = 0;
+    double* row(int j) const { return V ? V + (int64_t)j * ldv : ring + (int64_t)(j % 3) * ld_int; }
+};
+
+HaloPush halo_for(const lz_team* team, const ShardRun& r, int parity) {
+    HaloPush h{};
+    if (!team || !r.sh || r.sh->plane == 0) return h;
+    const lz_shard* sh = r.sh;
+    h.plane = sh->plane;
+    const size_t pb = (size_t)sh->plane * 8;
+    // my first plane is the plane ABOVE the lower neighbour's slab -> its ghost_hi
+    if (sh->lower >= 0)
+        h.lo_dst = reinterpret_cast<double*>((char*)sh->comm[sh->lower] + team->layout.ghost_hi_off + parity * pb);
+    if (sh->upper >= 0)
+        h.hi_dst = reinterpret_cast<double*>((char*)sh->comm[sh->upper] + team->layout.ghost_lo_off + parity * pb);
+    return h;
+}
+
+void bind_ghosts(const lz_team* team, ShardRun& r, int parity) {
+    if (!team || !r.sh || r.sh->plane == 0 || r.op->kind != LZ_OP_STENCIL) return;
+    const lz_shard* sh = r.sh;
+    const size_t pb = (size_t)sh->plane * 8;
+    char* mine = (char*)sh->comm[sh->rank];
+    r.op->st.sharded = 1;
+    r.op->st.ghost_lo = (sh->lower >= 0) ? reinterpret_cast<const double*>(mine + team->layout.ghost_lo_off + parity * pb) : nullptr;
+    r.op->st.ghost_hi = (sh->upper >= 0) ? reinterpret_cast<const double*>(mine + team->layout.ghost_hi_off + parity * pb) : nullptr;
+}
+
+// The loop over `nl` local shards (nl == 1 and team == nullptr: the plain single-GPU solve).
+int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s, int32_t n,
+             const lz_run_opts* opts, double* alpha_host, double* beta_host, double* const* Vs,
+             const int64_t* ldvs, double* row_scale_host, lz_run_info* info) {
+    LZ_REQUIRE(ops && v0s && opts && alpha_host, "lz_lanczos_run: null argument");
     LZ_REQUIRE(n >= 1, "lz_lanczos_run: n must be >= 1");
-    LZ_REQUIRE(n <= M, "n cannot be larger than M!");                 // Lanczos.py:76-77
     LZ_REQUIRE(!(opts->ref_compat && n < 2), "lz_lanczos_run: ref_compat needs n >= 2 (the reference raises IndexError for n == 1)");
     LZ_REQUIRE(n < 2 || beta_host, "lz_lanczos_run: beta_host is null");
     const int reorth = opts->reorth;
     LZ_REQUIRE(reorth >= LZ_REORTH_NONE && reorth <= LZ_REORTH_SELECTIVE, "lz_lanczos_run: bad reorth mode %d", reorth);
     const int passes = opts->cgs_passes <= 0 ? 1 : opts->cgs_passes;
     LZ_REQUIRE(passes <= 2, "lz_lanczos_run: cgs_passes must be 1 or 2");
-    LZ_REQUIRE(reorth == LZ_REORTH_NONE || V_dev, "lz_lanczos_run: re-orthogonalisation needs the basis buffer V_dev");
-    LZ_REQUIRE(!V_dev || ldv >= M, "lz_lanczos_run: ldv < M");
-    LZ_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
+    const int world = team ? team->world : 1;
+    LZ_REQUIRE(!team || n + 2 <= team->kmax, "lz_team_lanczos_run: n = %d exceeds the team's max_steps", n);
+    const bool split = nl > 1;            // several shards driven by this process: push / combine phases
+    const size_t nd = (size_t)n + 2;
+
+    std::vector<ShardRun> R(nl);
+    int64_t M_local = 0;
+    for (int s = 0; s < nl; ++s) {
+        ShardRun& r = R[s];
+        r.op = ops[s];
+        LZ_REQUIRE(r.op && v0s[s], "lz_lanczos_run: null operator or start vector");
+        r.ctx = r.op->ctx;
+        r.sh = team ? &team->shards[s] : nullptr;
+        LZ_REQUIRE(!team || r.sh->ctx == r.ctx, "lz_team_lanczos_run: operator %d is not on its shard's context", s);
+        r.v0 = v0s[s];
+        r.V = Vs ? Vs[s] : nullptr;
+        r.ldv = ldvs ? ldvs[s] : 0;
+        r.M = r.op->M;
+        M_local += r.M;
+        LZ_REQUIRE(reorth == LZ_REORTH_NONE || r.V, "lz_lanczos_run: re-orthogonalisation needs the basis buffer V_dev");
+        LZ_REQUIRE(!r.V || r.ldv >= r.M, "lz_lanczos_run: ldv < M");
+        if (team) r.pc = r.sh->pc;
+    }
+    if (!team) LZ_REQUIRE(n <= M_local, "n cannot be larger than M!");             // Lanczos.py:76-77
+    const double M_global = team ? (double)team->global_rows : (double)M_local;
+    LZ_REQUIRE(!team || n <= team->global_rows, "n cannot be larger than M!");
+    (void)world;
 
     // ---- workspace ---------------------------------------------------------------------------
-    const size_t nd = (size_t)n + 2;
-    const int64_t ld_int = (M + 63) & ~(int64_t)63;
-    const size_t vec_bytes = (size_t)ld_int * 8 + 512;
-    size_t need = 16 * 512 + 6 * (nd * 8 + 512) + vec_bytes;
-    if (!V_dev) need += 3 * vec_bytes;
-    if (reorth != LZ_REORTH_NONE) need += (size_t)(n + 1) * kMaxPartials * 8 + 512;
-    LZ_CHECK(arena_reserve(ctx, need));
-    Carver cv{(char*)ctx->arena};
-    RunState st{};
-    st.alpha = cv.take<double>(nd);
-    st.beta = cv.take<double>(nd);
-    st.scale = cv.take<double>(nd);
-    st.coef = cv.take<double>(nd);
-    st.omega_a = cv.take<double>(nd);
-    st.omega_b = cv.take<double>(nd);
-    st.cself = cv.take<double>(1);
-    st.v0scale = cv.take<double>(1);
-    st.alpha_pre = cv.take<double>(1);
-    st.anorm = cv.take<double>(1);
-    st.flags = cv.take<int>(8);
-    double* w = cv.take<double>((size_t)ld_int);
-    double* ring = V_dev ? nullptr : cv.take<double>((size_t)ld_int * 3);
-    double* gs_part = (reorth != LZ_REORTH_NONE) ? cv.take<double>((size_t)(n + 1) * kMaxPartials) : nullptr;
-
-    // alpha .. omega_b are contiguous 512-byte-rounded blocks: one memset clears them all
-    LZ_CUDA(cudaMemsetAsync(st.alpha, 0, (char*)st.cself - (char*)st.alpha, s));
-    LZ_CUDA(cudaMemsetAsync(st.anorm, 0, 8, s));
-    {
+    for (int s = 0; s < nl; ++s) {
+        ShardRun& r = R[s];
+        LZ_CUDA(cudaSetDevice(r.ctx->device));
+        r.ld_int = (r.M + 63) & ~(int64_t)63;
+        const size_t vec_bytes = (size_t)r.ld_int * 8 + 512;
+        size_t need = 16 * 512 + 6 * (nd * 8 + 512) + vec_bytes;
+        if (!r.V) need += 3 * vec_bytes;
+        if (reorth != LZ_REORTH_NONE) need += (size_t)(n + 1) * kMaxPartials * 8 + 512;
+        LZ_CHECK(arena_reserve(r.ctx, need));
+        Carver cv{(char*)r.ctx->arena};
+        RunState& st = r.st;
+        st.alpha = cv.take<double>(nd);
+        st.beta = cv.take<double>(nd);
+        st.scale = cv.take<double>(nd);
+        st.coef = cv.take<double>(nd);
+        st.omega_a = cv.take<double>(nd);
+        st.omega_b = cv.take<double>(nd);
+        st.cself = cv.take<double>(1);
+        st.v0scale = cv.take<double>(1);
+        st.alpha_pre = cv.take<double>(1);
+        st.anorm = cv.take<double>(1);
+        st.flags = cv.take<int>(8);
+        r.w = cv.take<double>((size_t)r.ld_int);
+        r.ring = r.V ? nullptr : cv.take<double>((size_t)r.ld_int * 3);
+        r.gs_part = (reorth != LZ_REORTH_NONE) ? cv.take<double>((size_t)(n + 1) * kMaxPartials) : nullptr;
+        r.om_cur = st.omega_a;
+        r.om_prev = st.omega_b;
+        r.pc.err = st.flags + 4;
+        cudaStream_t q = r.ctx->stream;
+        // alpha .. omega_b are contiguous 512-byte-rounded blocks: one memset clears them all
+        LZ_CUDA(cudaMemsetAsync(st.alpha, 0, (char*)st.cself - (char*)st.alpha, q));
+        LZ_CUDA(cudaMemsetAsync(st.anorm, 0, 8, q));
         const double one = 1.0;                       // omega_{0,0} = 1
-        LZ_CUDA(cudaMemcpyAsync(st.omega_a, &one, 8, cudaMemcpyHostToDevice, s));
+        LZ_CUDA(cudaMemcpyAsync(st.omega_a, &one, 8, cudaMemcpyHostToDevice, q));
         const int h_flags[8] = {-1, reorth == LZ_REORTH_FULL ? 1 : 0, 0, 0, 0, 0, 0, 0};
-        LZ_CUDA(cudaMemcpyAsync(st.flags, h_flags, sizeof(h_flags), cudaMemcpyHostToDevice, s));
+        LZ_CUDA(cudaMemcpyAsync(st.flags, h_flags, sizeof(h_flags), cudaMemcpyHostToDevice, q));
+        r.kt.ctx = r.ctx;
+        r.kt.on = (opts->profile != 0);
+        if (r.kt.on) {   // create the pool outside the timed loop
+            while (r.ctx->event_pool.size() < (size_t)(2 * (2 + 2 * passes) * n + 8)) {
+                cudaEvent_t e = nullptr;
+                LZ_CUDA(cudaEventCreate(&e));
+                r.ctx->event_pool.push_back(e);
+            }
+        }
     }
-    auto row = [&](int j) -> double* {
-        return V_dev ? V_dev + (int64_t)j * ldv : ring + (int64_t)(j % 3) * ld_int;
-    };
-    double* part = ctx->partials;
-    int launches = 0, np = 0;
+
+    int launches = 0;
     const int ref = opts->ref_compat ? 1 : 0;
     const double eps = 2.220446049250313e-16;
     const double delta = opts->select_tol > 0.0 ? opts->select_tol : sqrt(eps);
     const double eps1 = eps * 1.5;      // noise floor of the omega recurrence
-    const double psi = eps * sqrt((double)M);
-    KernelTimer kt;
-    kt.ctx = ctx;
-    kt.on = (opts->profile != 0);
-    if (kt.on) {   // create the pool outside the timed loop
-        while (ctx->event_pool.size() < (size_t)(2 * (2 + 2 * passes) * n + 8)) {
-            cudaEvent_t e = nullptr;
-            LZ_CUDA(cudaEventCreate(&e));
-            ctx->event_pool.push_back(e);
-        }
-    }
+    const double psi = eps * sqrt(M_global);
     enum { K_APPLY = 0, K_UPDATE = 1, K_DOTS = 2, K_GSUPD = 3, K_NKINDS = 4 };
 
-    LZ_CUDA(cudaEventRecord(ctx->ev_begin, s));
+    // run `fn(shard)` on every local shard, on its device
+    auto each = [&](auto&& fn) -> int {
+        for (int s = 0; s < nl; ++s) {
+            if (nl > 1) LZ_CUDA(cudaSetDevice(R[s].ctx->device));
+            LZ_CHECK(fn(R[s]));
+        }
+        return LZ_OK;
+    };
+    // a cross-rank exchange: one fused kernel per shard, or (several local shards) a push phase
+    // over all shards followed by a combine phase
+    auto exchange = [&](auto&& launch) -> int {
+        unsigned long long seq = 0;
+        if (team) seq = ++team->seq;
+        if (!split) return each([&](ShardRun& r) { return launch(r, seq, (int)LZ_XCHG_FUSED); });
+        LZ_CHECK(each([&](ShardRun& r) { return launch(r, seq, (int)LZ_XCHG_PUSH); }));
+        return each([&](ShardRun& r) { return launch(r, seq, (int)LZ_XCHG_COMBINE); });
+    };
+    auto fin_scalar = [&](int kind, auto&& out_of, int jn, double tol, auto&& mag_of) -> int {
+        return exchange([&](ShardRun& r, unsigned long long seq, int mode) -> int {
+            fin_scalar_kernel<<<1, kThreads, 0, r.ctx->stream>>>(r.ctx->partials, r.np, r.st, r.pc, seq, mode, kind,
+                                                                 out_of(r), jn, tol, mag_of(r));
+            ++launches;
+            return LZ_OK;
+        });
+    };
+    auto peer_sync = [&](bool predicated) -> int {
+        if (!team) return LZ_OK;
+        return exchange([&](ShardRun& r, unsigned long long seq, int mode) -> int {
+            peer_sync_kernel<<<1, 32, 0, r.ctx->stream>>>(r.pc, seq, mode, predicated ? r.st.flags + 1 : nullptr);
+            ++launches;
+            return LZ_OK;
+        });
+    };
+    auto nul = [](ShardRun&) -> double* { return nullptr; };
+
+    LZ_CHECK(each([&](ShardRun& r) { LZ_CUDA(cudaEventRecord(r.ctx->ev_begin, r.ctx->stream)); return LZ_OK; }));
 
     // ---- start: |v0| ---------------------------------------------------------------------
-    LZ_CHECK(launch_dot(ctx, v0_dev, v0_dev, M, part, &np)); ++launches;
-    fin_v0norm_kernel<<<1, kThreads, 0, s>>>(part, np, st); ++launches;
+    LZ_CHECK(each([&](ShardRun& r) { ++launches; return launch_dot(r.ctx, r.v0, r.v0, r.M, r.ctx->partials, &r.np); }));
+    LZ_CHECK(fin_scalar(FIN_V0NORM, nul, 0, 0.0, nul));
     if (ref) {
-        // pre-step (Lanczos.py:108-110): r = H q - (q.Hq) q with q = v0/|v0|; r becomes row 0
-        int l2 = 0;
-        LZ_CHECK(launch_apply_dot(op, v0_dev, st.v0scale, w, part, &np, &l2)); launches += l2;
-        fin_alpha_kernel<<<1, kThreads, 0, s>>>(part, np, st.alpha_pre); ++launches;
-        LZ_CHECK(launch_update_norm(ctx, w, v0_dev, nullptr, st.alpha_pre, st.v0scale, nullptr, nullptr,
-                                    row(0), M, part, &np)); ++launches;
-        fin_beta_kernel<<<1, kThreads, 0, s>>>(part, np, st, 0, opts->breakdown_tol, st.alpha_pre); ++launches;
+        // pre-step (Lanczos.py:108-110): r = H q - (q.Hq) q with q = v0/|v0|; r becomes row 0.
+        // Sharded: the ghost planes of v0 travel through the parity-1 buffers.
+        if (team) {
+            LZ_CHECK(each([&](ShardRun& r) {
+                HaloPush h = halo_for(team, r, 1);
+                if (h.lo_dst || h.hi_dst) ++launches;
+                return launch_halo_push(r.ctx, r.v0, r.M, &h);
+            }));
+            LZ_CHECK(peer_sync(false));
+        }
+        LZ_CHECK(each([&](ShardRun& r) {
+            bind_ghosts(team, r, 1);
+            int l2 = 0;
+            const int rc = launch_apply_dot(r.op, r.v0, r.st.v0scale, r.w, r.ctx->partials, &r.np, &l2);
+            launches += l2;
+            return rc;
+        }));
+        LZ_CHECK(fin_scalar(FIN_ALPHA, [](ShardRun& r) { return r.st.alpha_pre; }, 0, 0.0, nul));
+        LZ_CHECK(each([&](ShardRun& r) {
+            HaloPush h = halo_for(team, r, 0);
+            ++launches;
+            return launch_update_norm(r.ctx, r.w, r.v0, nullptr, r.st.alpha_pre, r.st.v0scale, nullptr, nullptr,
+                                      r.row(0), r.M, r.ctx->partials, &r.np, &h);
+        }));
+        LZ_CHECK(fin_scalar(FIN_BETA, nul, 0, opts->breakdown_tol, [](ShardRun& r) { return r.st.alpha_pre; }));
     } else {
-        LZ_CUDA(cudaMemcpyAsync(row(0), v0_dev, (size_t)M * 8, cudaMemcpyDeviceToDevice, s));
-        init_first_row_kernel<<<1, 32, 0, s>>>(st); ++launches;
+        LZ_CHECK(each([&](ShardRun& r) {
+            LZ_CUDA(cudaMemcpyAsync(r.row(0), r.v0, (size_t)r.M * 8, cudaMemcpyDeviceToDevice, r.ctx->stream));
+            init_first_row_kernel<<<1, 32, 0, r.ctx->stream>>>(r.st);
+            ++launches;
+            HaloPush h = halo_for(team, r, 0);
+            if (h.lo_dst || h.hi_dst) ++launches;
+            return launch_halo_push(r.ctx, r.v0, r.M, &h);
+        }));
+        LZ_CHECK(peer_sync(false));
     }
 
-    double* om_cur = st.omega_a;
-    double* om_prev = st.omega_b;
     for (int j = 0; j < n; ++j) {
-        double* rj = row(j);
+        const int par = j & 1;
         // ---- Gram-Schmidt sweeps of q_j against the rows before it ---------------------------
         const bool maybe_reorth = (reorth == LZ_REORTH_FULL) || (reorth == LZ_REORTH_SELECTIVE && j > 0);
         if (maybe_reorth && (j > 0 || ref)) {
-            const int* flag = (reorth == LZ_REORTH_SELECTIVE) ? (st.flags + 1) : nullptr;
+            const bool sel = (reorth == LZ_REORTH_SELECTIVE);
+            bool pushed = false;
             for (int p = 0; p < passes; ++p) {
                 const int ref_form = (ref && p == 0) ? 1 : 0;
                 const int nrows = ref_form ? j + 1 : j;      // the reference's sum includes row j itself
                 if (nrows == 0) continue;
-                int ncg = 0;
-                kt.begin(K_DOTS);
-                LZ_CHECK(launch_cgs_dots(ctx, V_dev, ldv, nrows, rj, M, gs_part, &ncg, flag)); ++launches;
-                kt.end();
-                fin_ip_kernel<<<1, kThreads, 0, s>>>(gs_part, ncg, j, ref_form, ref_form, st, flag,
-                                                     (p == 0) ? 1 : 0);
-                ++launches;
-                kt.begin(K_GSUPD);
-                LZ_CHECK(launch_cgs_update(ctx, V_dev, ldv, j, rj, st.coef, st.cself, rj, M, flag)); ++launches;
-                kt.end();
+                LZ_CHECK(each([&](ShardRun& r) {
+                    r.kt.begin(K_DOTS);
+                    const int rc = launch_cgs_dots(r.ctx, r.V, r.ldv, nrows, r.row(j), r.M, r.gs_part, &r.ncg,
+                                                   sel ? r.st.flags + 1 : nullptr);
+                    r.kt.end();
+                    ++launches;
+                    return rc;
+                }));
+                LZ_CHECK(exchange([&](ShardRun& r, unsigned long long seq, int mode) -> int {
+                    fin_ip_kernel<<<1, kThreads, 0, r.ctx->stream>>>(r.gs_part, r.ncg, j, ref_form, ref_form, r.st, r.pc,
+                                                                     seq, mode, sel ? r.st.flags + 1 : nullptr,
+                                                                     (p == 0 && mode != LZ_XCHG_PUSH) ? 1 : 0);
+                    ++launches;
+                    return LZ_OK;
+                }));
+                LZ_CHECK(each([&](ShardRun& r) {
+                    HaloPush h = halo_for(team, r, par);
+                    r.kt.begin(K_GSUPD);
+                    const int rc = launch_cgs_update(r.ctx, r.V, r.ldv, j, r.row(j), r.st.coef, r.st.cself, r.row(j),
+                                                     r.M, sel ? r.st.flags + 1 : nullptr, &h);
+                    r.kt.end();
+                    ++launches;
+                    return rc;
+                }));
+                pushed = true;
             }
+            // the re-written row's halo planes must reach the neighbours before K1 reads them
+            if (pushed) LZ_CHECK(peer_sync(sel));
         }
         // ---- w = H q_j, alpha_j = q_j . w ------------------------------------------------------
-        int l2 = 0;
-        kt.begin(K_APPLY);
-        LZ_CHECK(launch_apply_dot(op, rj, st.scale + j, w, part, &np, &l2)); launches += l2;
-        kt.end();
-        fin_alpha_kernel<<<1, kThreads, 0, s>>>(part, np, st.alpha + j); ++launches;
+        LZ_CHECK(each([&](ShardRun& r) {
+            bind_ghosts(team, r, par);
+            int l2 = 0;
+            r.kt.begin(K_APPLY);
+            const int rc = launch_apply_dot(r.op, r.row(j), r.st.scale + j, r.w, r.ctx->partials, &r.np, &l2);
+            r.kt.end();
+            launches += l2;
+            return rc;
+        }));
+        LZ_CHECK(fin_scalar(FIN_ALPHA, [j](ShardRun& r) { return r.st.alpha + j; }, 0, 0.0, nul));
         // ---- r = w - alpha_j q_j - beta_j q_{j-1}; beta_{j+1} = |r| --------------------------
-        double* out = (j + 1 < n) ? row(j + 1) : w;
-        kt.begin(K_UPDATE);
-        LZ_CHECK(launch_update_norm(ctx, w, rj, j > 0 ? row(j - 1) : nullptr, st.alpha + j, st.scale + j,
-                                    st.beta + j, j > 0 ? st.scale + j - 1 : nullptr, out, M, part, &np));
-        ++launches;
-        kt.end();
-        fin_beta_kernel<<<1, kThreads, 0, s>>>(part, np, st, j + 1, opts->breakdown_tol, st.alpha); ++launches;
+        LZ_CHECK(each([&](ShardRun& r) {
+            double* out = (j + 1 < n) ? r.row(j + 1) : r.w;
+            HaloPush h = (j + 1 < n) ? halo_for(team, r, (j + 1) & 1) : HaloPush{};
+            r.kt.begin(K_UPDATE);
+            const int rc = launch_update_norm(r.ctx, r.w, r.row(j), j > 0 ? r.row(j - 1) : nullptr, r.st.alpha + j,
+                                              r.st.scale + j, r.st.beta + j, j > 0 ? r.st.scale + j - 1 : nullptr,
+                                              out, r.M, r.ctx->partials, &r.np, &h);
+            r.kt.end();
+            ++launches;
+            return rc;
+        }));
+        LZ_CHECK(fin_scalar(FIN_BETA, nul, j + 1, opts->breakdown_tol, [](ShardRun& r) { return r.st.alpha; }));
         if (reorth == LZ_REORTH_SELECTIVE && j + 1 < n) {
-            omega_kernel<<<1, kThreads, 0, s>>>(st, j, om_cur, om_prev, delta, eps1, psi); ++launches;
-            std::swap(om_cur, om_prev);
+            LZ_CHECK(each([&](ShardRun& r) {
+                omega_kernel<<<1, kThreads, 0, r.ctx->stream>>>(r.st, j, r.om_cur, r.om_prev, delta, eps1, psi);
+                ++launches;
+                std::swap(r.om_cur, r.om_prev);
+                return LZ_OK;
+            }));
         }
     }
-    LZ_CUDA(cudaGetLastError());
-    LZ_CUDA(cudaEventRecord(ctx->ev_end, s));
+    LZ_CHECK(each([&](ShardRun& r) {
+        LZ_CUDA(cudaGetLastError());
+        LZ_CUDA(cudaEventRecord(r.ctx->ev_end, r.ctx->stream));
+        return LZ_OK;
+    }));
 
-    // ---- results ---------------------------------------------------------------------------
-    // alpha, beta, scale are adjacent in the arena: one D2H copy
+    // ---- results (identical on every shard: read them from shard 0) -----------------------------
     const size_t blk = (nd * 8 + 511) & ~(size_t)511;
     std::vector<char> h_blk(3 * blk);
-    int h_flags[8];
-    LZ_CUDA(cudaMemcpyAsync(h_blk.data(), st.alpha, 3 * blk, cudaMemcpyDeviceToHost, s));
-    LZ_CUDA(cudaMemcpyAsync(h_flags, st.flags, sizeof(h_flags), cudaMemcpyDeviceToHost, s));
-    LZ_CUDA(cudaStreamSynchronize(s));
+    std::vector<int> h_flags(8 * nl);
+    for (int s = 0; s < nl; ++s) {
+        ShardRun& r = R[s];
+        if (nl > 1) LZ_CUDA(cudaSetDevice(r.ctx->device));
+        if (s == 0) LZ_CUDA(cudaMemcpyAsync(h_blk.data(), r.st.alpha, 3 * blk, cudaMemcpyDeviceToHost, r.ctx->stream));
+        LZ_CUDA(cudaMemcpyAsync(&h_flags[8 * s], r.st.flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, r.ctx->stream));
+    }
+    for (int s = 0; s < nl; ++s) {
+        if (nl > 1) LZ_CUDA(cudaSetDevice(R[s].ctx->device));
+        LZ_CUDA(cudaStreamSynchronize(R[s].ctx->stream));
+    }
     const double* h_alpha = reinterpret_cast<const double*>(h_blk.data());
     const double* h_beta = reinterpret_cast<const double*>(h_blk.data() + blk);
     const double* h_scale = reinterpret_cast<const double*>(h_blk.data() + 2 * blk);
@@ -387,21 +622,37 @@ extern "C" int lz_lanczos_run(lz_ctx* ctx, lz_op* op, const double* v0_dev, int3
     if (row_scale_host)
         for (int j = 0; j < n; ++j) row_scale_host[j] = h_scale[j];
     float ms = 0.f;
-    LZ_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
-    float kms[K_NKINDS];
-    int kcnt[K_NKINDS];
-    kt.collect(kms, kcnt, K_NKINDS);
+    float kms[K_NKINDS] = {0, 0, 0, 0};
+    int kcnt[K_NKINDS] = {0, 0, 0, 0};
+    for (int s = 0; s < nl; ++s) {
+        ShardRun& r = R[s];
+        if (nl > 1) LZ_CUDA(cudaSetDevice(r.ctx->device));
+        float m1 = 0.f;
+        LZ_CUDA(cudaEventElapsedTime(&m1, r.ctx->ev_begin, r.ctx->ev_end));
+        ms = std::max(ms, m1);
+        float km[K_NKINDS];
+        int kc[K_NKINDS];
+        r.kt.collect(km, kc, K_NKINDS);
+        if (s == 0) for (int k = 0; k < K_NKINDS; ++k) { kms[k] = km[k]; kcnt[k] = kc[k]; }
+    }
     int steps_done = n;
     int status = LZ_OK;
+    for (int s = 0; s < nl; ++s) {
+        if (h_flags[8 * s + 4]) {
+            set_error("multi-GPU exchange timed out on rank %d (a peer did not arrive)", team ? team->shards[s].rank : 0);
+            status = LZ_ERR_PEER;
+        }
+    }
     // a breakdown at index jn means row jn could not be normalised: steps 0..jn-1 are valid.
     // beta[n] (after the last step) is not part of the output and is ignored.
-    if (h_flags[0] >= 0 && h_flags[0] < n) {
+    if (status == LZ_OK && h_flags[0] >= 0 && h_flags[0] < n) {
         steps_done = h_flags[0];
         set_error("Lanczos breakdown: beta[%d] = %.3e (Krylov space exhausted after %d steps)",
                   h_flags[0], h_beta[h_flags[0]], steps_done);
         status = LZ_ERR_BREAKDOWN;
     }
     if (info) {
+        memset(info, 0, sizeof(*info));
         info->steps_done = steps_done;
         info->reorth_count = (reorth == LZ_REORTH_FULL) ? (ref ? n : n - 1) : h_flags[2];
         info->launches = launches;
@@ -414,6 +665,22 @@ extern "C" int lz_lanczos_run(lz_ctx* ctx, lz_op* op, const double* v0_dev, int3
     return status;
 }
 
+}  // namespace
+
+extern "C" int lz_lanczos_run(lz_ctx* ctx, lz_op* op, const double* v0_dev, int32_t n,
+                              const lz_run_opts* opts, double* alpha_host, double* beta_host,
+                              double* V_dev, int64_t ldv, double* row_scale_host, lz_run_info* info) {
+    LZ_REQUIRE(ctx && op && v0_dev && opts && alpha_host, "lz_lanczos_run: null argument");
+    LZ_REQUIRE(op->ctx == ctx, "lz_lanczos_run: operator belongs to another context");
+    LZ_REQUIRE(!op->st.sharded, "lz_lanczos_run: this operator is a shard of a team; use lz_team_lanczos_run");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    lz_op* ops[1] = {op};
+    const double* v0s[1] = {v0_dev};
+    double* Vs[1] = {V_dev};
+    const int64_t ldvs[1] = {ldv};
+    return run_loop(nullptr, 1, ops, v0s, n, opts, alpha_host, beta_host, Vs, ldvs, row_scale_host, info);
+}
+
 extern "C" int lz_basis_normalize(lz_ctx* ctx, double* V_dev, int64_t ldv, int32_t n, int64_t M,
                                   const double* row_scale_host) {
     LZ_REQUIRE(ctx && V_dev && row_scale_host, "lz_basis_normalize: null argument");
@@ -422,5 +689,141 @@ extern "C" int lz_basis_normalize(lz_ctx* ctx, double* V_dev, int64_t ldv, int32
         if (row_scale_host[j] == 1.0) continue;
         LZ_CHECK(launch_scale(ctx, V_dev + (int64_t)j * ldv, M, row_scale_host[j]));
     }
+    return LZ_OK;
+}
+
+// ================================ multi-GPU team ==============================================
+
+extern "C" int lz_comm_bytes(int world, int32_t max_steps, int64_t plane, int64_t nghost, int64_t* bytes) {
+    LZ_REQUIRE(bytes && world >= 1 && world <= kMaxWorld && max_steps >= 1 && plane >= 0 && nghost >= 0,
+               "lz_comm_bytes: bad argument (world <= %d)", kMaxWorld);
+    *bytes = (int64_t)CommLayout::make(world, max_steps + 2, plane, nghost).total;
+    return LZ_OK;
+}
+
+extern "C" int lz_comm_alloc(lz_ctx* ctx, int64_t bytes, void** dev_ptr, unsigned char* ipc_handle64) {
+    LZ_REQUIRE(ctx && dev_ptr && bytes > 0, "lz_comm_alloc: bad argument");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    LZ_CUDA(cudaMalloc(&p, (size_t)bytes));
+    LZ_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    LZ_CUDA(cudaDeviceSynchronize());
+    if (ipc_handle64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, p);
+        if (e != cudaSuccess) {
+            cudaFree(p);
+            set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+            return LZ_ERR_CUDA;
+        }
+        memcpy(ipc_handle64, &h, 64);
+    }
+    *dev_ptr = p;
+    return LZ_OK;
+}
+
+extern "C" int lz_comm_open(lz_ctx* ctx, const unsigned char* ipc_handle64, void** dev_ptr) {
+    LZ_REQUIRE(ctx && ipc_handle64 && dev_ptr, "lz_comm_open: bad argument");
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, 64);
+    LZ_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return LZ_OK;
+}
+
+extern "C" int lz_comm_close(lz_ctx* ctx, void* dev_ptr) {
+    LZ_REQUIRE(ctx, "lz_comm_close: bad argument");
+    if (!dev_ptr) return LZ_OK;
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    LZ_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return LZ_OK;
+}
+
+extern "C" int lz_comm_free(lz_ctx* ctx, void* dev_ptr) {
+    LZ_REQUIRE(ctx, "lz_comm_free: bad argument");
+    if (!dev_ptr) return LZ_OK;
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    LZ_CUDA(cudaFree(dev_ptr));
+    return LZ_OK;
+}
+
+extern "C" int lz_team_create(int world, int nlocal, const int* local_ranks, lz_ctx* const* ctxs,
+                              int64_t global_rows, int32_t max_steps, int64_t plane, int64_t nghost,
+                              lz_team** out) {
+    LZ_REQUIRE(out && local_ranks && ctxs, "lz_team_create: null argument");
+    LZ_REQUIRE(world >= 1 && world <= kMaxWorld, "lz_team_create: world must be in 1..%d", kMaxWorld);
+    LZ_REQUIRE(nlocal >= 1 && nlocal <= world, "lz_team_create: bad nlocal");
+    LZ_REQUIRE(max_steps >= 1 && plane >= 0 && nghost >= 0, "lz_team_create: bad sizes");
+    lz_team* t = new lz_team();
+    t->world = world;
+    t->nlocal = nlocal;
+    t->kmax = max_steps + 2;
+    t->plane = plane;
+    t->nghost = nghost;
+    t->global_rows = global_rows;
+    t->layout = CommLayout::make(world, t->kmax, plane, nghost);
+    t->shards.resize(nlocal);
+    for (int s = 0; s < nlocal; ++s) {
+        if (local_ranks[s] < 0 || local_ranks[s] >= world || !ctxs[s]) {
+            delete t;
+            set_error("lz_team_create: bad rank or context for local shard %d", s);
+            return LZ_ERR_INVALID;
+        }
+        t->shards[s].ctx = ctxs[s];
+        t->shards[s].rank = local_ranks[s];
+        t->shards[s].plane = plane;
+    }
+    // shards of one process on different devices talk through direct peer access
+    for (int a = 0; a < nlocal; ++a)
+        for (int b = 0; b < nlocal; ++b) {
+            const int da = ctxs[a]->device, db = ctxs[b]->device;
+            if (da == db) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, da, db);
+            if (can) {
+                cudaSetDevice(da);
+                cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+                if (e != cudaSuccess) (void)cudaGetLastError();     // already enabled
+            }
+        }
+    *out = t;
+    return LZ_OK;
+}
+
+extern "C" int lz_team_attach(lz_team* team, int local_index, void* const* comm_ptrs, int lower_rank,
+                              int upper_rank) {
+    LZ_REQUIRE(team && comm_ptrs, "lz_team_attach: null argument");
+    LZ_REQUIRE(local_index >= 0 && local_index < team->nlocal, "lz_team_attach: bad shard index");
+    LZ_REQUIRE(lower_rank >= -1 && lower_rank < team->world && upper_rank >= -1 && upper_rank < team->world,
+               "lz_team_attach: bad neighbour rank");
+    lz_shard& sh = team->shards[local_index];
+    sh.lower = lower_rank;
+    sh.upper = upper_rank;
+    sh.pc.world = team->world;
+    sh.pc.rank = sh.rank;
+    sh.pc.kmax = team->kmax;
+    for (int q = 0; q < team->world; ++q) {
+        LZ_REQUIRE(comm_ptrs[q], "lz_team_attach: exchange buffer of rank %d is null", q);
+        sh.comm[q] = comm_ptrs[q];
+        sh.pc.flags[q] = reinterpret_cast<unsigned long long*>((char*)comm_ptrs[q] + team->layout.flags_off);
+        sh.pc.slots[q] = reinterpret_cast<double*>((char*)comm_ptrs[q] + team->layout.slots_off);
+    }
+    return LZ_OK;
+}
+
+extern "C" int lz_team_lanczos_run(lz_team* team, lz_op* const* ops, const double* const* v0_dev,
+                                   int32_t n, const lz_run_opts* opts, double* alpha_host,
+                                   double* beta_host, double* const* V_dev, const int64_t* ldv,
+                                   double* row_scale_host, lz_run_info* info) {
+    LZ_REQUIRE(team && ops && v0_dev && opts, "lz_team_lanczos_run: null argument");
+    for (int s = 0; s < team->nlocal; ++s)
+        LZ_REQUIRE(team->shards[s].comm[team->shards[s].rank], "lz_team_lanczos_run: shard %d is not attached", s);
+    return run_loop(team, team->nlocal, ops, v0_dev, n, opts, alpha_host, beta_host, V_dev, ldv,
+                    row_scale_host, info);
+}
+
+extern "C" int lz_team_destroy(lz_team* team) {
+    delete team;
     return LZ_OK;
 }

@@ -104,7 +104,7 @@ constexpr int kCoefSmem = 2048;
 __global__ void __launch_bounds__(kThreads)
 cgs_update_kernel(const double* __restrict__ V, int64_t ldv, int nrows, const double* target,
                   const double* __restrict__ coef, const double* __restrict__ cself_p, double* out,
-                  int64_t M, int vec_ok, const int* __restrict__ flag) {
+                  int64_t M, int vec_ok, const int* __restrict__ flag, const HaloPush halo) {
     if (flag && *flag == 0) return;
     __shared__ double sc[kCoefSmem];
     const int ns = min(nrows, kCoefSmem);
@@ -142,12 +142,17 @@ cgs_update_kernel(const double* __restrict__ V, int64_t ldv, int nrows, const do
                 ay = fma(-c, v.y, ay);
             }
             st_stream2(out + 2 * i, make_double2(ax, ay));
+            if (halo.lo_dst && 2 * i < halo.plane) st_stream2(halo.lo_dst + 2 * i, make_double2(ax, ay));
+            if (halo.hi_dst && 2 * i >= M - halo.plane)
+                st_stream2(halo.hi_dst + (2 * i - (M - halo.plane)), make_double2(ax, ay));
         }
         if (tid == 0 && (M & 1)) {
             const int64_t i = M - 1;
             double a = cself * target[i];
             for (int r = 0; r < nrows; ++r) a = fma(-__ldg(coef + r), V[(int64_t)r * ldv + i], a);
             out[i] = a;
+            if (halo.lo_dst && i < halo.plane) halo.lo_dst[i] = a;
+            if (halo.hi_dst && i >= M - halo.plane) halo.hi_dst[i - (M - halo.plane)] = a;
         }
     } else {
         for (int64_t i = tid; i < M; i += nthr) {
@@ -157,18 +162,26 @@ cgs_update_kernel(const double* __restrict__ V, int64_t ldv, int nrows, const do
                 a = fma(-c, ld_stream1(V + (int64_t)r * ldv + i), a);
             }
             out[i] = a;
+            if (halo.lo_dst && i < halo.plane) halo.lo_dst[i] = a;
+            if (halo.hi_dst && i >= M - halo.plane) halo.hi_dst[i - (M - halo.plane)] = a;
         }
     }
 }
 
 int launch_cgs_update(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, const double* target,
                       const double* coef_dev, const double* cself_dev, double* out, int64_t M,
-                      const int* flag_dev) {
+                      const int* flag_dev, const HaloPush* halo) {
     const int64_t want = (M / 2 + kThreads - 1) / kThreads;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sms * 8));
-    const int vec_ok = ((((uintptr_t)V | (uintptr_t)target | (uintptr_t)out) & 15) == 0) && ((ldv & 1) == 0);
+    int vec_ok = ((((uintptr_t)V | (uintptr_t)target | (uintptr_t)out) & 15) == 0) && ((ldv & 1) == 0);
+    HaloPush h{};
+    if (halo && (halo->lo_dst || halo->hi_dst)) {
+        h = *halo;
+        vec_ok = vec_ok && (((uintptr_t)h.lo_dst | (uintptr_t)h.hi_dst) & 15) == 0 && ((h.plane & 1) == 0) &&
+                 ((M & 1) == 0);
+    }
     cgs_update_kernel<<<grid, kThreads, 0, ctx->stream>>>(V, ldv, nrows, target, coef_dev, cself_dev, out,
-                                                          M, vec_ok, flag_dev);
+                                                          M, vec_ok, flag_dev, h);
     LZ_CUDA(cudaGetLastError());
     return LZ_OK;
 }

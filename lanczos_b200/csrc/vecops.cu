@@ -47,13 +47,32 @@ int launch_dot(lz_ctx* ctx, const double* x, const double* y, int64_t M, double*
     return LZ_OK;
 }
 
+// Sharded runs: the first / last z-plane of the vector being produced is also stored straight
+// into the neighbouring GPUs' ghost buffers (NVLink peer stores), so that the halo exchange
+// costs no extra pass and no extra launch.
+template <bool HALO>
+__device__ __forceinline__ void halo_store2(const HaloPush& h, int64_t e, int64_t M, double2 v) {
+    if (HALO) {
+        if (h.lo_dst && e < h.plane) st_stream2(h.lo_dst + e, v);
+        if (h.hi_dst && e >= M - h.plane) st_stream2(h.hi_dst + (e - (M - h.plane)), v);
+    }
+}
+template <bool HALO>
+__device__ __forceinline__ void halo_store1(const HaloPush& h, int64_t e, int64_t M, double v) {
+    if (HALO) {
+        if (h.lo_dst && e < h.plane) h.lo_dst[e] = v;
+        if (h.hi_dst && e >= M - h.plane) h.hi_dst[e - (M - h.plane)] = v;
+    }
+}
+
 // out = w - ca*sa*a - cb*sb*b ;  b nullable.  ca/sa/cb/sb are device scalars (nullable => 1).
-template <bool HAS_B>
+template <bool HAS_B, bool HALO>
 __global__ void __launch_bounds__(kThreads)
 update_norm_kernel(const double* w, const double* __restrict__ a, const double* __restrict__ b,
                    const double* __restrict__ ca, const double* __restrict__ sa,
                    const double* __restrict__ cb, const double* __restrict__ sb,
-                   double* out, int64_t M, int vec_ok, double* __restrict__ partials) {
+                   double* out, int64_t M, int vec_ok, double* __restrict__ partials,
+                   const HaloPush halo) {
     __shared__ double red[kWarps];
     const double fa = (ca ? __ldg(ca) : 1.0) * (sa ? __ldg(sa) : 1.0);
     const double fb = HAS_B ? (cb ? __ldg(cb) : 1.0) * (sb ? __ldg(sb) : 1.0) : 0.0;
@@ -78,6 +97,8 @@ update_norm_kernel(const double* w, const double* __restrict__ a, const double* 
             }
             st_stream2(out + 2 * i, r0);
             st_stream2(out + 2 * i1, r1);
+            halo_store2<HALO>(halo, 2 * i, M, r0);
+            halo_store2<HALO>(halo, 2 * i1, M, r1);
             acc0 = fma(r0.x, r0.x, acc0); acc1 = fma(r0.y, r0.y, acc1);
             acc0 = fma(r1.x, r1.x, acc0); acc1 = fma(r1.y, r1.y, acc1);
         }
@@ -91,12 +112,14 @@ update_norm_kernel(const double* w, const double* __restrict__ a, const double* 
                 r0.x = fma(-fb, b0.x, r0.x); r0.y = fma(-fb, b0.y, r0.y);
             }
             st_stream2(out + 2 * i, r0);
+            halo_store2<HALO>(halo, 2 * i, M, r0);
             acc0 = fma(r0.x, r0.x, acc0); acc1 = fma(r0.y, r0.y, acc1);
         }
         if (tid == 0 && (M & 1)) {
             double r = fma(-fa, a[M - 1], w[M - 1]);
             if (HAS_B) r = fma(-fb, b[M - 1], r);
             out[M - 1] = r;
+            halo_store1<HALO>(halo, M - 1, M, r);
             acc0 = fma(r, r, acc0);
         }
     } else {
@@ -104,6 +127,7 @@ update_norm_kernel(const double* w, const double* __restrict__ a, const double* 
             double r = fma(-fa, ld_stream1(a + i), w[i]);
             if (HAS_B) r = fma(-fb, ld_stream1(b + i), r);
             out[i] = r;
+            halo_store1<HALO>(halo, i, M, r);
             acc0 = fma(r, r, acc0);
         }
     }
@@ -113,17 +137,42 @@ update_norm_kernel(const double* w, const double* __restrict__ a, const double* 
 
 int launch_update_norm(lz_ctx* ctx, const double* w, const double* a, const double* b,
                        const double* ca_dev, const double* sa_dev, const double* cb_dev,
-                       const double* sb_dev, double* out, int64_t M, double* partials, int* nparts) {
+                       const double* sb_dev, double* out, int64_t M, double* partials, int* nparts,
+                       const HaloPush* halo) {
     const int grid = stream_grid(ctx, M, 4);
-    const int vec_ok = (((uintptr_t)w | (uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0;
-    if (b)
-        update_norm_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(w, a, b, ca_dev, sa_dev, cb_dev, sb_dev,
-                                                                    out, M, vec_ok, partials);
-    else
-        update_norm_kernel<false><<<grid, kThreads, 0, ctx->stream>>>(w, a, nullptr, ca_dev, sa_dev, nullptr,
-                                                                     nullptr, out, M, vec_ok, partials);
+    HaloPush h{};
+    const bool push = halo && (halo->lo_dst || halo->hi_dst);
+    if (push) h = *halo;
+    int vec_ok = (((uintptr_t)w | (uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0;
+    if (push) vec_ok = vec_ok && (((uintptr_t)h.lo_dst | (uintptr_t)h.hi_dst) & 15) == 0 &&
+                       ((h.plane & 1) == 0) && ((M & 1) == 0);
+#define LZ_UPD(HB, HL, bb, cbb, sbb)                                                               \
+    update_norm_kernel<HB, HL><<<grid, kThreads, 0, ctx->stream>>>(w, a, bb, ca_dev, sa_dev, cbb, sbb, \
+                                                                   out, M, vec_ok, partials, h)
+    if (b) { if (push) LZ_UPD(true, true, b, cb_dev, sb_dev); else LZ_UPD(true, false, b, cb_dev, sb_dev); }
+    else { if (push) LZ_UPD(false, true, nullptr, nullptr, nullptr); else LZ_UPD(false, false, nullptr, nullptr, nullptr); }
+#undef LZ_UPD
     LZ_CUDA(cudaGetLastError());
     if (nparts) *nparts = grid;
+    return LZ_OK;
+}
+
+// plain halo publication of an existing vector (start vector / first row)
+__global__ void __launch_bounds__(kThreads)
+halo_push_kernel(const double* __restrict__ x, int64_t M, const HaloPush h) {
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * kThreads;
+    for (int64_t e = tid; e < h.plane; e += nthr) {
+        if (h.lo_dst) h.lo_dst[e] = x[e];
+        if (h.hi_dst) h.hi_dst[e] = x[M - h.plane + e];
+    }
+}
+
+int launch_halo_push(lz_ctx* ctx, const double* x, int64_t M, const HaloPush* halo) {
+    if (!halo || !(halo->lo_dst || halo->hi_dst)) return LZ_OK;
+    const int grid = stream_grid(ctx, halo->plane, 1);
+    halo_push_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, M, *halo);
+    LZ_CUDA(cudaGetLastError());
     return LZ_OK;
 }
 

@@ -1,0 +1,365 @@
+"""Row-sharded (multi-GPU) Lanczos: host-side plan and plumbing.
+
+Vectors and the Krylov basis are split into contiguous row blocks, one per GPU; for structured
+grids with the reference's index map i = x + nx*(y + ny*z) (Hamiltonian.py:73-76) contiguous
+blocks are z-slabs (y-slabs of a 2-D grid, segments of a 1-D grid).  The exchange itself - halo
+planes and the scalar sums - happens inside the CUDA kernels over NVLink peer memory
+(csrc/peer.cuh); this module only decides who owns what, allocates the exchange buffers, swaps
+their cudaIpc handles through torch.distributed, and calls lz_team_lanczos_run.
+
+    torchrun --nproc-per-node 8 ...:   TeamLanczos(StencilOperator(...))        one process per GPU
+    single process, several shards:    LocalTeamLanczos(op, world=4, devices=[0, 0, 0, 0])
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi, engine
+from ._capi import LanczosBreakdown, RunInfo, RunOpts
+from .engine import Context, StencilOperator, padded_ld
+
+
+# --------------------------------------------------------------------------- the plan (pure host)
+@dataclass
+class SlabPlan:
+    """Who owns which slab.  The sharded axis is the slowest grid axis; it is presented to the
+    kernels as z (a 2-D grid (nx, ny) becomes (nx, 1, ny), a 1-D grid (nx,) becomes (1, 1, nx))."""
+    grid: tuple
+    world: int
+    periodic: bool
+
+    def __post_init__(self):
+        g = tuple(int(x) for x in self.grid)
+        if len(g) == 1:
+            self.grid3 = (1, 1, g[0])
+        elif len(g) == 2:
+            self.grid3 = (g[0], 1, g[1])
+        elif len(g) == 3:
+            self.grid3 = g
+        else:
+            raise ValueError("1, 2 or 3 grid dimensions")
+        nz = self.grid3[2]
+        if self.world < 1 or self.world > nz:
+            raise ValueError(f"cannot split {nz} slabs over {self.world} ranks")
+        base, extra = divmod(nz, self.world)
+        self.counts = [base + (1 if r < extra else 0) for r in range(self.world)]
+        self.starts = [sum(self.counts[:r]) for r in range(self.world)]
+        self.plane = self.grid3[0] * self.grid3[1]
+        self.M = self.plane * nz
+
+    def off3(self, off: Sequence[float]):
+        o = tuple(float(x) for x in off)
+        if len(o) == 1:
+            return (0.0, 0.0, o[0])
+        if len(o) == 2:
+            return (o[0], 0.0, o[1])
+        return o
+
+    def slab(self, rank: int):
+        """(z0, z1) planes owned by `rank`."""
+        return self.starts[rank], self.starts[rank] + self.counts[rank]
+
+    def rows(self, rank: int):
+        """[row0, row1) of the global vector owned by `rank`."""
+        z0, z1 = self.slab(rank)
+        return z0 * self.plane, z1 * self.plane
+
+    def local_rows(self, rank: int) -> int:
+        return self.counts[rank] * self.plane
+
+    def neighbours(self, rank: int):
+        """(lower, upper) ranks owning the plane below / above the slab; -1 at a Dirichlet wall.
+        With a single rank and periodic boundaries the slab is its own neighbour."""
+        lo, up = rank - 1, rank + 1
+        if lo < 0:
+            lo = self.world - 1 if self.periodic else -1
+        if up >= self.world:
+            up = 0 if self.periodic else -1
+        return lo, up
+
+    def halo_planes(self, rank: int):
+        """Global z indices of the two ghost planes of `rank` (None at a wall) - the contract the
+        kernels implement, used by the CPU tests."""
+        z0, z1 = self.slab(rank)
+        nz = self.grid3[2]
+        lo = z0 - 1 if z0 > 0 else (nz - 1 if self.periodic else None)
+        up = z1 if z1 < nz else (0 if self.periodic else None)
+        return lo, up
+
+
+# --------------------------------------------------------------------------- device side
+class _Shard:
+    def __init__(self, ctx: Context, rank: int):
+        self.ctx, self.rank = ctx, rank
+        self.comm_ptr = None
+        self.opened = {}
+        self.op_handle = None
+        self.keep = ()
+
+
+class _TeamBase:
+    """Shared driver: subclasses provide the shards and the mapped exchange buffers."""
+
+    def __init__(self, H: StencilOperator, world: int):
+        if not isinstance(H, StencilOperator):
+            raise TypeError("row-sharded runs take a StencilOperator (sparse operators: single GPU for now)")
+        self.H = H
+        self.world = int(world)
+        self.plan = SlabPlan(H.grid, self.world, H.bc == "periodic")
+        self.M = self.plan.M
+        self.lib = _capi.load()
+        self.team = None
+        self.max_steps = 0
+        self.Lanczos_has_been_executed = False
+        self._results = None
+
+    # subclasses: self.shards (list of _Shard), self._map_buffers(nbytes) -> per-shard list of `world` pointers
+    def _ensure_team(self, n: int):
+        if self.team is not None and n <= self.max_steps:
+            return
+        self._destroy_team()
+        max_steps = max(int(n), 128)
+        nbytes = C.c_int64()
+        # a single shard wraps periodic boundaries inside its own vector: no ghost planes
+        plane = self.plan.plane if self.world > 1 else 0
+        _capi.check(self.lib.lz_comm_bytes(self.world, max_steps, plane, 0, C.byref(nbytes)))
+        tables = self._map_buffers(nbytes.value)
+        nl = len(self.shards)
+        ranks = (C.c_int * nl)(*[s.rank for s in self.shards])
+        ctxs = (C.c_void_p * nl)(*[s.ctx.handle for s in self.shards])
+        h = C.c_void_p()
+        _capi.check(self.lib.lz_team_create(self.world, nl, ranks, ctxs, self.M, max_steps, plane, 0, C.byref(h)))
+        self.team = h
+        self.max_steps = max_steps
+        for i, s in enumerate(self.shards):
+            ptrs = (C.c_void_p * self.world)(*tables[i])
+            lo, up = self.plan.neighbours(s.rank)
+            if self.world == 1:
+                lo = up = -1
+            _capi.check(self.lib.lz_team_attach(self.team, i, ptrs, lo, up))
+        self._make_ops()
+
+    def _make_ops(self):
+        torch = engine._torch()
+        H, plan = self.H, self.plan
+        off3 = plan.off3(H.off)
+        for s in self.shards:
+            z0, z1 = plan.slab(s.rank)
+            shape = (C.c_int64 * 3)(plan.grid3[0], plan.grid3[1], z1 - z0)
+            off = (C.c_double * 3)(*off3)
+            diag_t, diag_p = None, C.c_void_p(0)
+            if H.diag is not None:
+                r0, r1 = plan.rows(s.rank)
+                if isinstance(H.diag, torch.Tensor):
+                    diag_t = H.diag.reshape(-1)[r0:r1].to(device=s.ctx.torch_device, dtype=torch.float64).contiguous()
+                else:
+                    diag_t = torch.from_numpy(np.ascontiguousarray(np.asarray(H.diag, dtype=np.float64).reshape(-1)[r0:r1])).to(s.ctx.torch_device)
+                diag_p = C.c_void_p(diag_t.data_ptr())
+            h = C.c_void_p()
+            bc = _capi.LZ_BC_PERIODIC if H.bc == "periodic" else _capi.LZ_BC_DIRICHLET
+            _capi.check(self.lib.lz_op_stencil_create(s.ctx.handle, 3, shape, bc, float(H.center), off, diag_p, C.byref(h)))
+            s.op_handle = h
+            s.keep = (diag_t,)
+
+    def _destroy_team(self):
+        if getattr(self, "team", None):
+            for s in self.shards:
+                if s.op_handle:
+                    self.lib.lz_op_destroy(s.op_handle)
+                    s.op_handle = None
+            self.lib.lz_team_destroy(self.team)
+            self.team = None
+            self._unmap_buffers()
+
+    def __del__(self):
+        try:
+            self._destroy_team()
+        except Exception:
+            pass
+
+    # ---- the loop ---------------------------------------------------------------------------------
+    def _local_start_vectors(self, seed, v0):
+        """Per local shard: a CUDA tensor with the shard's rows of the start vector.  `v0` may be
+        None (the reference's seeded global vector, Lanczos.py:93-97, sliced), a global host array,
+        or a list of per-shard CUDA tensors / one CUDA tensor (single local shard)."""
+        torch = engine._torch()
+        out = []
+        if v0 is None or isinstance(v0, np.ndarray) or (isinstance(v0, (list, tuple)) and np.isscalar(v0[0])):
+            full = engine.start_vector(self.M, seed, v0)
+            for s in self.shards:
+                r0, r1 = self.plan.rows(s.rank)
+                out.append(torch.from_numpy(np.ascontiguousarray(full[r0:r1])).to(s.ctx.torch_device))
+            return out
+        np.random.seed(seed)
+        vs = list(v0) if isinstance(v0, (list, tuple)) else [v0]
+        if len(vs) != len(self.shards):
+            raise ValueError("one start-vector shard per local shard")
+        for s, v in zip(self.shards, vs):
+            t = v.to(device=s.ctx.torch_device, dtype=torch.float64).contiguous().reshape(-1)
+            if t.numel() != self.plan.local_rows(s.rank):
+                raise ValueError(f"shard of rank {s.rank} must have {self.plan.local_rows(s.rank)} rows")
+            out.append(t)
+        return out
+
+    def execute_Lanczos(self, n, seed=99, use_cuda=True, v0=None, *, reorth="full", cgs_passes=1,
+                        ref_compat=True, keep_basis=True, breakdown_tol=0.0, select_tol=0.0,
+                        profile=False, **_ignored):
+        torch = engine._torch()
+        n = int(n)
+        if n > self.M:
+            raise ValueError("n cannot be larger than M!")
+        if ref_compat and n < 2:
+            raise IndexError("index -1 is out of bounds for axis 0 with size 0")
+        self._ensure_team(n)
+        self._results = None
+        self.Lanczos_has_been_executed = False
+        mode = engine._REORTH[reorth]
+        need_basis = keep_basis or mode != _capi.LZ_REORTH_NONE
+        starts = self._local_start_vectors(seed, v0)
+        nl = len(self.shards)
+        Vs, lds = [], []
+        for s in self.shards:
+            ld = padded_ld(self.plan.local_rows(s.rank))
+            lds.append(ld)
+            with torch.cuda.device(s.ctx.device):
+                Vs.append(torch.empty((n, ld), dtype=torch.float64, device=s.ctx.torch_device) if need_basis else None)
+        alpha, beta, scale = np.zeros(n), np.zeros(max(n - 1, 0)), np.ones(n)
+        opts = RunOpts(mode, int(cgs_passes), 1 if ref_compat else 0, 1 if profile else 0,
+                       float(breakdown_tol), float(select_tol))
+        info = RunInfo()
+        ops = (C.c_void_p * nl)(*[s.op_handle for s in self.shards])
+        v0p = (C.c_void_p * nl)(*[t.data_ptr() for t in starts])
+        Vp = (C.c_void_p * nl)(*[(V.data_ptr() if V is not None else 0) for V in Vs])
+        ldp = (C.c_int64 * nl)(*lds)
+        for s in self.shards:          # inputs were produced on torch's streams
+            torch.cuda.synchronize(s.ctx.device)
+        status = self.lib.lz_team_lanczos_run(
+            self.team, ops, v0p, n, C.byref(opts), alpha.ctypes.data_as(C.c_void_p),
+            beta.ctypes.data_as(C.c_void_p), Vp, ldp, scale.ctypes.data_as(C.c_void_p), C.byref(info))
+        if status == _capi.LZ_ERR_BREAKDOWN:
+            raise LanczosBreakdown(self.lib.lz_last_error().decode(), steps_done=info.steps_done)
+        _capi.check(status)
+        self.n = n
+        self._results = [engine.LanczosResult(s.ctx, n, self.plan.local_rows(s.rank), alpha, beta, V, ld,
+                                              scale.copy(), info)
+                         for s, V, ld in zip(self.shards, Vs, lds)]
+        self._H_eff = self._results[0].tridiagonal()
+        self.Lanczos_has_been_executed = True
+
+    execute_LanczosOld = execute_Lanczos
+
+    @property
+    def result(self):
+        if not self.Lanczos_has_been_executed:
+            raise ValueError("Lanczos Algorithm has not been called.")
+        return self._results[0]
+
+    @property
+    def results(self):
+        if not self.Lanczos_has_been_executed:
+            raise ValueError("Lanczos Algorithm has not been called.")
+        return self._results
+
+    @property
+    def H_eff(self):
+        if not self.Lanczos_has_been_executed:
+            raise ValueError("Lanczos Algorithm has not been called.")
+        return self._H_eff
+
+    def ritz_values(self, k=None):
+        theta = np.linalg.eigvalsh(self.H_eff)
+        return theta if k is None else theta[:k]
+
+    @property
+    def M_local(self):
+        return self.plan.local_rows(self.shards[0].rank)
+
+
+class LocalTeamLanczos(_TeamBase):
+    """All `world` shards driven by this process: on one GPU (tests of the exchange logic - the
+    kernels of different shards then run one after the other, push phase before combine phase) or
+    on several GPUs (`devices`)."""
+
+    def __init__(self, H: StencilOperator, world: int, devices: Optional[List[int]] = None):
+        super().__init__(H, world)
+        torch = engine._torch()
+        if devices is None:
+            devices = [torch.cuda.current_device()] * self.world
+        if len(devices) != self.world:
+            raise ValueError("one device per shard")
+        # one context (own partials / workspace arena) per shard, even on a shared device
+        self.shards = [_Shard(Context(d), r) for r, d in enumerate(devices)]
+
+    def _map_buffers(self, nbytes):
+        ptrs = []
+        for s in self.shards:
+            p = C.c_void_p()
+            _capi.check(self.lib.lz_comm_alloc(s.ctx.handle, nbytes, C.byref(p), None))
+            s.comm_ptr = p
+            ptrs.append(p.value)
+        return [list(ptrs) for _ in self.shards]
+
+    def _unmap_buffers(self):
+        for s in self.shards:
+            if s.comm_ptr:
+                self.lib.lz_comm_free(s.ctx.handle, s.comm_ptr)
+                s.comm_ptr = None
+
+    def basis_rows_host(self):
+        """(n, M) host array assembled from the shards (tests)."""
+        parts = [r.basis_rows_host() for r in self.results]
+        return np.concatenate(parts, axis=1)
+
+
+class TeamLanczos(_TeamBase):
+    """One process per GPU (torchrun): this process drives the shard of its rank; exchange
+    buffers of the other ranks are mapped through cudaIpc handles swapped over torch.distributed."""
+
+    def __init__(self, H: StencilOperator, rank: Optional[int] = None, world: Optional[int] = None, device=None):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("TeamLanczos needs an initialised torch.distributed process group")
+        self.dist = dist
+        rank = dist.get_rank() if rank is None else rank
+        world = dist.get_world_size() if world is None else world
+        super().__init__(H, world)
+        self.rank = rank
+        self.shards = [_Shard(Context.default(device), rank)]
+
+    def _map_buffers(self, nbytes):
+        s = self.shards[0]
+        p = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        _capi.check(self.lib.lz_comm_alloc(s.ctx.handle, nbytes, C.byref(p), handle))
+        s.comm_ptr = p
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, bytes(handle))
+        ptrs = []
+        for q in range(self.world):
+            if q == self.rank:
+                ptrs.append(p.value)
+                continue
+            buf = (C.c_ubyte * 64).from_buffer_copy(handles[q])
+            mapped = C.c_void_p()
+            _capi.check(self.lib.lz_comm_open(s.ctx.handle, buf, C.byref(mapped)))
+            s.opened[q] = mapped
+            ptrs.append(mapped.value)
+        self.dist.barrier()
+        return [ptrs]
+
+    def _unmap_buffers(self):
+        s = self.shards[0]
+        for q, mapped in list(s.opened.items()):
+            self.lib.lz_comm_close(s.ctx.handle, mapped)
+        s.opened = {}
+        try:
+            self.dist.barrier()        # nobody frees while a peer still has the buffer mapped
+        except Exception:
+            pass
+        if s.comm_ptr:
+            self.lib.lz_comm_free(s.ctx.handle, s.comm_ptr)
+            s.comm_ptr = None

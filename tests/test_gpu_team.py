@@ -1,0 +1,149 @@
+"""Row-sharded solves on the GPU.  With one device the P shards are driven by one process
+(LocalTeamLanczos: same kernels, same peer-memory exchange, push phase before combine phase);
+with >= 2 devices the same test also runs across real GPUs, and through one process per GPU
+(TeamLanczos, NCCL only for the handle swap)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import lanczos_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lz():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import lanczos_b200
+    return lanczos_b200
+
+
+def rel(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(b), 1e-300))
+
+
+CASES = [
+    ((16, 12, 20), "periodic", 4, "full", 1),
+    ((16, 12, 10), "dirichlet", 3, "full", 1),        # uneven slabs 4/3/3
+    ((16, 12, 9), "periodic", 2, "full", 2),
+    ((18, 7, 8), "periodic", 8, "none", 1),           # one plane per shard
+    ((40, 36), "periodic", 4, "full", 1),             # 2-D: y-slabs
+    ((40, 36), "dirichlet", 3, "selective", 2),
+    ((15, 6, 8), "periodic", 2, "full", 1),           # odd nx: scalar path, odd plane
+    ((257,), "dirichlet", 4, "full", 1),              # 1-D segments
+]
+
+
+@pytest.mark.parametrize("grid,bc,world,reorth,passes", CASES)
+def test_local_team_matches_single_gpu(lz, grid, bc, world, reorth, passes):
+    from lanczos_b200.team import LocalTeamLanczos
+    dim = len(grid)
+    op = lz.StencilOperator(grid, 2.0 * dim + 0.25, [-1.0, -0.8, -1.1][:dim], bc=bc)
+    n = 24
+    one = lz.Lanczos(op)
+    one.execute_Lanczos(n, seed=7, reorth=reorth, cgs_passes=passes)
+    team = LocalTeamLanczos(op, world)
+    team.execute_Lanczos(n, seed=7, reorth=reorth, cgs_passes=passes)
+    a1, b1 = np.diag(one.H_eff), np.diag(one.H_eff, 1)
+    a2, b2 = np.diag(team.H_eff), np.diag(team.H_eff, 1)
+    tol = 1e-12 if reorth != "none" else 1e-9
+    assert rel(a2, a1) < tol
+    assert rel(b2, b1) < tol
+    # and against the oracle when the run follows the reference (full reorth)
+    if reorth == "full" and passes == 1:
+        H = orc.laplacian_csr(grid, 2.0 * dim + 0.25, [-1.0, -0.8, -1.1][:dim], periodic=(bc == "periodic"))
+        ref = orc.lanczos(H, n, seed=7)
+        assert rel(a2, ref["alpha"]) < 1e-12
+        assert rel(b2, ref["beta"]) < 1e-12
+        V = team.basis_rows_host()
+        assert np.max(np.abs(V - ref["V"].T)) < 1e-12
+
+
+def test_local_team_with_potential_and_clean_start(lz):
+    from lanczos_b200.team import LocalTeamLanczos
+    H, c, o, pot = orc.deuteron_hamiltonian(12)
+    op = lz.StencilOperator((12, 12, 12), c, o, diag=pot)
+    one = lz.Lanczos(op)
+    one.execute_Lanczos(40, seed=78)
+    team = LocalTeamLanczos(op, 3)
+    team.execute_Lanczos(40, seed=78)
+    assert rel(np.diag(team.H_eff), np.diag(one.H_eff)) < 1e-12
+    assert rel(np.diag(team.H_eff, 1), np.diag(one.H_eff, 1)) < 1e-12
+    v0 = orc.start_vector(12 ** 3, seed=5)
+    one.execute_Lanczos(16, v0=v0, ref_compat=False)
+    team.execute_Lanczos(16, v0=v0, ref_compat=False)
+    assert rel(np.diag(team.H_eff), np.diag(one.H_eff)) < 1e-12
+    V = team.basis_rows_host()
+    assert np.max(np.abs(V[0] - v0)) < 1e-15
+
+
+def test_team_results_identical_on_every_shard_and_reproducible(lz):
+    from lanczos_b200.team import LocalTeamLanczos
+    op = lz.StencilOperator((32, 16, 24), 6.0, -1.0)
+    team = LocalTeamLanczos(op, 4)
+    team.execute_Lanczos(20, seed=3)
+    T1 = team.H_eff.copy()
+    team.execute_Lanczos(20, seed=3)
+    assert np.array_equal(T1, team.H_eff)          # rank-ordered sums: bit-reproducible
+
+
+def test_multi_device_single_process(lz):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from lanczos_b200.team import LocalTeamLanczos
+    op = lz.StencilOperator((64, 32, 48), 6.0, -1.0)
+    one = lz.Lanczos(op)
+    one.execute_Lanczos(30, seed=7)
+    ndev = torch.cuda.device_count()
+    team = LocalTeamLanczos(op, ndev, devices=list(range(ndev)))
+    team.execute_Lanczos(30, seed=7)
+    assert rel(np.diag(team.H_eff), np.diag(one.H_eff)) < 1e-12
+    assert rel(np.diag(team.H_eff, 1), np.diag(one.H_eff, 1)) < 1e-12
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _rank_main(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import lanczos_b200 as lz
+        from lanczos_b200.team import TeamLanczos
+        op = lz.StencilOperator((64, 32, 48), 6.0, -1.0)
+        t = TeamLanczos(op)
+        t.execute_Lanczos(30, seed=7)
+        t.execute_Lanczos(30, seed=7, reorth="selective", cgs_passes=2)
+        if rank == 0:
+            np.save(out, t.H_eff)
+        del t
+    finally:
+        dist.destroy_process_group()
+
+
+def test_one_process_per_gpu(lz, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    out = str(tmp_path / "T.npy")
+    mp.spawn(_rank_main, args=(world, _free_port(), out), nprocs=world, join=True)
+    T = np.load(out)
+    one = lz.Lanczos(lz.StencilOperator((64, 32, 48), 6.0, -1.0))
+    one.execute_Lanczos(30, seed=7, reorth="selective", cgs_passes=2)
+    assert rel(np.diag(T), np.diag(one.H_eff)) < 1e-11
