@@ -370,7 +370,9 @@ def main():
                     "frac_of_8TBs_nominal": pk["achieved_gbs"] / 8000.0}
     step_bytes = apply_bytes + 32.0 * N
     ms_per_step = ms_dev / K
-    value = K / (ms_dev / 1e3)
+    # whole-job aggregate: every rank advances its own 512^3-unknown shard K steps (weak scaling),
+    # so the job processes world*K shard-steps; at N = 1 this is plain Lanczos steps/s.
+    value = world * K / (ms_dev / 1e3)
     fused = {"alg_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / ms_per_step / 1e6 if reorths == 0 else None,
              "frac_of_measured_peak": step_bytes / ms_per_step / 1e6 / peak if reorths == 0 else None,
              "frac_of_8TBs_nominal": step_bytes / ms_per_step / 1e6 / 8000.0 if reorths == 0 else None,
@@ -383,8 +385,11 @@ def main():
         "config": {"workload": f"{args.workload}: {wl['desc']}", "grid": list(grid), "unknowns": M_total,
                    "unknowns_per_gpu": M_local, "lanczos_m": chunks, "reorth": wl["reorth"],
                    "cgs_passes": wl["cgs_passes"], "l2": "inputs larger than L2 (each vector %.2f GB)" % (8 * M_local / 1e9),
-                   "sharding": "z-slabs, one process per GPU" if world > 1 else "single GPU"},
-        "e2e": {"value": K / e_wall, "unit": UNIT, "h2d_bytes_per_step": 8.0 * M_local * len(chunks) / K,
+                   "sharding": "z-slabs, one process per GPU" if world > 1 else "single GPU",
+                   "aggregate": "value = n_gpus * K / time: each GPU advances its 512^3 shard K steps; "
+                                "the global (n_gpus x larger) solve advances K steps",
+                   "global_steps_per_sec": K / (ms_dev / 1e3)},
+        "e2e": {"value": world * K / e_wall, "unit": UNIT, "h2d_bytes_per_step": 8.0 * M_local * len(chunks) / K,
                 "d2h_bytes_per_step": (sum(3 * (8 * (c + 2) + 512) + 32 for c in chunks)) / K,
                 "wall_s": e_wall},
         "gpu_launches": launches,
