@@ -29,15 +29,17 @@ class LanczosBreakdown(ArithmeticError):
 
 class RunOpts(C.Structure):
     _fields_ = [("reorth", C.c_int32), ("cgs_passes", C.c_int32), ("ref_compat", C.c_int32),
-                ("profile", C.c_int32), ("breakdown_tol", C.c_double), ("select_tol", C.c_double)]
+                ("profile", C.c_int32), ("step_kernel", C.c_int32), ("reserved", C.c_int32),
+                ("breakdown_tol", C.c_double), ("select_tol", C.c_double)]
 
 
 class RunInfo(C.Structure):
     _fields_ = [("steps_done", C.c_int32), ("reorth_count", C.c_int32), ("launches", C.c_int32),
                 ("apply_launches", C.c_int32), ("update_launches", C.c_int32),
                 ("dots_launches", C.c_int32), ("gsupd_launches", C.c_int32),
+                ("fused_launches", C.c_int32),
                 ("gpu_ms", C.c_float), ("apply_ms", C.c_float), ("update_ms", C.c_float),
-                ("dots_ms", C.c_float), ("gsupd_ms", C.c_float)]
+                ("dots_ms", C.c_float), ("gsupd_ms", C.c_float), ("fused_ms", C.c_float)]
 
 
 _vp, _i32, _i64, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double

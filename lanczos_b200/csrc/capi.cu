@@ -20,19 +20,19 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 
 int launch_stencil_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
-                             double* partials, int* nparts);
+                             double* partials, int* nparts, const int* flag_dev);
 int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double* y, double* partials,
-                    int* nparts);
+                    int* nparts, const int* flag_dev);
 int build_csr(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const int32_t* indices,
               const double* data);
 int build_sell(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const int32_t* indices,
                const double* data, int sigma);
 
 int launch_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y, double* partials,
-                     int* nparts, int* launches) {
+                     int* nparts, int* launches, const int* flag_dev) {
     if (launches) *launches = 1;
-    if (op->kind == LZ_OP_STENCIL) return launch_stencil_apply_dot(op, x, scale_dev, y, partials, nparts);
-    return launch_spmv_dot(op, x, scale_dev, y, partials, nparts);
+    if (op->kind == LZ_OP_STENCIL) return launch_stencil_apply_dot(op, x, scale_dev, y, partials, nparts, flag_dev);
+    return launch_spmv_dot(op, x, scale_dev, y, partials, nparts, flag_dev);
 }
 
 // sum of np partials -> out[0] (one CTA, fixed order)

@@ -59,6 +59,7 @@ struct lz_op {
     lz_stencil st;
     lz_csr csr;
     lz_sell sell;
+    int fused_per_sm = 0;          // cached occupancy of the fused step kernel
     // host copy of the CSR arrays is NOT kept; export reads them back from the device.
 };
 
@@ -76,7 +77,13 @@ struct HaloPush {
 // `scale_dev` (nullable => 1) points at a device double.  `partials` has room for
 // kMaxPartials doubles; *nparts receives the number written.
 int launch_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
-                     double* partials, int* nparts, int* launches);
+                     double* partials, int* nparts, int* launches, const int* flag_dev = nullptr);
+
+// ---- single-pass fused step (fused.cu) ---------------------------------------------------
+bool fused_step_supported(const lz_op* op);
+int launch_fused_step(lz_op* op, const double* u, const double* rj, const double* rjm1,
+                      const double* s_j, const double* alpha_j, const double* beta_j, const double* s_jm1,
+                      double* out_r, double* out_u, double* partials, int* nparts);
 
 // ---- streaming vector kernels (vecops.cu) ------------------------------------------------
 // partials[cta] = sum x*y

@@ -51,13 +51,14 @@ struct RunState {          // all device pointers
                            // [2] reorth count, [3] force-next flag, [4] peer timeout
 };
 
-enum { FIN_V0NORM = 0, FIN_ALPHA = 1, FIN_BETA = 2 };
+enum { FIN_V0NORM = 0, FIN_ALPHA = 1, FIN_BETA = 2, FIN_ALPHA_S2 = 3 };
 
 // One scalar: CTA partials -> local sum -> (sharded) sum over ranks -> bookkeeping by `kind`.
 __global__ void __launch_bounds__(kThreads)
 fin_scalar_kernel(const double* __restrict__ partials, int np, RunState st, PeerComm pc,
                   unsigned long long seq, int mode, int kind, double* out, int jn, double tol_rel,
-                  const double* __restrict__ magnitude) {
+                  const double* __restrict__ magnitude, const int* __restrict__ flag) {
+    if (flag && *flag == 0) return;
     __shared__ double red[kWarps];
     double s = 0.0;
     if (mode != LZ_XCHG_COMBINE) s = cta_sum_partials(partials, np, red);
@@ -77,6 +78,9 @@ fin_scalar_kernel(const double* __restrict__ partials, int np, RunState st, Peer
         if (!(nrm > 0.0) && st.flags[0] < 0) st.flags[0] = 0;
     } else if (kind == FIN_ALPHA) {
         out[0] = s;
+    } else if (kind == FIN_ALPHA_S2) {        // alpha_j = q_j.H q_j from un-normalised r_j, u_j = H r_j
+        const double sc = st.scale[jn];
+        out[0] = s * sc * sc;
     } else {
         const double b = sqrt(s);
         st.beta[jn] = b;
@@ -85,6 +89,25 @@ fin_scalar_kernel(const double* __restrict__ partials, int np, RunState st, Peer
         st.scale[jn] = (isfinite(b) && b > 0.0) ? 1.0 / b : 0.0;
         if (!ok && st.flags[0] < 0) st.flags[0] = jn;
     }
+}
+
+// Fin of the single-pass fused step: partials[0..g) = sum r^2, partials[g..2g) = sum r.u with
+// r = r_{jn}, u = H r_{jn}:  beta[jn] = |r|, scale[jn] = 1/beta, alpha[jn] = scale^2 * r.u
+__global__ void __launch_bounds__(kThreads)
+fin_fused_kernel(const double* __restrict__ partials, int g, RunState st, int jn, double tol_rel,
+                 const double* __restrict__ magnitude) {
+    __shared__ double red[kWarps];
+    const double srr = cta_sum_partials(partials, g, red);
+    const double sru = cta_sum_partials(partials + g, g, red);
+    if (threadIdx.x != 0) return;
+    const double b = sqrt(srr);
+    st.beta[jn] = b;
+    const double thresh = tol_rel * fabs(magnitude[0]);
+    const bool ok = isfinite(b) && (b > thresh) && (b > 0.0);
+    const double sc = (isfinite(b) && b > 0.0) ? 1.0 / b : 0.0;
+    st.scale[jn] = sc;
+    st.alpha[jn] = sru * sc * sc;
+    if (!ok && st.flags[0] < 0) st.flags[0] = jn;
 }
 
 // Non-ref start: beta[0] = |v0|, scale[0] = 1/|v0|.
@@ -312,6 +335,7 @@ struct ShardRun {           // per-shard state of one run
     int64_t ldv = 0;
     int64_t M = 0;
     double* w = nullptr;
+    double* w2 = nullptr;   // second work vector of the fused single-pass step
     double* ring = nullptr;
     int64_t ld_int = 0;
     double* gs_part = nullptr;
@@ -363,6 +387,15 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     LZ_REQUIRE(!team || n + 2 <= team->kmax, "lz_team_lanczos_run: n = %d exceeds the team's max_steps", n);
     const bool split = nl > 1;            // several shards driven by this process: push / combine phases
     const size_t nd = (size_t)n + 2;
+    // single-pass fused step KF: structured grid, one shard, steps that (normally) need no sweep
+    // (opt-in: measured on par with the two-pass step on B200, see fused.cu)
+    const bool fused = !team && nl == 1 && ops[0] && opts->step_kernel == 2 && reorth != LZ_REORTH_FULL &&
+                       n >= 2 && fused_step_supported(ops[0]);
+    if (opts->step_kernel == 2 && !fused) {
+        set_error("lz_lanczos_run: the fused single-pass step needs a 3-D structured grid with nx %% 64 == 0, "
+                  "ny %% 8 == 0 on one GPU and reorth != full");
+        return LZ_ERR_UNSUPPORTED;
+    }
 
     std::vector<ShardRun> R(nl);
     int64_t M_local = 0;
@@ -394,6 +427,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         r.ld_int = (r.M + 63) & ~(int64_t)63;
         const size_t vec_bytes = (size_t)r.ld_int * 8 + 512;
         size_t need = 16 * 512 + 6 * (nd * 8 + 512) + vec_bytes;
+        if (fused) need += vec_bytes;
         if (!r.V) need += 3 * vec_bytes;
         if (reorth != LZ_REORTH_NONE) need += (size_t)(n + 1) * kMaxPartials * 8 + 512;
         LZ_CHECK(arena_reserve(r.ctx, need));
@@ -411,6 +445,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         st.anorm = cv.take<double>(1);
         st.flags = cv.take<int>(8);
         r.w = cv.take<double>((size_t)r.ld_int);
+        r.w2 = fused ? cv.take<double>((size_t)r.ld_int) : nullptr;
         r.ring = r.V ? nullptr : cv.take<double>((size_t)r.ld_int * 3);
         r.gs_part = (reorth != LZ_REORTH_NONE) ? cv.take<double>((size_t)(n + 1) * kMaxPartials) : nullptr;
         r.om_cur = st.omega_a;
@@ -427,7 +462,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         r.kt.ctx = r.ctx;
         r.kt.on = (opts->profile != 0);
         if (r.kt.on) {   // create the pool outside the timed loop
-            while (r.ctx->event_pool.size() < (size_t)(2 * (2 + 2 * passes) * n + 8)) {
+            while (r.ctx->event_pool.size() < (size_t)(2 * (3 + 2 * passes) * n + 8)) {
                 cudaEvent_t e = nullptr;
                 LZ_CUDA(cudaEventCreate(&e));
                 r.ctx->event_pool.push_back(e);
@@ -441,7 +476,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     const double delta = opts->select_tol > 0.0 ? opts->select_tol : sqrt(eps);
     const double eps1 = eps * 1.5;      // noise floor of the omega recurrence
     const double psi = eps * sqrt(M_global);
-    enum { K_APPLY = 0, K_UPDATE = 1, K_DOTS = 2, K_GSUPD = 3, K_NKINDS = 4 };
+    enum { K_APPLY = 0, K_UPDATE = 1, K_DOTS = 2, K_GSUPD = 3, K_FUSED = 4, K_NKINDS = 5 };
 
     // run `fn(shard)` on every local shard, on its device
     auto each = [&](auto&& fn) -> int {
@@ -463,7 +498,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     auto fin_scalar = [&](int kind, auto&& out_of, int jn, double tol, auto&& mag_of) -> int {
         return exchange([&](ShardRun& r, unsigned long long seq, int mode) -> int {
             fin_scalar_kernel<<<1, kThreads, 0, r.ctx->stream>>>(r.ctx->partials, r.np, r.st, r.pc, seq, mode, kind,
-                                                                 out_of(r), jn, tol, mag_of(r));
+                                                                 out_of(r), jn, tol, mag_of(r), nullptr);
             ++launches;
             return LZ_OK;
         });
@@ -497,7 +532,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         LZ_CHECK(each([&](ShardRun& r) {
             bind_ghosts(team, r, 1);
             int l2 = 0;
-            const int rc = launch_apply_dot(r.op, r.v0, r.st.v0scale, r.w, r.ctx->partials, &r.np, &l2);
+            const int rc = launch_apply_dot(r.op, r.v0, r.st.v0scale, r.w, r.ctx->partials, &r.np, &l2, nullptr);
             launches += l2;
             return rc;
         }));
@@ -521,7 +556,64 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         LZ_CHECK(peer_sync(false));
     }
 
-    for (int j = 0; j < n; ++j) {
+    if (fused) {
+        ShardRun& r = R[0];
+        cudaStream_t q = r.ctx->stream;
+        const bool sel = (reorth == LZ_REORTH_SELECTIVE);
+        const int* flag = sel ? r.st.flags + 1 : nullptr;
+        PeerComm solo;                       // world = 1
+        double* ucur = r.w;
+        double* unxt = r.w2;
+        int l2 = 0;
+        // u_0 = H r_0 (un-normalised), alpha_0 = s_0^2 r_0.u_0
+        r.kt.begin(K_APPLY);
+        LZ_CHECK(launch_apply_dot(r.op, r.row(0), nullptr, ucur, r.ctx->partials, &r.np, &l2, nullptr));
+        r.kt.end();
+        launches += l2;
+        fin_scalar_kernel<<<1, kThreads, 0, q>>>(r.ctx->partials, r.np, r.st, solo, 0, LZ_XCHG_FUSED, FIN_ALPHA_S2,
+                                                 r.st.alpha, 0, 0.0, nullptr, nullptr);
+        ++launches;
+        for (int j = 0; j < n; ++j) {
+            if (sel && j > 0) {
+                // predicated on the device flag: sweep q_j, then recompute u_j = H q_j and alpha_j
+                for (int p = 0; p < passes; ++p) {
+                    r.kt.begin(K_DOTS);
+                    LZ_CHECK(launch_cgs_dots(r.ctx, r.V, r.ldv, j, r.row(j), r.M, r.gs_part, &r.ncg, flag));
+                    r.kt.end();
+                    fin_ip_kernel<<<1, kThreads, 0, q>>>(r.gs_part, r.ncg, j, 0, 0, r.st, solo, 0, LZ_XCHG_FUSED, flag,
+                                                         p == 0 ? 1 : 0);
+                    r.kt.begin(K_GSUPD);
+                    LZ_CHECK(launch_cgs_update(r.ctx, r.V, r.ldv, j, r.row(j), r.st.coef, r.st.cself, r.row(j), r.M,
+                                               flag, nullptr));
+                    r.kt.end();
+                    launches += 3;
+                }
+                LZ_CHECK(launch_apply_dot(r.op, r.row(j), nullptr, ucur, r.ctx->partials, &r.np, &l2, flag));
+                launches += l2;
+                fin_scalar_kernel<<<1, kThreads, 0, q>>>(r.ctx->partials, r.np, r.st, solo, 0, LZ_XCHG_FUSED,
+                                                         FIN_ALPHA_S2, r.st.alpha + j, j, 0.0, nullptr, flag);
+                ++launches;
+            }
+            if (j + 1 < n) {
+                r.kt.begin(K_FUSED);
+                LZ_CHECK(launch_fused_step(r.op, ucur, r.row(j), j > 0 ? r.row(j - 1) : nullptr, r.st.scale + j,
+                                           r.st.alpha + j, r.st.beta + j, j > 0 ? r.st.scale + j - 1 : nullptr,
+                                           r.row(j + 1), unxt, r.ctx->partials, &r.np));
+                r.kt.end();
+                fin_fused_kernel<<<1, kThreads, 0, q>>>(r.ctx->partials, r.np, r.st, j + 1, opts->breakdown_tol,
+                                                        r.st.alpha);
+                launches += 2;
+                std::swap(ucur, unxt);
+                if (sel) {
+                    omega_kernel<<<1, kThreads, 0, q>>>(r.st, j, r.om_cur, r.om_prev, delta, eps1, psi);
+                    ++launches;
+                    std::swap(r.om_cur, r.om_prev);
+                }
+            }
+        }
+    }
+
+    for (int j = 0; !fused && j < n; ++j) {
         const int par = j & 1;
         // ---- Gram-Schmidt sweeps of q_j against the rows before it ---------------------------
         const bool maybe_reorth = (reorth == LZ_REORTH_FULL) || (reorth == LZ_REORTH_SELECTIVE && j > 0);
@@ -566,7 +658,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
             bind_ghosts(team, r, par);
             int l2 = 0;
             r.kt.begin(K_APPLY);
-            const int rc = launch_apply_dot(r.op, r.row(j), r.st.scale + j, r.w, r.ctx->partials, &r.np, &l2);
+            const int rc = launch_apply_dot(r.op, r.row(j), r.st.scale + j, r.w, r.ctx->partials, &r.np, &l2, nullptr);
             r.kt.end();
             launches += l2;
             return rc;
@@ -622,8 +714,8 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     if (row_scale_host)
         for (int j = 0; j < n; ++j) row_scale_host[j] = h_scale[j];
     float ms = 0.f;
-    float kms[K_NKINDS] = {0, 0, 0, 0};
-    int kcnt[K_NKINDS] = {0, 0, 0, 0};
+    float kms[K_NKINDS] = {0, 0, 0, 0, 0};
+    int kcnt[K_NKINDS] = {0, 0, 0, 0, 0};
     for (int s = 0; s < nl; ++s) {
         ShardRun& r = R[s];
         if (nl > 1) LZ_CUDA(cudaSetDevice(r.ctx->device));
@@ -661,6 +753,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         info->update_ms = kms[K_UPDATE]; info->update_launches = kcnt[K_UPDATE];
         info->dots_ms = kms[K_DOTS];     info->dots_launches = kcnt[K_DOTS];
         info->gsupd_ms = kms[K_GSUPD];   info->gsupd_launches = kcnt[K_GSUPD];
+        info->fused_ms = kms[K_FUSED];   info->fused_launches = kcnt[K_FUSED];
     }
     return status;
 }

@@ -96,7 +96,8 @@ spmv_sell_dot_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __res
 }
 
 int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
-                    double* partials, int* nparts) {
+                    double* partials, int* nparts, const int* flag_dev) {
+    (void)flag_dev;   // predicated applies exist only on the structured-grid fused path
     lz_ctx* ctx = op->ctx;
     const int64_t cap = std::min<int64_t>((int64_t)ctx->sms * 8, kMaxPartials);
     if (op->kind == LZ_OP_CSR) {

@@ -27,6 +27,7 @@ struct StencilArgs {
     const double* zlo;    // plane below local plane 0 (nullptr: zero)
     const double* zhi;    // plane above local plane nz-1
     const double* scale;  // device scalar, nullptr: 1
+    const int* skip;      // device flag, nullptr or *skip != 0: run
     double* partials;
     int tiles_x, tiles_y, chunks_z, zc;
     int64_t nitems;
@@ -52,6 +53,7 @@ __device__ __forceinline__ void zero_vec(double (&v)[VEC]) {
 template <int VEC, bool HAS_Y, bool HAS_Z, bool HAS_DIAG>
 __global__ void __launch_bounds__(kThreads)
 stencil_apply_dot_kernel(const StencilArgs a) {
+    if (a.skip && *a.skip == 0) return;
     __shared__ double red[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double s = a.scale ? __ldg(a.scale) : 1.0;
@@ -165,7 +167,7 @@ static const void* pick_kernel(bool has_y, bool has_z, bool has_diag) {
 }
 
 int launch_stencil_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
-                             double* partials, int* nparts) {
+                             double* partials, int* nparts, const int* flag_dev) {
     const lz_stencil& st = op->st;
     lz_ctx* ctx = op->ctx;
     StencilArgs a;
@@ -174,7 +176,7 @@ int launch_stencil_apply_dot(lz_op* op, const double* x, const double* scale_dev
     a.plane = st.nx * st.ny;
     a.c = st.center; a.ox = st.offx; a.oy = st.offy; a.oz = st.offz;
     a.x = x; a.y = y; a.diag = st.diag;
-    a.scale = scale_dev; a.partials = partials;
+    a.scale = scale_dev; a.partials = partials; a.skip = flag_dev;
     const bool has_y = (st.offy != 0.0);
     const bool has_z = (st.offz != 0.0);
     if (st.sharded) {

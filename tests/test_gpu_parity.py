@@ -356,3 +356,61 @@ def test_large_grid_invariants(lz):
     L3 = lz.Lanczos(op)
     L3.execute_Lanczos(n, v0=v0, reorth="none", keep_basis=False)
     assert rel(np.diag(L2.H_eff), np.diag(L3.H_eff)) < 1e-11
+
+
+# ---- KF: the single-pass fused step (structured grids, nx % 64 == 0, ny % 8 == 0) ----------------
+
+@pytest.mark.parametrize("grid,bc", [((64, 16, 12), "periodic"), ((128, 8, 9), "dirichlet"), ((64, 24, 2), "periodic")])
+def test_fused_step_matches_two_pass_and_oracle(lz, grid, bc):
+    op = lz.StencilOperator(grid, 6.5, [-1.0, -0.7, -1.2], bc=bc)
+    H = orc.laplacian_csr(grid, 6.5, [-1.0, -0.7, -1.2], periodic=(bc == "periodic"))
+    n = 20
+    ref = orc.lanczos(H, n, seed=13)                  # full reorth; a Laplacian stays orthogonal anyway
+    runs = {}
+    for kern in ("two_pass", "fused"):
+        L = lz.Lanczos(op)
+        L.execute_Lanczos(n, seed=13, reorth="none", keep_basis=True, step_kernel=kern)
+        runs[kern] = (np.diag(L.H_eff).copy(), np.diag(L.H_eff, 1).copy(), L.V.copy(), L.result.kernel_ms)
+    a2, b2, V2, _ = runs["two_pass"]
+    af, bf, Vf, _ = runs["fused"]
+    assert rel(af, a2) < 1e-12 and rel(bf, b2) < 1e-12
+    assert rel(af, ref["alpha"]) < 1e-10 and rel(bf, ref["beta"]) < 1e-10
+    assert np.max(np.abs(Vf - V2)) < 1e-12
+    # ring mode (no basis kept)
+    L = lz.Lanczos(op)
+    L.execute_Lanczos(n, seed=13, reorth="none", keep_basis=False, step_kernel="fused")
+    assert rel(np.diag(L.H_eff), af) < 1e-14
+
+
+def test_fused_step_with_potential_and_selective_sweeps(lz):
+    """Deuteron-like operator on a grid the fused kernel accepts: Ritz values converge, the omega
+    monitor fires, and the predicated sweep + recompute path of the fused loop is exercised."""
+    grid = (64, 16, 16)
+    g = [np.linspace(-12.5, 12.5, m) for m in grid]
+    Z, Y, X = np.meshgrid(g[2], g[1], g[0], indexing="ij")
+    pot = orc.deuteron_potential(X, Y, Z).ravel()
+    dx = 25.0 / 16
+    T = 197.327 ** 2 / (2 * 469.4592) / dx ** 2
+    H = orc.laplacian_csr(grid, 6.0 * T, -T, periodic=True, diag=pot)
+    op = lz.StencilOperator(grid, 6.0 * T, -T, diag=pot)
+    n = 140
+    ref = orc.lanczos(H, n, seed=78)
+    sel = lz.Lanczos(op)
+    sel.execute_Lanczos(n, seed=78, reorth="selective", cgs_passes=2, step_kernel="fused")
+    assert 0 < sel.result.reorth_count < n // 2
+    scale = np.abs(ref["theta"]).max()
+    assert np.max(np.abs(sel.ritz_values(6) - ref["theta"][:6])) < TOL_RITZ * scale
+    two = lz.Lanczos(op)
+    two.execute_Lanczos(n, seed=78, reorth="selective", cgs_passes=2, step_kernel="two_pass")
+    assert np.max(np.abs(two.ritz_values(6) - ref["theta"][:6])) < TOL_RITZ * scale
+    V = sel.V
+    assert np.abs(V.T @ V - np.eye(n)).max() < 1e-6
+    # first 30 steps (before any sweep) agree with the reference to round-off
+    assert rel(np.diag(sel.H_eff)[:30], ref["alpha"][:30]) < 1e-11
+
+
+def test_fused_step_rejected_where_it_does_not_apply(lz):
+    L = lz.Lanczos(lz.StencilOperator((20, 20, 20), 6.0, -1.0))
+    with pytest.raises(RuntimeError):
+        L.execute_Lanczos(5, reorth="none", step_kernel="fused")
+    L.execute_Lanczos(5, reorth="none", step_kernel="auto")     # falls back to the two-pass step

@@ -46,7 +46,10 @@ if __name__ == "__main__":
             return
         _print(*a, **k)
     builtins.print = quiet_print
-    run(big, 20, reorth="none", keep_basis=False, ref_compat=False)
+    run(big, 20, reorth="none", keep_basis=False, ref_compat=False, step_kernel="two_pass")
+    run(big, 20, reorth="none", keep_basis=False, ref_compat=False, step_kernel="fused")
+    run(big, 40, reorth="selective", cgs_passes=2, step_kernel="fused")
+    run(big, 40, reorth="selective", cgs_passes=2, step_kernel="two_pass")
     run(big, 20, reorth="selective", cgs_passes=2)
     run(big, 20, reorth="full")
     run(big, 20, reorth="full", cgs_passes=2)
