@@ -90,6 +90,12 @@ int lz_op_csr_create(lz_ctx* ctx, int64_t M, int64_t nnz, const int32_t* indptr_
                      const int32_t* indices_host, const double* data_host,
                      int fmt, int sigma, lz_op** out);
 
+/* Row shard of a sparse operator for a team run: M_local rows, columns renumbered so that
+ * [0, M_local) are the owned entries of x and [M_local, ncols) index the shard's ghost list. */
+int lz_op_csr_shard_create(lz_ctx* ctx, int64_t M_local, int64_t ncols, int64_t nnz,
+                           const int32_t* indptr_host, const int32_t* indices_host,
+                           const double* data_host, int fmt, int sigma, lz_op** out);
+
 int lz_op_rows(const lz_op* op, int64_t* M);
 int lz_op_nnz(const lz_op* op, int64_t* nnz_true, int64_t* nnz_stored);
 
@@ -187,13 +193,19 @@ int lz_comm_close(lz_ctx* ctx, void* dev_ptr);
 int lz_comm_free(lz_ctx* ctx, void* dev_ptr);
 
 /* local_ranks[nlocal], ctxs[nlocal]; global_rows = M of the whole operator; max_steps = largest
- * n a run will use; plane_elems = nx*ny of a structured grid (0: none); nghost reserved. */
+ * n a run will use; plane_elems = nx*ny of a structured grid (0: none); nghost = largest ghost
+ * list of any rank of a sparse operator (0: none). */
 int lz_team_create(int world, int nlocal, const int* local_ranks, lz_ctx* const* ctxs,
                    int64_t global_rows, int32_t max_steps, int64_t plane_elems, int64_t nghost,
                    lz_team** out);
 /* comm_ptrs[world]: exchange buffers of all ranks as mapped in this process; lower/upper = ranks
  * owning the slab below/above this shard (-1: domain boundary, Dirichlet). */
 int lz_team_attach(lz_team* team, int local_index, void* const* comm_ptrs, int lower_rank, int upper_rank);
+/* Ghost-index exchange of a sparse row shard: send_idx_host[nsend] = local rows whose x entries
+ * other ranks need, grouped by destination rank (seg_start[world+1]); the segment for rank q
+ * lands at offset dst_off[q] of q's gather buffer (= position in q's ghost list). */
+int lz_team_set_ghosts(lz_team* team, int local_index, int32_t nsend, const int32_t* send_idx_host,
+                       const int32_t* seg_start, const int64_t* dst_off);
 /* As lz_lanczos_run, with one operator / start vector / basis buffer per local shard (the local
  * slab: an lz_op_stencil_create with the local extents).  alpha/beta are the global values. */
 int lz_team_lanczos_run(lz_team* team, lz_op* const* ops, const double* const* v0_dev, int32_t n,

@@ -157,17 +157,31 @@ int lz_op_stencil_create(lz_ctx* ctx, int dim, const int64_t* shape, int bc, dou
     return LZ_OK;
 }
 
+static int csr_create_impl(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, const int32_t* indptr,
+                           const int32_t* indices, const double* data, int fmt, int sigma, lz_op** out);
+
 int lz_op_csr_create(lz_ctx* ctx, int64_t M, int64_t nnz, const int32_t* indptr, const int32_t* indices,
                      const double* data, int fmt, int sigma, lz_op** out) {
+    return csr_create_impl(ctx, M, M, nnz, indptr, indices, data, fmt, sigma, out);
+}
+
+int lz_op_csr_shard_create(lz_ctx* ctx, int64_t M_local, int64_t ncols, int64_t nnz, const int32_t* indptr,
+                           const int32_t* indices, const double* data, int fmt, int sigma, lz_op** out) {
+    LZ_REQUIRE(ncols >= M_local, "lz_op_csr_shard_create: ncols < M_local");
+    return csr_create_impl(ctx, M_local, ncols, nnz, indptr, indices, data, fmt, sigma, out);
+}
+
+static int csr_create_impl(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, const int32_t* indptr,
+                           const int32_t* indices, const double* data, int fmt, int sigma, lz_op** out) {
     LZ_REQUIRE(ctx && indptr && out && (nnz == 0 || (indices && data)), "lz_op_csr_create: null argument");
-    LZ_REQUIRE(M >= 1 && M <= 0x7fffffff, "lz_op_csr_create: M out of range");
+    LZ_REQUIRE(M >= 1 && M <= 0x7fffffff && ncols <= 0x7fffffff, "lz_op_csr_create: M out of range");
     LZ_REQUIRE(nnz >= 0 && nnz <= 0x7fffffff, "lz_op_csr_create: nnz must fit int32 indptr");
     LZ_REQUIRE(fmt == LZ_FMT_CSR || fmt == LZ_FMT_SELL, "lz_op_csr_create: unknown format %d", fmt);
     LZ_REQUIRE(indptr[0] == 0 && indptr[M] == nnz, "lz_op_csr_create: indptr does not span [0, nnz]");
     for (int64_t i = 0; i < M; ++i)
         LZ_REQUIRE(indptr[i + 1] >= indptr[i], "lz_op_csr_create: indptr not monotone at row %lld", (long long)i);
     for (int64_t k = 0; k < nnz; ++k)
-        LZ_REQUIRE(indices[k] >= 0 && indices[k] < M, "lz_op_csr_create: column index %d out of range at entry %lld",
+        LZ_REQUIRE(indices[k] >= 0 && indices[k] < ncols, "lz_op_csr_create: column index %d out of range at entry %lld",
                    indices[k], (long long)k);
     LZ_CUDA(cudaSetDevice(ctx->device));
     lz_op* op = new lz_op();
@@ -175,6 +189,7 @@ int lz_op_csr_create(lz_ctx* ctx, int64_t M, int64_t nnz, const int32_t* indptr,
     int st = (fmt == LZ_FMT_CSR) ? build_csr(op, M, nnz, indptr, indices, data)
                                  : build_sell(op, M, nnz, indptr, indices, data, sigma);
     if (st != LZ_OK) { lz_op_destroy(op); return st; }
+    op->ncols = ncols;
     *out = op;
     return LZ_OK;
 }
@@ -204,6 +219,7 @@ int lz_op_nnz(const lz_op* op, int64_t* nnz_true, int64_t* nnz_stored) {
 int lz_op_apply(lz_op* op, const double* x_dev, double* y_dev) {
     LZ_REQUIRE(op && x_dev && y_dev, "lz_op_apply: null argument");
     LZ_REQUIRE(x_dev != y_dev, "lz_op_apply: in-place apply is not supported");
+    LZ_REQUIRE(op->kind == LZ_OP_STENCIL || op->ncols <= op->M, "lz_op_apply: row shards are applied by the team run");
     LZ_CUDA(cudaSetDevice(op->ctx->device));
     int np = 0, l = 0;
     return launch_apply_dot(op, x_dev, nullptr, y_dev, op->ctx->partials + kMaxPartials, &np, &l);

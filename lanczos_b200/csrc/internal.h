@@ -60,6 +60,8 @@ struct lz_op {
     lz_csr csr;
     lz_sell sell;
     int fused_per_sm = 0;          // cached occupancy of the fused step kernel
+    int64_t ncols = 0;             // sparse: number of columns (> M for a row shard: M owned + ghosts)
+    const double* xghost = nullptr;   // sparse row shard: where the ghost entries of x live (set per launch)
     // host copy of the CSR arrays is NOT kept; export reads them back from the device.
 };
 
@@ -95,6 +97,8 @@ int launch_update_norm(lz_ctx* ctx, const double* w, const double* a, const doub
                        const double* sb_dev, double* out, int64_t M, double* partials, int* nparts,
                        const HaloPush* halo = nullptr);
 int launch_halo_push(lz_ctx* ctx, const double* x, int64_t M, const HaloPush* halo);
+int launch_ghost_push(lz_ctx* ctx, const double* x, const int32_t* send_idx, int nsend, int world,
+                      const int* seg_start, double* const* dst, const int* flag_dev);
 int launch_scale(lz_ctx* ctx, double* x, int64_t M, double s);
 
 // ---- Gram-Schmidt block GEMV pair (reorth.cu) --------------------------------------------

@@ -309,6 +309,11 @@ struct lz_shard {
     // structured-grid halo: where my boundary planes go / where my neighbours' planes arrive
     int lower = -1, upper = -1;          // neighbour ranks (-1: none, domain boundary)
     int64_t plane = 0;
+    // sparse row shard: ghost-index exchange (what I send to whom, where it lands)
+    int32_t* send_idx = nullptr;         // device, nsend local row indices, grouped by destination rank
+    int nsend = 0;
+    int seg_start[kMaxWorld + 1] = {};
+    int64_t dst_off[kMaxWorld] = {};
 };
 
 struct lz_team {
@@ -369,6 +374,25 @@ void bind_ghosts(const lz_team* team, ShardRun& r, int parity) {
     r.op->st.sharded = 1;
     r.op->st.ghost_lo = (sh->lower >= 0) ? reinterpret_cast<const double*>(mine + team->layout.ghost_lo_off + parity * pb) : nullptr;
     r.op->st.ghost_hi = (sh->upper >= 0) ? reinterpret_cast<const double*>(mine + team->layout.ghost_hi_off + parity * pb) : nullptr;
+}
+
+// sparse row shard: ghost entries of x arrive in my gather buffer of the given parity
+void bind_gather(const lz_team* team, ShardRun& r, int parity) {
+    if (!team || !r.sh || r.op->kind == LZ_OP_STENCIL) return;
+    if (team->nghost == 0 || r.op->ncols <= r.op->M) { r.op->xghost = nullptr; return; }
+    char* mine = (char*)r.sh->comm[r.sh->rank];
+    r.op->xghost = reinterpret_cast<const double*>(mine + team->layout.gather_off) + (size_t)parity * team->nghost;
+}
+
+// sparse row shard: send the entries of `x` that other ranks need (gather + NVLink peer stores)
+int push_ghosts(const lz_team* team, ShardRun& r, const double* x, int parity, const int* flag, int* launches) {
+    if (!team || !r.sh || r.op->kind == LZ_OP_STENCIL || r.sh->nsend == 0) return LZ_OK;
+    double* dst[kMaxWorld];
+    for (int q = 0; q < team->world; ++q)
+        dst[q] = reinterpret_cast<double*>((char*)r.sh->comm[q] + team->layout.gather_off) +
+                 (size_t)parity * team->nghost + r.sh->dst_off[q];
+    ++*launches;
+    return launch_ghost_push(r.ctx, x, r.sh->send_idx, r.sh->nsend, team->world, r.sh->seg_start, dst, flag);
 }
 
 // The loop over `nl` local shards (nl == 1 and team == nullptr: the plain single-GPU solve).
@@ -525,12 +549,14 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
             LZ_CHECK(each([&](ShardRun& r) {
                 HaloPush h = halo_for(team, r, 1);
                 if (h.lo_dst || h.hi_dst) ++launches;
-                return launch_halo_push(r.ctx, r.v0, r.M, &h);
+                LZ_CHECK(launch_halo_push(r.ctx, r.v0, r.M, &h));
+                return push_ghosts(team, r, r.v0, 1, nullptr, &launches);
             }));
             LZ_CHECK(peer_sync(false));
         }
         LZ_CHECK(each([&](ShardRun& r) {
             bind_ghosts(team, r, 1);
+            bind_gather(team, r, 1);
             int l2 = 0;
             const int rc = launch_apply_dot(r.op, r.v0, r.st.v0scale, r.w, r.ctx->partials, &r.np, &l2, nullptr);
             launches += l2;
@@ -540,8 +566,9 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         LZ_CHECK(each([&](ShardRun& r) {
             HaloPush h = halo_for(team, r, 0);
             ++launches;
-            return launch_update_norm(r.ctx, r.w, r.v0, nullptr, r.st.alpha_pre, r.st.v0scale, nullptr, nullptr,
-                                      r.row(0), r.M, r.ctx->partials, &r.np, &h);
+            LZ_CHECK(launch_update_norm(r.ctx, r.w, r.v0, nullptr, r.st.alpha_pre, r.st.v0scale, nullptr, nullptr,
+                                        r.row(0), r.M, r.ctx->partials, &r.np, &h));
+            return push_ghosts(team, r, r.row(0), 0, nullptr, &launches);
         }));
         LZ_CHECK(fin_scalar(FIN_BETA, nul, 0, opts->breakdown_tol, [](ShardRun& r) { return r.st.alpha_pre; }));
     } else {
@@ -551,7 +578,8 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
             ++launches;
             HaloPush h = halo_for(team, r, 0);
             if (h.lo_dst || h.hi_dst) ++launches;
-            return launch_halo_push(r.ctx, r.v0, r.M, &h);
+            LZ_CHECK(launch_halo_push(r.ctx, r.v0, r.M, &h));
+            return push_ghosts(team, r, r.v0, 0, nullptr, &launches);
         }));
         LZ_CHECK(peer_sync(false));
     }
@@ -646,7 +674,8 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
                                                      r.M, sel ? r.st.flags + 1 : nullptr, &h);
                     r.kt.end();
                     ++launches;
-                    return rc;
+                    LZ_CHECK(rc);
+                    return push_ghosts(team, r, r.row(j), par, sel ? r.st.flags + 1 : nullptr, &launches);
                 }));
                 pushed = true;
             }
@@ -656,6 +685,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         // ---- w = H q_j, alpha_j = q_j . w ------------------------------------------------------
         LZ_CHECK(each([&](ShardRun& r) {
             bind_ghosts(team, r, par);
+            bind_gather(team, r, par);
             int l2 = 0;
             r.kt.begin(K_APPLY);
             const int rc = launch_apply_dot(r.op, r.row(j), r.st.scale + j, r.w, r.ctx->partials, &r.np, &l2, nullptr);
@@ -674,7 +704,9 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
                                               out, r.M, r.ctx->partials, &r.np, &h);
             r.kt.end();
             ++launches;
-            return rc;
+            LZ_CHECK(rc);
+            if (j + 1 < n) return push_ghosts(team, r, out, (j + 1) & 1, nullptr, &launches);
+            return LZ_OK;
         }));
         LZ_CHECK(fin_scalar(FIN_BETA, nul, j + 1, opts->breakdown_tol, [](ShardRun& r) { return r.st.alpha; }));
         if (reorth == LZ_REORTH_SELECTIVE && j + 1 < n) {
@@ -905,6 +937,30 @@ extern "C" int lz_team_attach(lz_team* team, int local_index, void* const* comm_
     return LZ_OK;
 }
 
+extern "C" int lz_team_set_ghosts(lz_team* team, int local_index, int32_t nsend, const int32_t* send_idx_host,
+                                  const int32_t* seg_start, const int64_t* dst_off) {
+    LZ_REQUIRE(team && seg_start && dst_off, "lz_team_set_ghosts: null argument");
+    LZ_REQUIRE(local_index >= 0 && local_index < team->nlocal, "lz_team_set_ghosts: bad shard index");
+    LZ_REQUIRE(nsend >= 0 && (nsend == 0 || send_idx_host), "lz_team_set_ghosts: bad send list");
+    lz_shard& sh = team->shards[local_index];
+    LZ_REQUIRE(seg_start[0] == 0 && seg_start[team->world] == nsend, "lz_team_set_ghosts: segments do not span the send list");
+    LZ_CUDA(cudaSetDevice(sh.ctx->device));
+    if (sh.send_idx) { cudaFree(sh.send_idx); sh.send_idx = nullptr; }
+    sh.nsend = nsend;
+    for (int q = 0; q <= team->world; ++q) sh.seg_start[q] = seg_start[q];
+    for (int q = 0; q < team->world; ++q) {
+        LZ_REQUIRE(seg_start[q + 1] >= seg_start[q], "lz_team_set_ghosts: segments not monotone");
+        LZ_REQUIRE(dst_off[q] >= 0 && dst_off[q] + (seg_start[q + 1] - seg_start[q]) <= team->nghost,
+                   "lz_team_set_ghosts: destination range of rank %d exceeds the gather buffer", q);
+        sh.dst_off[q] = dst_off[q];
+    }
+    if (nsend > 0) {
+        LZ_CUDA(cudaMalloc((void**)&sh.send_idx, (size_t)nsend * 4));
+        LZ_CUDA(cudaMemcpy(sh.send_idx, send_idx_host, (size_t)nsend * 4, cudaMemcpyHostToDevice));
+    }
+    return LZ_OK;
+}
+
 extern "C" int lz_team_lanczos_run(lz_team* team, lz_op* const* ops, const double* const* v0_dev,
                                    int32_t n, const lz_run_opts* opts, double* alpha_host,
                                    double* beta_host, double* const* V_dev, const int64_t* ldv,
@@ -917,6 +973,9 @@ extern "C" int lz_team_lanczos_run(lz_team* team, lz_op* const* ops, const doubl
 }
 
 extern "C" int lz_team_destroy(lz_team* team) {
+    if (team)
+        for (lz_shard& sh : team->shards)
+            if (sh.send_idx) { cudaSetDevice(sh.ctx->device); cudaFree(sh.send_idx); }
     delete team;
     return LZ_OK;
 }

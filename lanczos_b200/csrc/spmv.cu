@@ -24,9 +24,11 @@ __global__ void __launch_bounds__(kThreads)
 spmv_csr_dot_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                     const double* __restrict__ data, const double* __restrict__ x,
                     const double* __restrict__ scale, double* __restrict__ y, int64_t M,
-                    double* __restrict__ partials) {
+                    double* __restrict__ partials, const double* __restrict__ xg) {
     __shared__ double red[kWarps];
     constexpr int RPW = 32 / T;                       // rows per warp
+    // sharded operator: columns >= M are ghost entries that live in the exchange buffer
+    const double* const xgs = xg ? xg - M : x;
     const double s = scale ? __ldg(scale) : 1.0;
     const int lane = threadIdx.x & 31;
     const int sub = lane % T;
@@ -39,8 +41,10 @@ spmv_csr_dot_kernel(const int32_t* __restrict__ indptr, const int32_t* __restric
         double sum = 0.0;
         if (valid) {
             const int32_t k0 = __ldg(indptr + row), k1 = __ldg(indptr + row + 1);
-            for (int32_t k = k0 + sub; k < k1; k += T)
-                sum = fma(__ldg(data + k), __ldg(x + __ldg(indices + k)), sum);
+            for (int32_t k = k0 + sub; k < k1; k += T) {
+                const int32_t c = __ldg(indices + k);
+                sum = fma(__ldg(data + k), __ldg((c < M ? x : xgs) + c), sum);
+            }
         }
 #pragma unroll
         for (int o = T / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -58,10 +62,12 @@ __global__ void __launch_bounds__(kThreads)
 spmv_sell_dot_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __restrict__ col,
                      const double* __restrict__ val, const int32_t* __restrict__ row_of,
                      const double* __restrict__ x, const double* __restrict__ scale,
-                     double* __restrict__ y, int64_t nchunks, double* __restrict__ partials) {
+                     double* __restrict__ y, int64_t nchunks, double* __restrict__ partials,
+                     const double* __restrict__ xg, int32_t M) {
     __shared__ double red[kWarps];
     const double s = scale ? __ldg(scale) : 1.0;
     const int lane = threadIdx.x & 31;
+    const double* const xgs = xg ? xg - M : x;        // ghost columns (>= M) of a sharded operator
     const int64_t warp_global = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * kThreads) >> 5;
     double acc = 0.0;
@@ -79,11 +85,14 @@ spmv_sell_dot_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __res
             for (int u = 0; u < 4; ++u) { cc[u] = __ldg(pc + (k + u) * 32); vv[u] = ld_stream1(pv + (k + u) * 32); }
             double xx[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) xx[u] = __ldg(x + cc[u]);
+            for (int u = 0; u < 4; ++u) xx[u] = __ldg((cc[u] < M ? x : xgs) + cc[u]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) sum = fma(vv[u], xx[u], sum);
         }
-        for (; k < width; ++k) sum = fma(ld_stream1(pv + k * 32), __ldg(x + __ldg(pc + k * 32)), sum);
+        for (; k < width; ++k) {
+            const int32_t c1 = __ldg(pc + k * 32);
+            sum = fma(ld_stream1(pv + k * 32), __ldg((c1 < M ? x : xgs) + c1), sum);
+        }
         const int32_t row = __ldg(row_of + c * 32 + lane);
         if (row >= 0) {
             const double yi = s * sum;
@@ -107,7 +116,7 @@ int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double*
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((op->M + rows_per_cta - 1) / rows_per_cta, cap));
 #define LZ_CSR_LAUNCH(TT)                                                                          \
     spmv_csr_dot_kernel<TT><<<grid, kThreads, 0, ctx->stream>>>(c.indptr, c.indices, c.data, x,    \
-                                                                scale_dev, y, op->M, partials)
+                                                                scale_dev, y, op->M, partials, op->xghost)
         switch (T) {
             case 2: LZ_CSR_LAUNCH(2); break;
             case 4: LZ_CSR_LAUNCH(4); break;
@@ -123,9 +132,49 @@ int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double*
     const lz_sell& sl = op->sell;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((sl.nchunks + kWarps - 1) / kWarps, cap));
     spmv_sell_dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(sl.chunk_off, sl.col, sl.val, sl.row_of, x,
-                                                             scale_dev, y, sl.nchunks, partials);
+                                                             scale_dev, y, sl.nchunks, partials, op->xghost,
+                                                             (int32_t)op->M);
     LZ_CUDA(cudaGetLastError());
     if (nparts) *nparts = grid;
+    return LZ_OK;
+}
+
+// Ghost-index exchange of a row-sharded sparse operator: entry e of my send list goes to the
+// gather buffer of the rank that owns segment q (seg_start[q] <= e < seg_start[q+1]) at offset
+// dst_off[q] + (e - seg_start[q]) - a gather from my vector followed by NVLink peer stores.
+struct GhostPushArgs {
+    const int32_t* send_idx;      // device, nsend local row indices
+    int nsend;
+    int world;
+    int seg_start[17];            // prefix over peers
+    double* dst[16];              // peer gather buffer (parity already applied) + dst_off
+};
+
+__global__ void __launch_bounds__(kThreads)
+ghost_push_kernel(const double* __restrict__ x, const GhostPushArgs g, const int* __restrict__ flag) {
+    if (flag && *flag == 0) return;
+    const int tid = blockIdx.x * kThreads + threadIdx.x;
+    const int nthr = gridDim.x * kThreads;
+    for (int e = tid; e < g.nsend; e += nthr) {
+        int q = 0;
+        while (e >= g.seg_start[q + 1]) ++q;
+        g.dst[q][e - g.seg_start[q]] = __ldg(x + __ldg(g.send_idx + e));
+    }
+}
+
+int launch_ghost_push(lz_ctx* ctx, const double* x, const int32_t* send_idx, int nsend, int world,
+                      const int* seg_start, double* const* dst, const int* flag_dev) {
+    if (nsend <= 0) return LZ_OK;
+    GhostPushArgs g;
+    g.send_idx = send_idx;
+    g.nsend = nsend;
+    g.world = world;
+    for (int q = 0; q <= world; ++q) g.seg_start[q] = seg_start[q];
+    for (int q = world + 1; q < 17; ++q) g.seg_start[q] = nsend;
+    for (int q = 0; q < 16; ++q) g.dst[q] = q < world ? dst[q] : nullptr;
+    const int grid = std::max(1, std::min((nsend + kThreads - 1) / kThreads, ctx->sms * 4));
+    ghost_push_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, g, flag_dev);
+    LZ_CUDA(cudaGetLastError());
     return LZ_OK;
 }
 

@@ -91,6 +91,80 @@ class SlabPlan:
         return lo, up
 
 
+class RowBlockPlan:
+    """Contiguous row blocks of a sparse operator: rank r owns rows [r0, r1); the
+    columns of its block are renumbered - owned columns to [0, M_loc), the others to
+    M_loc + (position in the rank's sorted list of ghost columns).  The ghost list of a rank is,
+    per owner, a contiguous run (owners are contiguous row ranges), so every peer's contribution
+    lands as one segment of the rank's gather buffer."""
+
+    def __init__(self, H, world: int, align: int = 32):
+        import scipy.sparse as sp
+        A = sp.csr_matrix(H)
+        if A.shape[0] != A.shape[1]:
+            raise ValueError("operator must be square")
+        A.sort_indices()
+        self.A = A
+        self.world = int(world)
+        self.M = A.shape[0]
+        self.plane = 0
+        per = -(-self.M // self.world)
+        per = -(-per // align) * align
+        self.starts = [min(r * per, self.M) for r in range(self.world + 1)]
+        if self.starts[-2] >= self.M:
+            raise ValueError(f"cannot split {self.M} rows over {self.world} ranks in blocks of {align}")
+        self.ghost_cols = []          # per rank: sorted global columns it needs from others
+        for r in range(self.world):
+            r0, r1 = self.rows(r)
+            cols = A.indices[A.indptr[r0]:A.indptr[r1]]
+            self.ghost_cols.append(np.unique(cols[(cols < r0) | (cols >= r1)]).astype(np.int64))
+        self.nghost_max = max(len(g) for g in self.ghost_cols)
+
+    def rows(self, rank: int):
+        return self.starts[rank], self.starts[rank + 1]
+
+    def local_rows(self, rank: int) -> int:
+        return self.starts[rank + 1] - self.starts[rank]
+
+    def owner_segments(self, rank: int):
+        """[(owner q, start, end)] : ghost_cols[rank][start:end] are owned by q."""
+        g = self.ghost_cols[rank]
+        cuts = np.searchsorted(g, self.starts)
+        return [(q, int(cuts[q]), int(cuts[q + 1])) for q in range(self.world)]
+
+    def local_csr(self, rank: int):
+        """(indptr, indices, data, ncols) of the rank's row block with renumbered columns."""
+        r0, r1 = self.rows(rank)
+        A = self.A
+        lo, hi = A.indptr[r0], A.indptr[r1]
+        cols = A.indices[lo:hi].astype(np.int64)
+        own = (cols >= r0) & (cols < r1)
+        local = np.empty_like(cols)
+        local[own] = cols[own] - r0
+        local[~own] = (r1 - r0) + np.searchsorted(self.ghost_cols[rank], cols[~own])
+        indptr = (A.indptr[r0:r1 + 1] - lo).astype(np.int32)
+        return indptr, local.astype(np.int32), np.ascontiguousarray(A.data[lo:hi], dtype=np.float64), \
+            (r1 - r0) + len(self.ghost_cols[rank])
+
+    def send_lists(self, rank: int):
+        """What `rank` sends: (send_idx, seg_start[world+1], dst_off[world]).  For destination q the
+        entries are q's ghost columns owned by `rank` (as local row indices), and they land at the
+        position of that run inside q's ghost list."""
+        r0, _ = self.rows(rank)
+        idx, seg, off = [], [0], []
+        for q in range(self.world):
+            if q == rank:
+                seg.append(seg[-1])
+                off.append(0)
+                continue
+            _, a, b = self.owner_segments(q)[rank]
+            idx.append(self.ghost_cols[q][a:b] - r0)
+            seg.append(seg[-1] + (b - a))
+            off.append(a)
+        send = np.concatenate(idx).astype(np.int32) if idx else np.zeros(0, dtype=np.int32)
+        return send, np.asarray(seg, dtype=np.int32), np.asarray(off, dtype=np.int64)
+
+
 # --------------------------------------------------------------------------- device side
 class _Shard:
     def __init__(self, ctx: Context, rank: int):
@@ -104,12 +178,19 @@ class _Shard:
 class _TeamBase:
     """Shared driver: subclasses provide the shards and the mapped exchange buffers."""
 
-    def __init__(self, H: StencilOperator, world: int):
-        if not isinstance(H, StencilOperator):
-            raise TypeError("row-sharded runs take a StencilOperator (sparse operators: single GPU for now)")
+    def __init__(self, H, world: int, fmt: str = "sell", sigma: int = 0):
+        import scipy.sparse as sp
         self.H = H
         self.world = int(world)
-        self.plan = SlabPlan(H.grid, self.world, H.bc == "periodic")
+        self.fmt, self.sigma = fmt, int(sigma)
+        if isinstance(H, StencilOperator):
+            self.plan = SlabPlan(H.grid, self.world, H.bc == "periodic")
+            self.sparse = False
+        elif sp.issparse(H):
+            self.plan = RowBlockPlan(H, self.world)
+            self.sparse = True
+        else:
+            raise TypeError("row-sharded runs take a StencilOperator or a scipy.sparse matrix")
         self.M = self.plan.M
         self.lib = _capi.load()
         self.team = None
@@ -126,26 +207,40 @@ class _TeamBase:
         nbytes = C.c_int64()
         # a single shard wraps periodic boundaries inside its own vector: no ghost planes
         plane = self.plan.plane if self.world > 1 else 0
-        _capi.check(self.lib.lz_comm_bytes(self.world, max_steps, plane, 0, C.byref(nbytes)))
+        nghost = self.plan.nghost_max if self.sparse else 0
+        _capi.check(self.lib.lz_comm_bytes(self.world, max_steps, plane, nghost, C.byref(nbytes)))
         tables = self._map_buffers(nbytes.value)
         nl = len(self.shards)
         ranks = (C.c_int * nl)(*[s.rank for s in self.shards])
         ctxs = (C.c_void_p * nl)(*[s.ctx.handle for s in self.shards])
         h = C.c_void_p()
-        _capi.check(self.lib.lz_team_create(self.world, nl, ranks, ctxs, self.M, max_steps, plane, 0, C.byref(h)))
+        _capi.check(self.lib.lz_team_create(self.world, nl, ranks, ctxs, self.M, max_steps, plane, nghost, C.byref(h)))
         self.team = h
         self.max_steps = max_steps
         for i, s in enumerate(self.shards):
             ptrs = (C.c_void_p * self.world)(*tables[i])
-            lo, up = self.plan.neighbours(s.rank)
-            if self.world == 1:
-                lo = up = -1
+            lo, up = (-1, -1) if (self.sparse or self.world == 1) else self.plan.neighbours(s.rank)
             _capi.check(self.lib.lz_team_attach(self.team, i, ptrs, lo, up))
+            if self.sparse:
+                send, seg, off = self.plan.send_lists(s.rank)
+                _capi.check(self.lib.lz_team_set_ghosts(
+                    self.team, i, len(send), send.ctypes.data_as(C.c_void_p),
+                    seg.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p)))
         self._make_ops()
 
     def _make_ops(self):
         torch = engine._torch()
         H, plan = self.H, self.plan
+        if self.sparse:
+            f = {"csr": _capi.LZ_FMT_CSR, "sell": _capi.LZ_FMT_SELL, "auto": _capi.LZ_FMT_SELL}[self.fmt]
+            for s in self.shards:
+                indptr, indices, data, ncols = plan.local_csr(s.rank)
+                h = C.c_void_p()
+                _capi.check(self.lib.lz_op_csr_shard_create(
+                    s.ctx.handle, plan.local_rows(s.rank), ncols, len(data), indptr.ctypes.data_as(C.c_void_p),
+                    indices.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p), f, self.sigma, C.byref(h)))
+                s.op_handle = h
+            return
         off3 = plan.off3(H.off)
         for s in self.shards:
             z0, z1 = plan.slab(s.rank)
@@ -284,8 +379,8 @@ class LocalTeamLanczos(_TeamBase):
     kernels of different shards then run one after the other, push phase before combine phase) or
     on several GPUs (`devices`)."""
 
-    def __init__(self, H: StencilOperator, world: int, devices: Optional[List[int]] = None):
-        super().__init__(H, world)
+    def __init__(self, H, world: int, devices: Optional[List[int]] = None, **kw):
+        super().__init__(H, world, **kw)
         torch = engine._torch()
         if devices is None:
             devices = [torch.cuda.current_device()] * self.world
@@ -319,14 +414,14 @@ class TeamLanczos(_TeamBase):
     """One process per GPU (torchrun): this process drives the shard of its rank; exchange
     buffers of the other ranks are mapped through cudaIpc handles swapped over torch.distributed."""
 
-    def __init__(self, H: StencilOperator, rank: Optional[int] = None, world: Optional[int] = None, device=None):
+    def __init__(self, H, rank: Optional[int] = None, world: Optional[int] = None, device=None, **kw):
         import torch.distributed as dist
         if not dist.is_initialized():
             raise RuntimeError("TeamLanczos needs an initialised torch.distributed process group")
         self.dist = dist
         rank = dist.get_rank() if rank is None else rank
         world = dist.get_world_size() if world is None else world
-        super().__init__(H, world)
+        super().__init__(H, world, **kw)
         self.rank = rank
         self.shards = [_Shard(Context.default(device), rank)]
 

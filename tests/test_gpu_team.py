@@ -147,3 +147,32 @@ def test_one_process_per_gpu(lz, tmp_path):
     one = lz.Lanczos(lz.StencilOperator((64, 32, 48), 6.0, -1.0))
     one.execute_Lanczos(30, seed=7, reorth="selective", cgs_passes=2)
     assert rel(np.diag(T), np.diag(one.H_eff)) < 1e-11
+
+
+@pytest.mark.parametrize("fmt,world,reorth", [("sell", 3, "full"), ("csr", 2, "full"), ("sell", 4, "selective"), ("sell", 5, "none")])
+def test_local_team_sparse_matches_single_gpu(lz, fmt, world, reorth):
+    """Row-sharded sparse operator with the ghost-index exchange vs the single-GPU run and the oracle."""
+    from lanczos_b200.team import LocalTeamLanczos
+    H = orc.delaunay_graph_laplacian(6000, seed=5)
+    n = 30
+    one = lz.IrrLanczos(H)
+    one.execute_LanczosOld(n, seed=3, reorth=reorth, cgs_passes=2 if reorth == "selective" else 1, fmt=fmt)
+    team = LocalTeamLanczos(H, world, fmt=fmt)
+    team.execute_LanczosOld(n, seed=3, reorth=reorth, cgs_passes=2 if reorth == "selective" else 1)
+    tol = 1e-12 if reorth != "none" else 1e-9
+    assert rel(np.diag(team.H_eff), np.diag(one.H_eff)) < tol
+    assert rel(np.diag(team.H_eff, 1), np.diag(one.H_eff, 1)) < tol
+    if reorth == "full":
+        ref = orc.lanczos(H, n, seed=3)
+        assert rel(np.diag(team.H_eff), ref["alpha"]) < 1e-12
+        assert rel(np.diag(team.H_eff, 1), ref["beta"]) < 1e-12
+
+
+def test_local_team_sparse_rgg(lz):
+    from lanczos_b200.team import LocalTeamLanczos
+    H = orc.rgg_graph_laplacian(20000, mean_degree=13.0, seed=4)
+    ref = orc.lanczos(H, 25, seed=11)
+    team = LocalTeamLanczos(H, 4)
+    team.execute_LanczosOld(25, seed=11)
+    assert rel(np.diag(team.H_eff), ref["alpha"]) < 1e-12
+    assert rel(np.diag(team.H_eff, 1), ref["beta"]) < 1e-12
