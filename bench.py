@@ -311,12 +311,13 @@ def main():
     # ---- region A2: the same K steps again with a CUDA-event pair around every bandwidth kernel
     # (per-kernel roofline).  Kept out of region A because the event records break up
     # back-to-back launches and cost several percent of step time.
-    kern = {"apply": [0.0, 0], "update": [0.0, 0], "dots": [0.0, 0], "gs_update": [0.0, 0]}
+    kern = {"apply": [0.0, 0], "update": [0.0, 0], "dots": [0.0, 0], "gs_update": [0.0, 0], "fused": [0.0, 0]}
     for c in chunks:
         res = solve(c, v0_dev, profile=True)
         for k, (ms, cnt) in res.kernel_ms.items():
-            kern[k][0] += ms
-            kern[k][1] += cnt
+            acc = kern.setdefault(k, [0.0, 0])
+            acc[0] += ms
+            acc[1] += cnt
         del res
     barrier()
     theta = solver.ritz_values(10)
