@@ -109,7 +109,12 @@ class LanczosBase:
             print("+++ Executing Lanczos algorithm")
         self.n = n
         ctx = Context.default(device)
-        op = as_device_operator(self.H, ctx, fmt=fmt, sigma=sigma)
+        # the device copy of the operator (CSR upload / SELL conversion) is made once per instance
+        key = (id(ctx), fmt, sigma)
+        cache = self.__dict__.setdefault("_op_cache", {})
+        if key not in cache:
+            cache[key] = as_device_operator(self.H, ctx, fmt=fmt, sigma=sigma)
+        op = cache[key]
         torch = engine._torch()
         if isinstance(v0, torch.Tensor):
             np.random.seed(seed)                                             # Lanczos.py:93
