@@ -119,6 +119,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel_name):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel_name` from the
+    committed `ncu --set full` summary (profiles/r1_ncu_traffic.json; captured at the 512^3 config)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
+            t = json.load(f)
+        for k, v in t.items():
+            if k.startswith(kernel_name):
+                return v["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -363,8 +377,9 @@ def main():
     roofline = None
     if dom:
         pk = per_kernel[dom]
+        traffic = ncu_traffic(names[dom]) if (args.workload in ("c3", "c3full") and M_local == 512 ** 3) else None
         roofline = {"kernel": names[dom], "bound": "hbm", "achieved": pk["achieved_gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": pk["achieved_gbs"] / peak, "traffic": None,
+                    "unit": "GB/s", "frac": pk["achieved_gbs"] / peak, "traffic": traffic,
                     "peak_source": peak_src, "alg_bytes_per_launch": pk["alg_bytes"],
                     "avg_launch_ms": pk["avg_ms"], "launches": pk["launches"],
                     "timing": "CUDA-event pair around every launch of a second K-step solve on the launching stream",
