@@ -81,6 +81,13 @@ int lz_op_stencil_create(lz_ctx* ctx, int dim, const int64_t* shape, int bc,
                          double center, const double* offdiag,
                          const double* diag_dev, lz_op** out);
 
+/* lz_op_stencil27_create: matrix-free 27-point operator on a 3-D grid, the reference's default
+ * Laplacian (Hamiltonian.create_sparse_T(points="27"), Hamiltonian.py:102-128):
+ * weights[4] = coefficient of the centre / the 6 face / the 12 edge / the 8 corner neighbours
+ * (reference T: T_factor * 3/13 * {-44/3, 1, 1/2, 1/3}; H = -T + V, 3Ddeuteron.py:80). */
+int lz_op_stencil27_create(lz_ctx* ctx, const int64_t* shape, int bc, const double* weights,
+                           const double* diag_dev, lz_op** out);
+
 /* lz_op_csr_create: general sparse operator from host CSR arrays (scipy layout:
  * indptr[M+1], indices[nnz], data[nnz]).  Replaces cupyx.scipy.sparse.csr_matrix(H)
  * at Lanczos.py:88 / csc_matrix(H) at IrrLanczos.py:205.  The arrays are copied

@@ -6,10 +6,10 @@ Only the hot path lives here: hand-written sm_100a CUDA (csrc/) behind a C ABI
 (include/lanczos_b200.h), a ctypes binding and the two drop-in classes.
 """
 from ._capi import LanczosBreakdown
-from .engine import Context, DeviceOperator, StencilOperator, run_lanczos
+from .engine import Context, DeviceOperator, StencilOperator, reference_T27_weights, run_lanczos
 from .irregular import IrrLanczos
 from .regular import Lanczos
 
-__all__ = ["Lanczos", "IrrLanczos", "StencilOperator", "DeviceOperator", "Context",
+__all__ = ["Lanczos", "IrrLanczos", "StencilOperator", "DeviceOperator", "Context", "reference_T27_weights",
            "run_lanczos", "LanczosBreakdown"]
 __version__ = "0.1.0"

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblanczos_b200.so")
-SOURCES = ["capi.cu", "stencil.cu", "vecops.cu", "reorth.cu", "spmv.cu", "fused.cu", "lanczos.cu"]
+SOURCES = ["capi.cu", "stencil.cu", "stencil27.cu", "vecops.cu", "reorth.cu", "spmv.cu", "fused.cu", "lanczos.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",

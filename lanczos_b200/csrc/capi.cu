@@ -23,6 +23,8 @@ int launch_stencil_apply_dot(lz_op* op, const double* x, const double* scale_dev
                              double* partials, int* nparts, const int* flag_dev);
 int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double* y, double* partials,
                     int* nparts, const int* flag_dev);
+int launch_stencil27_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
+                               double* partials, int* nparts, const int* flag_dev);
 int build_csr(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const int32_t* indices,
               const double* data);
 int build_sell(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const int32_t* indices,
@@ -31,6 +33,8 @@ int build_sell(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const i
 int launch_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y, double* partials,
                      int* nparts, int* launches, const int* flag_dev) {
     if (launches) *launches = 1;
+    if (op->kind == LZ_OP_STENCIL && op->st.points == 27)
+        return launch_stencil27_apply_dot(op, x, scale_dev, y, partials, nparts, flag_dev);
     if (op->kind == LZ_OP_STENCIL) return launch_stencil_apply_dot(op, x, scale_dev, y, partials, nparts, flag_dev);
     return launch_spmv_dot(op, x, scale_dev, y, partials, nparts, flag_dev);
 }
@@ -160,6 +164,17 @@ int lz_op_stencil_create(lz_ctx* ctx, int dim, const int64_t* shape, int bc, dou
 static int csr_create_impl(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, const int32_t* indptr,
                            const int32_t* indices, const double* data, int fmt, int sigma, lz_op** out);
 
+int lz_op_stencil27_create(lz_ctx* ctx, const int64_t* shape, int bc, const double* weights,
+                           const double* diag_dev, lz_op** out) {
+    LZ_REQUIRE(ctx && shape && weights && out, "lz_op_stencil27_create: null argument");
+    const double off[3] = {weights[1], weights[1], weights[1]};
+    LZ_CHECK(lz_op_stencil_create(ctx, 3, shape, bc, weights[0], off, diag_dev, out));
+    lz_stencil& st = (*out)->st;
+    st.points = 27;
+    for (int k = 0; k < 4; ++k) st.w27[k] = weights[k];
+    return LZ_OK;
+}
+
 int lz_op_csr_create(lz_ctx* ctx, int64_t M, int64_t nnz, const int32_t* indptr, const int32_t* indices,
                      const double* data, int fmt, int sigma, lz_op** out) {
     return csr_create_impl(ctx, M, M, nnz, indptr, indices, data, fmt, sigma, out);
@@ -208,6 +223,7 @@ int lz_op_nnz(const lz_op* op, int64_t* nnz_true, int64_t* nnz_stored) {
     else {
         const lz_stencil& g = op->st;
         int per = 1 + 2 * ((g.offx != 0.0) + (g.offy != 0.0) + (g.offz != 0.0));
+        if (g.points == 27) per = 27;
         t = (int64_t)per * op->M;   // upper bound (boundaries/duplicates merge), matrix-free: nothing stored
         s = 0;
     }
@@ -292,6 +308,26 @@ int lz_op_export_csr(lz_op* op, int64_t* nnz_out, int32_t* indptr_host, int32_t*
         const int64_t stride[3] = {1, g.nx, g.nx * g.ny};
         return canonical_emit([&](int64_t i, std::vector<std::pair<int32_t, double>>& e) {
             const int64_t c[3] = {i % g.nx, (i / g.nx) % g.ny, i / (g.nx * g.ny)};
+            if (g.points == 27) {
+                for (int dz = -1; dz <= 1; ++dz)
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            int64_t k[3] = {c[0] + dx, c[1] + dy, c[2] + dz};
+                            bool inside = true;
+                            for (int a = 0; a < 3; ++a) {
+                                if (k[a] < 0 || k[a] >= ext[a]) {
+                                    if (g.bc != LZ_BC_PERIODIC) { inside = false; break; }
+                                    k[a] = (k[a] + ext[a]) % ext[a];
+                                }
+                            }
+                            if (!inside) continue;
+                            const int nz_off = (dx != 0) + (dy != 0) + (dz != 0);
+                            double w = g.w27[nz_off];
+                            if (nz_off == 0 && g.diag) w += diag[(size_t)i];
+                            e.push_back({(int32_t)(k[0] + k[1] * stride[1] + k[2] * stride[2]), w});
+                        }
+                return;
+            }
             e.push_back({(int32_t)i, g.center + (g.diag ? diag[(size_t)i] : 0.0)});
             for (int a = 0; a < 3; ++a) {
                 if (off[a] == 0.0) continue;

@@ -258,7 +258,7 @@ constexpr size_t kFSmemBytes = (size_t)kFStages * kFStageDoubles * 8 + (size_t)3
 bool fused_step_supported(const lz_op* op) {
     if (op->kind != LZ_OP_STENCIL) return false;
     const lz_stencil& st = op->st;
-    if (st.sharded) return false;
+    if (st.sharded || st.points != 7) return false;
     if (st.offx == 0.0 || st.offy == 0.0 || st.offz == 0.0) return false;
     if (st.nx % kFTileX != 0 || st.ny % kFTileY != 0) return false;
     if (st.nz < 2) return false;

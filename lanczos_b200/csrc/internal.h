@@ -26,6 +26,8 @@ struct lz_stencil {
     int64_t nx = 1, ny = 1, nz = 1;
     int bc = LZ_BC_PERIODIC;
     double center = 0.0, offx = 0.0, offy = 0.0, offz = 0.0;
+    int points = 7;                    // 7: axis neighbours only; 27: the full 3x3x3 box (3-D only)
+    double w27[4] = {0, 0, 0, 0};      // 27-point weights by number of non-zero offsets: centre, face, edge, corner
     const double* diag = nullptr;
     // sharded execution: ghost planes (nx*ny doubles each) written by the z-neighbours.
     // When null, the kernel wraps (periodic) or drops (Dirichlet) the out-of-slab plane.

@@ -34,6 +34,12 @@ def padded_ld(M: int) -> int:
     return (int(M) + 63) // 64 * 64
 
 
+def reference_T27_weights(T_factor: float = 1.0):
+    """(centre, face, edge, corner) coefficients of the reference's 27-point Laplacian T
+    (Hamiltonian.get_weights_27point, Hamiltonian.py:116-128)."""
+    return tuple(T_factor * 3.0 / 13.0 * w for w in (-44.0 / 3.0, 1.0, 0.5, 1.0 / 3.0))
+
+
 @dataclass(eq=False)
 class StencilOperator:
     """Matrix-free structured-grid operator descriptor
@@ -48,6 +54,8 @@ class StencilOperator:
     off: Sequence[float] | float
     bc: str = "periodic"
     diag: Optional[np.ndarray] = None      # potential on the diagonal, length M (host) or a CUDA tensor
+    weights27: Optional[Sequence[float]] = None   # 27-point box stencil (3-D): (centre, face, edge, corner)
+                                                  # coefficients; `center`/`off` are then ignored
     _dev: dict = field(default_factory=dict, repr=False, compare=False)
 
     def __post_init__(self):
@@ -61,6 +69,10 @@ class StencilOperator:
             raise ValueError("StencilOperator: one off-diagonal coefficient per axis")
         if self.bc not in ("periodic", "dirichlet"):
             raise ValueError("StencilOperator: bc must be 'periodic' or 'dirichlet'")
+        if self.weights27 is not None:
+            if len(self.grid) != 3 or len(tuple(self.weights27)) != 4:
+                raise ValueError("StencilOperator: weights27 needs a 3-D grid and 4 coefficients")
+            self.weights27 = tuple(float(w) for w in self.weights27)
         self.M = int(np.prod(self.grid))
         if self.diag is not None and int(np.prod(tuple(self.diag.shape))) != self.M:
             raise ValueError("StencilOperator: diag must have M entries")
@@ -156,7 +168,11 @@ class DeviceOperator:
             diag_p = C.c_void_p(diag_t.data_ptr())
         h = C.c_void_p()
         bc = LZ_BC_PERIODIC if st.bc == "periodic" else LZ_BC_DIRICHLET
-        _capi.check(ctx.lib.lz_op_stencil_create(ctx.handle, dim, shape, bc, float(st.center), off, diag_p, C.byref(h)))
+        if st.weights27 is not None:
+            w = (C.c_double * 4)(*st.weights27)
+            _capi.check(ctx.lib.lz_op_stencil27_create(ctx.handle, shape, bc, w, diag_p, C.byref(h)))
+        else:
+            _capi.check(ctx.lib.lz_op_stencil_create(ctx.handle, dim, shape, bc, float(st.center), off, diag_p, C.byref(h)))
         return cls(ctx, h, st.M, "stencil", keep=(diag_t,))
 
     @classmethod

@@ -256,7 +256,11 @@ class _TeamBase:
                 diag_p = C.c_void_p(diag_t.data_ptr())
             h = C.c_void_p()
             bc = _capi.LZ_BC_PERIODIC if H.bc == "periodic" else _capi.LZ_BC_DIRICHLET
-            _capi.check(self.lib.lz_op_stencil_create(s.ctx.handle, 3, shape, bc, float(H.center), off, diag_p, C.byref(h)))
+            if H.weights27 is not None:
+                w = (C.c_double * 4)(*H.weights27)
+                _capi.check(self.lib.lz_op_stencil27_create(s.ctx.handle, shape, bc, w, diag_p, C.byref(h)))
+            else:
+                _capi.check(self.lib.lz_op_stencil_create(s.ctx.handle, 3, shape, bc, float(H.center), off, diag_p, C.byref(h)))
             s.op_handle = h
             s.keep = (diag_t,)
 

@@ -26,7 +26,7 @@ import scipy.sparse as sp
 
 __all__ = [
     "start_vector", "gram_schmidt_row", "tridiagonalize", "assemble_tridiagonal",
-    "ritz_pairs", "lanczos", "laplacian_csr", "reference_T_csr", "deuteron_potential",
+    "ritz_pairs", "lanczos", "laplacian_csr", "laplacian27_csr", "box27_weights", "reference_T_csr", "deuteron_potential",
     "deuteron_hamiltonian", "delaunay_graph_laplacian", "rgg_graph_laplacian",
     "csr_matvec_rows", "timed_steps",
 ]
@@ -168,6 +168,36 @@ def laplacian_csr(shape, center, off, periodic=True, diag=None):
         for b in range(ax + 1, dim):   # slower axes go to the left
             term = sp.kron(sp.identity(shape[b]), term, format="csr")
         H = H + off[ax] * term
+    if diag is not None:
+        H = H + sp.diags(np.asarray(diag, dtype=np.float64))
+    H = sp.csr_matrix(H)
+    H.sum_duplicates()
+    H.sort_indices()
+    H.indices = H.indices.astype(np.int32)
+    H.indptr = H.indptr.astype(np.int32)
+    return H
+
+
+def box27_weights(T_factor=1.0):
+    """(centre, face, edge, corner) coefficients of the reference's 27-point Laplacian:
+    3/13 * {-44/3, 1, 1/2, 1/3} * T_factor (Hamiltonian.get_weights_27point, Hamiltonian.py:116-128)."""
+    return tuple(T_factor * 3.0 / 13.0 * w for w in (-44.0 / 3.0, 1.0, 0.5, 1.0 / 3.0))
+
+
+def laplacian27_csr(shape, weights, periodic=True, diag=None):
+    """27-point box operator on a 3-D grid: the coefficient of a neighbour depends on how many of its
+    three offsets are non-zero (Hamiltonian.py:24,102-128); index map and periodic wrap as the
+    7-point one.  Built from Kronecker products of per-axis neighbour sums; sorted CSR, int32."""
+    shape = tuple(int(s) for s in shape)
+    assert len(shape) == 3
+    A = [[sp.identity(n, format="csr"), _shift1d(n, periodic)] for n in shape]    # per axis: I, S
+    M = int(np.prod(shape))
+    H = sp.csr_matrix((M, M))
+    for ez in (0, 1):
+        for ey in (0, 1):
+            for ex in (0, 1):
+                term = sp.kron(A[2][ez], sp.kron(A[1][ey], A[0][ex], format="csr"), format="csr")
+                H = H + float(weights[ex + ey + ez]) * term
     if diag is not None:
         H = H + sp.diags(np.asarray(diag, dtype=np.float64))
     H = sp.csr_matrix(H)

@@ -101,6 +101,15 @@ def main():
                 out[f"T7_N{N}_indptr"] = T.indptr.astype(np.int32)
                 out[f"T7_N{N}_indices"] = T.indices.astype(np.int32)
                 out[f"T7_N{N}_data"] = T.data.astype(np.float64)
+                with quiet():
+                    ham27 = ref_ham.Hamiltonian(N, 25.0, orc.deuteron_potential, 1.75)
+                    ham27.create_sparse_T("27")
+                T27 = ham27.T_sparse.copy()
+                T27.sum_duplicates()
+                T27.sort_indices()
+                out[f"T27_N{N}_indptr"] = T27.indptr.astype(np.int32)
+                out[f"T27_N{N}_indices"] = T27.indices.astype(np.int32)
+                out[f"T27_N{N}_data"] = T27.data.astype(np.float64)
                 Hd = (-ham.T_sparse + ham.V_sparse)
                 Hd.sort_indices()
                 out[f"H_N{N}_indptr"] = Hd.indptr.astype(np.int32)
@@ -135,6 +144,25 @@ def main():
     L = run_regular(ref_reg, Hd, 120, seed=78)
     a, b = tri_parts(L.H_eff)
     out["deut_alpha"], out["deut_beta"], out["deut_theta"] = a, b, L.H_eigvals.copy()
+
+    # ---- G5b: the driver's actual operator: 27-point T (3Ddeuteron.py:76 default), N = 12, n = 60 ----
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            N = 12
+            dx = 25.0 / N
+            Tf = 197.327 ** 2 / (2 * 469.4592) * 1 / dx ** 2
+            with quiet():
+                ham = ref_ham.Hamiltonian(N, 25.0, orc.deuteron_potential, Tf)
+                ham.create_sparse_T()
+                ham.create_sparse_V()
+            H27 = (-ham.T_sparse + ham.V_sparse)
+            H27.sort_indices()
+        finally:
+            os.chdir(cwd)
+    L = run_regular(ref_reg, H27, 60, seed=78)
+    a, b = tri_parts(L.H_eff)
+    out["deut27_alpha"], out["deut27_beta"], out["deut27_theta"] = a, b, L.H_eigvals.copy()
 
     # ---- G6: Irregular: Delaunay graph Laplacian 3000 vertices, CSR and CSC, n = 50 -
     Ld = orc.delaunay_graph_laplacian(3000, seed=0)

@@ -414,3 +414,52 @@ def test_fused_step_rejected_where_it_does_not_apply(lz):
     with pytest.raises(RuntimeError):
         L.execute_Lanczos(5, reorth="none", step_kernel="fused")
     L.execute_Lanczos(5, reorth="none", step_kernel="auto")     # falls back to the two-pass step
+
+
+# ---- K1b: the reference's default 27-point Laplacian, matrix-free ------------------------------------
+
+@pytest.mark.parametrize("grid,bc", [((5, 5, 5), "periodic"), ((2, 2, 2), "periodic"), ((6, 5, 4), "dirichlet"),
+                                      ((66, 9, 3), "periodic"), ((7, 3, 1), "periodic")])
+def test_stencil27_pattern_and_values(lz, golden, grid, bc):
+    w = orc.box27_weights(1.75)
+    A = orc.laplacian27_csr(grid, w, periodic=(bc == "periodic"))
+    op = lz.StencilOperator(grid, 0.0, 0.0, bc=bc, weights27=w)
+    E = op.tocsr()
+    assert np.array_equal(E.indptr, A.indptr)
+    assert np.array_equal(E.indices, A.indices)
+    np.testing.assert_allclose(E.data, A.data, rtol=1e-15)
+    if grid == (5, 5, 5):
+        assert np.array_equal(E.indices, golden["T27_N5_indices"])       # == Hamiltonian.create_sparse_T("27")
+        np.testing.assert_allclose(E.data, golden["T27_N5_data"], rtol=1e-15)
+    M = A.shape[0]
+    D = A.toarray()
+    rs = np.random.RandomState(1)
+    for i in rs.choice(M, size=min(M, 40), replace=False):          # unit-vector probes of the kernel
+        e = np.zeros(M)
+        e[i] = 1.0
+        np.testing.assert_allclose(op.matvec(e), D[:, i], rtol=1e-15, atol=1e-16)
+    x = rs.uniform(-1, 1, M)
+    ref = A * x
+    assert np.max(np.abs(op.matvec(x) - ref)) <= 1e-14 * np.max(np.abs(ref))
+
+
+def test_deuteron27_driver_operator(lz, golden):
+    """3Ddeuteron.py's actual operator (27-point T, H = -T + V) at N = 12: matrix-free run vs the
+    reference's alpha/beta, and the same operator handed over as the scipy matrix."""
+    N = 12
+    dx = 25.0 / N
+    Tf = 197.327 ** 2 / (2 * 469.4592) * 1 / dx ** 2
+    g = np.linspace(-12.5, 12.5, N)
+    Z, Y, X = np.meshgrid(g, g, g, indexing="ij")
+    pot = orc.deuteron_potential(X, Y, Z).ravel()
+    w = tuple(-v for v in lz.reference_T27_weights(Tf))
+    op = lz.StencilOperator((N, N, N), 0.0, 0.0, weights27=w, diag=pot)
+    L = lz.Lanczos(op)
+    L.execute_Lanczos(60, seed=78)
+    a, b = np.diag(L.H_eff), np.diag(L.H_eff, 1)
+    assert rel(a[:50], golden["deut27_alpha"][:50]) < TOL_AB
+    assert rel(b[:50], golden["deut27_beta"][:50]) < TOL_AB
+    Hs = orc.laplacian27_csr((N, N, N), w, periodic=True, diag=pot)
+    L2 = lz.Lanczos(Hs)
+    L2.execute_Lanczos(60, seed=78)
+    assert rel(np.diag(L2.H_eff)[:50], golden["deut27_alpha"][:50]) < TOL_AB

@@ -176,3 +176,16 @@ def test_local_team_sparse_rgg(lz):
     team.execute_LanczosOld(25, seed=11)
     assert rel(np.diag(team.H_eff), ref["alpha"]) < 1e-12
     assert rel(np.diag(team.H_eff, 1), ref["beta"]) < 1e-12
+
+
+def test_local_team_stencil27(lz):
+    from lanczos_b200.team import LocalTeamLanczos
+    w = tuple(-v for v in orc.box27_weights(2.0))
+    grid = (16, 10, 12)
+    H = orc.laplacian27_csr(grid, w, periodic=True)
+    ref = orc.lanczos(H, 20, seed=5)
+    op = lz.StencilOperator(grid, 0.0, 0.0, weights27=w)
+    team = LocalTeamLanczos(op, 3)
+    team.execute_Lanczos(20, seed=5)
+    assert rel(np.diag(team.H_eff), ref["alpha"]) < 1e-12
+    assert rel(np.diag(team.H_eff, 1), ref["beta"]) < 1e-12

@@ -119,3 +119,29 @@ def test_rgg_laplacian_shape():
     assert abs(L.sum()) < 1e-9
     assert 9.0 < (L.nnz / 4000.0 - 1.0) < 14.0   # boundary effects lower the mean degree
     assert (abs(L - L.T)).nnz == 0
+
+
+@pytest.mark.parametrize("N", [2, 3, 5])
+def test_pattern_T27_matches_reference(golden, N):
+    # the reference's default 27-point Laplacian (Hamiltonian.create_sparse_T("27"))
+    T = orc.laplacian27_csr((N, N, N), orc.box27_weights(1.75), periodic=True)
+    assert np.array_equal(T.indptr, golden[f"T27_N{N}_indptr"])
+    assert np.array_equal(T.indices, golden[f"T27_N{N}_indices"])
+    np.testing.assert_allclose(T.data, golden[f"T27_N{N}_data"], rtol=4e-16, atol=1e-15)
+
+
+def _deuteron27(N):
+    dx = 25.0 / N
+    Tf = 197.327 ** 2 / (2 * 469.4592) * 1 / dx ** 2
+    g = np.linspace(-12.5, 12.5, N)
+    Z, Y, X = np.meshgrid(g, g, g, indexing="ij")
+    pot = orc.deuteron_potential(X, Y, Z).ravel()
+    w = tuple(-x for x in orc.box27_weights(Tf))          # H = -T + V
+    return orc.laplacian27_csr((N, N, N), w, periodic=True, diag=pot), w, pot
+
+
+def test_deuteron27_matches_reference(golden):
+    H, _, _ = _deuteron27(12)
+    res = orc.lanczos(H, 60, seed=78)
+    np.testing.assert_allclose(res["alpha"], golden["deut27_alpha"], rtol=1e-12)
+    np.testing.assert_allclose(res["beta"], golden["deut27_beta"], rtol=1e-12)
