@@ -77,21 +77,24 @@ spmv_sell_dot_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __res
         const int32_t* pc = col + o0 + lane;
         const double* pv = val + o0 + lane;
         double sum = 0.0;
-        int k = 0;
-        for (; k + 4 <= width; k += 4) {
-            int32_t cc[4];
-            double vv[4];
+        // blocks of 8 entries with predication (no serial remainder loop): all column indices of a
+        // block are in flight together, then all gathers of x - rows of 7..14 entries are one or two
+        // blocks deep instead of a chain of dependent load pairs
+        constexpr int U = 8;
+        for (int k = 0; k < width; k += U) {
+            int32_t cc[U];
+            double vv[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { cc[u] = __ldg(pc + (k + u) * 32); vv[u] = ld_stream1(pv + (k + u) * 32); }
-            double xx[4];
+            for (int u = 0; u < U; ++u) {
+                const bool on = k + u < width;
+                cc[u] = on ? __ldg(pc + (k + u) * 32) : 0;
+                vv[u] = on ? ld_stream1(pv + (k + u) * 32) : 0.0;
+            }
+            double xx[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) xx[u] = __ldg((cc[u] < M ? x : xgs) + cc[u]);
+            for (int u = 0; u < U; ++u) xx[u] = (k + u < width) ? __ldg((cc[u] < M ? x : xgs) + cc[u]) : 0.0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) sum = fma(vv[u], xx[u], sum);
-        }
-        for (; k < width; ++k) {
-            const int32_t c1 = __ldg(pc + k * 32);
-            sum = fma(ld_stream1(pv + k * 32), __ldg((c1 < M ? x : xgs) + c1), sum);
+            for (int u = 0; u < U; ++u) sum = fma(vv[u], xx[u], sum);
         }
         const int32_t row = __ldg(row_of + c * 32 + lane);
         if (row >= 0) {

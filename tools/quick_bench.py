@@ -56,3 +56,24 @@ if __name__ == "__main__":
     run((256, 256, 256), 50, reorth="full")
     run((200, 200), 100, reorth="full")
     run((64, 64, 64), 50, reorth="full")
+    # 27-point operator and sparse operators at scale
+    def run_op(op, n, label, cls=lz.Lanczos, **kw):
+        g = torch.Generator(device="cuda").manual_seed(0)
+        v0 = torch.rand(op.shape[0], dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+        L = cls(op)
+        ex = L.execute_Lanczos if cls is lz.Lanczos else L.execute_LanczosOld
+        best = None
+        for rep in range(3):
+            ex(n, v0=v0, profile=True, **kw)
+            ms = L.result.gpu_ms
+            best = ms if best is None else min(best, ms)
+        print(f"{label} n={n} {kw}: {best/n:.4f} ms/step kernels={ {k: (round(v[0]/max(v[1],1),4), v[1]) for k, v in L.result.kernel_ms.items() if v[1]} }", flush=True)
+    run_op(lz.StencilOperator(big, 0.0, 0.0, weights27=lz.reference_T27_weights(-1.0)), 12, "27pt 512^3", reorth="none", keep_basis=False)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import lanczos_oracle as orc
+    Hbig = orc.laplacian_csr((256, 256, 128), 6.0, -1.0)
+    for fmt in ("sell", "csr"):
+        run_op(Hbig, 12, f"7pt-as-{fmt} 8.4M rows", reorth="none", keep_basis=False, fmt=fmt)
+    Hd = orc.delaunay_graph_laplacian(1_000_000, seed=0)
+    for fmt in ("sell", "csr"):
+        run_op(Hd, 30, f"delaunay 1M {fmt}", cls=lz.IrrLanczos, reorth="full", fmt=fmt)
