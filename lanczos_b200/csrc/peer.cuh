@@ -87,7 +87,7 @@ __device__ __forceinline__ void peer_wait(const PeerComm& pc, unsigned long long
         const unsigned long long* f = pc.flags[pc.rank] + (size_t)slot * pc.world + threadIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) != seq) {
-            if (clock64() - t0 > 8000000000LL) {      // ~4 s at 2 GHz: a peer died
+            if (clock64() - t0 > 40000000000LL) {     // ~20 s at 2 GHz: a peer died
                 *pc.err = 1;
                 break;
             }

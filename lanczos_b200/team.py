@@ -336,6 +336,7 @@ class _TeamBase:
         ldp = (C.c_int64 * nl)(*lds)
         for s in self.shards:          # inputs were produced on torch's streams
             torch.cuda.synchronize(s.ctx.device)
+        self._pre_run_barrier()        # ranks enter the loop together (the device-side waits are bounded)
         status = self.lib.lz_team_lanczos_run(
             self.team, ops, v0p, n, C.byref(opts), alpha.ctypes.data_as(C.c_void_p),
             beta.ctypes.data_as(C.c_void_p), Vp, ldp, scale.ctypes.data_as(C.c_void_p), C.byref(info))
@@ -350,6 +351,9 @@ class _TeamBase:
         self.Lanczos_has_been_executed = True
 
     execute_LanczosOld = execute_Lanczos
+
+    def _pre_run_barrier(self):
+        pass
 
     @property
     def result(self):
@@ -449,6 +453,9 @@ class TeamLanczos(_TeamBase):
             ptrs.append(mapped.value)
         self.dist.barrier()
         return [ptrs]
+
+    def _pre_run_barrier(self):
+        self.dist.barrier()
 
     def _unmap_buffers(self):
         s = self.shards[0]
