@@ -83,7 +83,9 @@ __device__ __forceinline__ void peer_store(const PeerComm& pc, unsigned long lon
 // Whole CTA: wait until the payloads of all ranks for `seq` have landed in my buffer.
 __device__ __forceinline__ void peer_wait(const PeerComm& pc, unsigned long long seq) {
     const int slot = (int)(seq % kPeerSlots);
-    if (threadIdx.x < pc.world) {
+    // after one timeout the run is lost anyway: do not wait again (a dead peer must not turn
+    // into minutes of spinning)
+    if (threadIdx.x < pc.world && *reinterpret_cast<volatile int*>(pc.err) == 0) {
         const unsigned long long* f = pc.flags[pc.rank] + (size_t)slot * pc.world + threadIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) != seq) {
