@@ -371,11 +371,25 @@ def main():
         if cnt:
             per_kernel[k] = {"launches": cnt, "avg_ms": ms / cnt, "alg_bytes": alg[k],
                              "achieved_gbs": alg[k] / (ms / cnt) / 1e6}
-    # Gram-Schmidt kernels: bytes depend on the row count of each launch; report the aggregate
+    # Gram-Schmidt kernels: the bytes depend on the row count of each launch; with full
+    # re-orthogonalisation the schedule is known: at step j every sweep reads the j rows before row j
+    # and row j itself ((2k+3)*8*N bytes per sweep against k vectors).
+    if wl["reorth"] == "full":
+        dots_b = upd_b = 0.0
+        for c in chunks:
+            for j in range(c):
+                for p_ in range(wl["cgs_passes"]):
+                    dots_b += (j + 1) * 8.0 * N               # j basis rows + the target row
+                    upd_b += (j + 2) * 8.0 * N                # j rows + target in, target out
+        for k, tot_b in (("dots", dots_b), ("gs_update", upd_b)):
+            ms, cnt = kern[k]
+            if cnt:
+                per_kernel[k] = {"launches": cnt, "avg_ms": ms / cnt, "alg_bytes": tot_b / cnt,
+                                 "achieved_gbs": tot_b / ms / 1e6}
     gs_ms = kern["dots"][0] + kern["gs_update"][0]
     dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"] * per_kernel[k]["launches"]) if per_kernel else None
     names = {"apply": "stencil_apply_dot_kernel" if is_stencil else "spmv_sell_dot_kernel",
-             "update": "update_norm_kernel"}
+             "update": "update_norm_kernel", "dots": "cgs_dots_kernel", "gs_update": "cgs_update_kernel"}
     roofline = None
     if dom:
         pk = per_kernel[dom]
