@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - Lanczos steps/s and achieved HBM GB/s on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1|c4|c5|c3full] [--impl reference]
 
 One "step" = one Lanczos step (operator apply + alpha, three-term update + beta, and the
 re-orthogonalisation sweeps the configuration asks for).  The default workload is BASELINE
@@ -36,6 +36,9 @@ WORKLOADS = {
                    grid=(512, 512, 512), steps=60, reorth="full", cgs_passes=1),
     "c2": dict(desc="graph Laplacian of a 2D Delaunay mesh, 1M vertices, SELL-32-1024, full reorth",
                npts=1_000_000, steps=200, reorth="full", cgs_passes=1),
+    "c4": dict(desc="graph Laplacian of a 3D random geometric graph (Poisson points, mean degree 13, ~14 nnz/row), "
+                    "~50M vertices in cell order, SELL-32-1024, selective reorth, z-slabs of cells over the GPUs (strong scaling)",
+               cells=(253, 253, 252), steps=100, reorth="selective", cgs_passes=2, strong=True),
     "c5": dict(desc="3D 7-point periodic Laplacian 1024^3 (1.07 B unknowns) fp64, CGS2 every step, z-slabs over the GPUs (strong scaling)",
                grid=(1024, 1024, 1024), steps=60, reorth="full", cgs_passes=2, strong=True),
     "c1": dict(desc="2D 5-point Dirichlet Laplacian 200x200 fp64, full reorth",
@@ -171,6 +174,15 @@ def cpu_reference_leg(workload: str, budget_s: float = 20.0):
                   f"step-only (no reorth) extrapolated: {step_only:.3f} steps/s")
         return dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample,
                     step_only_value=step_only, numpy=np.__version__)
+    if workload == "c4":
+        npts, n = 200_000, 32
+        H = orc.rgg_graph_laplacian(npts, mean_degree=13.0, seed=0)
+        v0 = np.random.RandomState(99).uniform(-1, 1, npts)
+        t = orc.timed_steps(H, n, v0, reorth=True)
+        full = 50_000_000
+        return dict(value=(n / t) * npts / full, unit=UNIT, cores=cores, kind="port",
+                    sample=f"3D random geometric graph, {npts} vertices, mean degree 13, n={n}, full reorth as the "
+                           f"reference always does ({n/t:.2f} steps/s), extrapolated linearly in M to {full}")
     if workload == "c2":
         npts, n = 100_000, 40
         H = orc.delaunay_graph_laplacian(npts, seed=0)
@@ -216,6 +228,14 @@ def build_operator(lz, workload, world, rank):
         if dim == 3 and world > 1 and not wl.get("strong"):
             grid = (grid[0], grid[1], grid[2] * world)       # weak scaling in z
         return lz.StencilOperator(grid, 2.0 * dim, -1.0, bc="periodic" if dim == 3 else "dirichlet"), grid
+    if "cells" in wl:
+        # generated on the device, one row block per GPU (include/lz_synth.h)
+        from lanczos_b200 import synth
+        from lanczos_b200.engine import DeviceCSR
+        gen = synth.RggGenerator(wl["cells"], seed=0)
+        if world > 1:
+            return gen.row_block(rank, world), (gen.M,)
+        return DeviceCSR(*gen.rows(0, gen.M)), (gen.M,)
     from oracle import lanczos_oracle as orc             # input generator only (test infrastructure)
     H = orc.delaunay_graph_laplacian(wl["npts"], seed=0)
     return H, (wl["npts"],)
@@ -362,7 +382,7 @@ def main():
     if is_stencil:
         apply_bytes = 16.0 * N                      # read v_j, write w  (alpha fused)
     else:
-        nnz_true, _ = solver._device_op.nnz()
+        nnz_true, nnz_stored = solver.nnz_local() if world > 1 else solver._device_op.nnz()
         apply_bytes = 12.0 * nnz_true + 16.0 * N
     per_kernel = {}
     alg = {"apply": apply_bytes, "update": 32.0 * N}
@@ -418,9 +438,10 @@ def main():
         "config": {"workload": f"{args.workload}: {wl['desc']}", "grid": list(grid), "unknowns": M_total,
                    "unknowns_per_gpu": M_local, "lanczos_m": chunks, "reorth": wl["reorth"],
                    "cgs_passes": wl["cgs_passes"], "l2": "inputs larger than L2 (each vector %.2f GB)" % (8 * M_local / 1e9),
-                   "sharding": "z-slabs, one process per GPU" if world > 1 else "single GPU",
-                   "aggregate": "value = n_gpus * K / time: each GPU advances its 512^3 shard K steps; "
-                                "the global (n_gpus x larger) solve advances K steps",
+                   "sharding": ("z-slabs, one process per GPU" if is_stencil else "contiguous row blocks (z-slabs of cells), ghost-index exchange over peer memory, one process per GPU") if world > 1 else "single GPU",
+                   "aggregate": ("strong scaling: value = K / time of the one global solve" if strong else
+                                 "value = n_gpus * K / time: each GPU advances its 512^3 shard K steps; "
+                                 "the global (n_gpus x larger) solve advances K steps"),
                    "global_steps_per_sec": K / (ms_dev / 1e3)},
         "e2e": {"value": (1 if strong else world) * K / e_wall, "unit": UNIT, "h2d_bytes_per_step": 8.0 * M_local * len(chunks) / K,
                 "d2h_bytes_per_step": (sum(3 * (8 * (c + 2) + 512) + 32 for c in chunks)) / K,
@@ -434,6 +455,9 @@ def main():
         "fused_step": fused,
         "ritz_lowest": [float(x) for x in theta[:4]],
     }
+    if not is_stencil:
+        line["config"]["nnz_per_gpu"] = int(nnz_true)
+        line["config"]["sell_stored_over_true"] = float(nnz_stored) / max(1, nnz_true)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -103,6 +103,15 @@ int lz_op_csr_shard_create(lz_ctx* ctx, int64_t M_local, int64_t ncols, int64_t 
                            const int32_t* indptr_host, const int32_t* indices_host,
                            const double* data_host, int fmt, int sigma, lz_op** out);
 
+/* As lz_op_csr_create / lz_op_csr_shard_create for CSR arrays that already live on the context's
+ * device - the reference's GPU mode holds H as a cupyx matrix in device memory (Lanczos.py:88,
+ * read back with H.get() at :137).  The arrays are copied / converted on the device (SELL: same
+ * layout, bit for bit, as the host conversion); ncols == M for a whole operator, > M for a row
+ * shard with renumbered ghost columns.  Synchronises. */
+int lz_op_csr_create_dev(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, const int32_t* indptr_dev,
+                         const int32_t* indices_dev, const double* data_dev, int fmt, int sigma,
+                         lz_op** out);
+
 int lz_op_rows(const lz_op* op, int64_t* M);
 int lz_op_nnz(const lz_op* op, int64_t* nnz_true, int64_t* nnz_stored);
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "lz_op_stencil27_create": (C.c_int, [_vp, _P(_i64), C.c_int, _P(_dbl), _vp, _P(_vp)]),
     "lz_op_csr_create": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, C.c_int, C.c_int, _P(_vp)]),
     "lz_op_csr_shard_create": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, C.c_int, C.c_int, _P(_vp)]),
+    "lz_op_csr_create_dev": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, C.c_int, C.c_int, _P(_vp)]),
     "lz_op_rows": (C.c_int, [_vp, _P(_i64)]),
     "lz_op_nnz": (C.c_int, [_vp, _P(_i64), _P(_i64)]),
     "lz_op_apply": (C.c_int, [_vp, _vp, _vp]),

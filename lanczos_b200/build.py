@@ -13,6 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblanczos_b200.so")
+SYNTH_LIB = os.path.join(HERE, "liblz_synth.so")          # synthetic benchmark inputs (include/lz_synth.h)
+SYNTH_SOURCES = ["synth_rgg.cu"]
 SOURCES = ["capi.cu", "stencil.cu", "stencil27.cu", "vecops.cu", "reorth.cu", "spmv.cu", "fused.cu", "lanczos.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -40,7 +42,20 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_synth(force: bool = False) -> str:
+    """liblz_synth.so: device-side generator of the config-4 random geometric graph (bench/tests)."""
+    srcs = [os.path.join(CSRC, s) for s in SYNTH_SOURCES]
+    deps = srcs + [os.path.join(os.path.dirname(HERE), "include", "lz_synth.h")]
+    if not force and os.path.exists(SYNTH_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(SYNTH_LIB) for d in deps):
+        return SYNTH_LIB
+    res = subprocess.run([_nvcc()] + NVCC_FLAGS + ["-o", SYNTH_LIB] + srcs, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return SYNTH_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    build_synth(force)
     if not force and not is_stale():
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()

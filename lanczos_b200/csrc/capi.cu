@@ -29,6 +29,8 @@ int build_csr(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const in
               const double* data);
 int build_sell(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const int32_t* indices,
                const double* data, int sigma);
+int build_from_device(lz_op* op, int64_t M, int64_t ncols, int64_t nnz, const int32_t* indptr,
+                      const int32_t* indices, const double* data, int fmt, int sigma);
 
 int launch_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y, double* partials,
                      int* nparts, int* launches, const int* flag_dev) {
@@ -184,6 +186,22 @@ int lz_op_csr_shard_create(lz_ctx* ctx, int64_t M_local, int64_t ncols, int64_t 
                            const int32_t* indices, const double* data, int fmt, int sigma, lz_op** out) {
     LZ_REQUIRE(ncols >= M_local, "lz_op_csr_shard_create: ncols < M_local");
     return csr_create_impl(ctx, M_local, ncols, nnz, indptr, indices, data, fmt, sigma, out);
+}
+
+int lz_op_csr_create_dev(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, const int32_t* indptr_dev,
+                         const int32_t* indices_dev, const double* data_dev, int fmt, int sigma, lz_op** out) {
+    LZ_REQUIRE(ctx && indptr_dev && out && (nnz == 0 || (indices_dev && data_dev)), "lz_op_csr_create_dev: null argument");
+    LZ_REQUIRE(M >= 1 && M <= 0x7fffffff && ncols >= M && ncols <= 0x7fffffff, "lz_op_csr_create_dev: M / ncols out of range");
+    LZ_REQUIRE(nnz >= 0 && nnz <= 0x7fffffff, "lz_op_csr_create_dev: nnz must fit int32 indptr");
+    LZ_REQUIRE(fmt == LZ_FMT_CSR || fmt == LZ_FMT_SELL, "lz_op_csr_create_dev: unknown format %d", fmt);
+    LZ_CUDA(cudaSetDevice(ctx->device));
+    lz_op* op = new lz_op();
+    op->ctx = ctx;
+    const int st = build_from_device(op, M, ncols, nnz, indptr_dev, indices_dev, data_dev, fmt, sigma);
+    if (st != LZ_OK) { lz_op_destroy(op); return st; }
+    op->ncols = ncols;
+    *out = op;
+    return LZ_OK;
 }
 
 static int csr_create_impl(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, const int32_t* indptr,

@@ -266,4 +266,163 @@ int build_sell(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const i
     return LZ_OK;
 }
 
+// ---- device-side construction (operator already resident in HBM) --------------------------------
+// The reference's GPU mode holds H as a cupyx matrix on the device (Lanczos.py:88,137); at the sizes
+// of BASELINE config 4 (5e7 rows, 7e8 entries) a round trip through host CSR would dominate set-up,
+// so the SELL-32-sigma conversion also exists as kernels.  It reproduces build_sell bit for bit
+// (stable descending-length order inside each window), which tests/test_gpu_parity.py checks.
+
+// error bits: 1 indptr not monotone / does not span [0, nnz], 2 column out of range
+__global__ void __launch_bounds__(kThreads)
+csr_validate_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, int64_t M,
+                    int64_t ncols, int64_t nnz, int* __restrict__ err) {
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * kThreads;
+    int bad = 0;
+    if (tid == 0 && (indptr[0] != 0 || (int64_t)indptr[M] != nnz)) bad |= 1;
+    for (int64_t i = tid; i < M; i += nthr)
+        if (indptr[i + 1] < indptr[i]) bad |= 1;
+    for (int64_t k = tid; k < nnz; k += nthr) {
+        const int32_t c = indices[k];
+        if (c < 0 || c >= ncols) bad |= 2;
+    }
+    if (bad) atomicOr(err, bad);
+}
+
+// One CTA per window of sigma rows: slot of row t = #(longer rows) + #(equally long rows before it).
+__global__ void __launch_bounds__(kThreads)
+sell_order_kernel(const int32_t* __restrict__ indptr, int64_t M, int sigma, int32_t* __restrict__ row_of) {
+    extern __shared__ int32_t s_len[];
+    const int64_t w0 = (int64_t)blockIdx.x * sigma;
+    const int cnt = (int)min((int64_t)sigma, M - w0);
+    for (int t = threadIdx.x; t < cnt; t += kThreads) s_len[t] = indptr[w0 + t + 1] - indptr[w0 + t];
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt; t += kThreads) {
+        const int32_t mine = s_len[t];
+        int slot = 0;
+        for (int u = 0; u < cnt; ++u) {
+            const int32_t l = s_len[u];
+            slot += (l > mine) || (l == mine && u < t);
+        }
+        row_of[w0 + slot] = (int32_t)(w0 + t);
+    }
+}
+
+// One warp per chunk: stored entries of the chunk = 32 * (longest of its rows).
+__global__ void __launch_bounds__(kThreads)
+sell_width_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ row_of, int64_t nchunks,
+                  int64_t* __restrict__ stored) {
+    const int64_t c = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    if (c >= nchunks) return;
+    const int lane = threadIdx.x & 31;
+    const int32_t r = row_of[c * 32 + lane];
+    int w = r >= 0 ? indptr[r + 1] - indptr[r] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if (lane == 0) stored[c] = (int64_t)w * 32;
+}
+
+__global__ void __launch_bounds__(kThreads)
+sell_fill_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                 const double* __restrict__ data, const int32_t* __restrict__ row_of,
+                 const int64_t* __restrict__ chunk_off, int64_t nchunks, int32_t* __restrict__ col,
+                 double* __restrict__ val) {
+    const int64_t c = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    if (c >= nchunks) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t o0 = chunk_off[c];
+    const int width = (int)((chunk_off[c + 1] - o0) >> 5);
+    const int32_t r = row_of[c * 32 + lane];
+    const int32_t k0 = r >= 0 ? indptr[r] : 0;
+    const int len = r >= 0 ? indptr[r + 1] - k0 : 0;
+    const int32_t pad_col = r >= 0 ? r : 0;
+    for (int k = 0; k < width; ++k) {
+        const int64_t at = o0 + (int64_t)k * 32 + lane;
+        if (k < len) { col[at] = indices[k0 + k]; val[at] = data[k0 + k]; }
+        else { col[at] = pad_col; val[at] = 0.0; }
+    }
+}
+
+// exclusive prefix of n int64 values by one CTA (set-up only; n = number of chunks + 1)
+__global__ void __launch_bounds__(1024)
+scan_i64_kernel(int64_t* __restrict__ a, int64_t n) {
+    __shared__ int64_t s_tot[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (n + 1023) / 1024;
+    const int64_t b = min(n, t * per), e = min(n, b + per);
+    int64_t sum = 0;
+    for (int64_t i = b; i < e; ++i) sum += a[i];
+    s_tot[t] = sum;
+    __syncthreads();
+    if (t == 0) {
+        int64_t run = 0;
+        for (int i = 0; i < 1024; ++i) { const int64_t v = s_tot[i]; s_tot[i] = run; run += v; }
+    }
+    __syncthreads();
+    int64_t run = s_tot[t];
+    for (int64_t i = b; i < e; ++i) { const int64_t v = a[i]; a[i] = run; run += v; }
+}
+
+int build_from_device(lz_op* op, int64_t M, int64_t ncols, int64_t nnz, const int32_t* indptr,
+                      const int32_t* indices, const double* data, int fmt, int sigma) {
+    lz_ctx* ctx = op->ctx;
+    cudaStream_t q = ctx->stream;
+    const int wide = ctx->sms * 8;
+    // validate on the device (same conditions as the host path)
+    int* err = reinterpret_cast<int*>(ctx->scratch);
+    LZ_CUDA(cudaMemsetAsync(err, 0, sizeof(int), q));
+    csr_validate_kernel<<<wide, kThreads, 0, q>>>(indptr, indices, M, ncols, nnz, err);
+    int h_err = 0;
+    LZ_CUDA(cudaMemcpyAsync(&h_err, err, sizeof(int), cudaMemcpyDeviceToHost, q));
+    LZ_CUDA(cudaStreamSynchronize(q));
+    LZ_REQUIRE(!(h_err & 1), "lz_op_csr_create_dev: indptr is not monotone or does not span [0, nnz]");
+    LZ_REQUIRE(!(h_err & 2), "lz_op_csr_create_dev: column index out of range");
+    op->M = M;
+    if (fmt == LZ_FMT_CSR) {
+        op->kind = LZ_OP_CSR;
+        op->csr.nnz = nnz;
+        LZ_CUDA(cudaMalloc((void**)&op->csr.indptr, (size_t)(M + 1) * 4));
+        LZ_CUDA(cudaMalloc((void**)&op->csr.indices, nnz ? (size_t)nnz * 4 : 16));
+        LZ_CUDA(cudaMalloc((void**)&op->csr.data, nnz ? (size_t)nnz * 8 : 16));
+        LZ_CUDA(cudaMemcpyAsync(op->csr.indptr, indptr, (size_t)(M + 1) * 4, cudaMemcpyDeviceToDevice, q));
+        if (nnz) {
+            LZ_CUDA(cudaMemcpyAsync(op->csr.indices, indices, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, q));
+            LZ_CUDA(cudaMemcpyAsync(op->csr.data, data, (size_t)nnz * 8, cudaMemcpyDeviceToDevice, q));
+        }
+        const double mean = (double)nnz / (double)M;
+        op->csr.lanes_per_row = mean <= 2.5 ? 2 : mean <= 5.0 ? 4 : mean <= 12.0 ? 8 : mean <= 24.0 ? 16 : 32;
+        LZ_CUDA(cudaStreamSynchronize(q));
+        return LZ_OK;
+    }
+    if (sigma <= 0) sigma = 1024;
+    sigma = (sigma + 31) / 32 * 32;
+    LZ_REQUIRE(sigma <= 8192, "lz_op_csr_create_dev: sigma must be <= 8192 rows");
+    const int64_t nchunks = (M + 31) / 32;
+    lz_sell& sl = op->sell;
+    op->kind = LZ_OP_SELL;
+    sl.nnz_true = nnz;
+    sl.nchunks = nchunks;
+    sl.sigma = sigma;
+    LZ_CUDA(cudaMalloc((void**)&sl.row_of, (size_t)nchunks * 32 * 4));
+    LZ_CUDA(cudaMalloc((void**)&sl.chunk_off, (size_t)(nchunks + 1) * 8));
+    LZ_CUDA(cudaMemsetAsync(sl.row_of, 0xff, (size_t)nchunks * 32 * 4, q));          // -1: padding rows
+    LZ_CUDA(cudaMemsetAsync(sl.chunk_off, 0, (size_t)(nchunks + 1) * 8, q));
+    const int64_t nwin = (M + sigma - 1) / sigma;
+    sell_order_kernel<<<(unsigned)nwin, kThreads, (size_t)sigma * 4, q>>>(indptr, M, sigma, sl.row_of);
+    const unsigned cgrid = (unsigned)((nchunks + kWarps - 1) / kWarps);
+    sell_width_kernel<<<cgrid, kThreads, 0, q>>>(indptr, sl.row_of, nchunks, sl.chunk_off);
+    scan_i64_kernel<<<1, 1024, 0, q>>>(sl.chunk_off, nchunks + 1);
+    int64_t stored = 0;
+    LZ_CUDA(cudaMemcpyAsync(&stored, sl.chunk_off + nchunks, 8, cudaMemcpyDeviceToHost, q));
+    LZ_CUDA(cudaStreamSynchronize(q));
+    LZ_CUDA(cudaGetLastError());
+    sl.nnz_stored = stored;
+    LZ_CUDA(cudaMalloc((void**)&sl.col, stored ? (size_t)stored * 4 : 16));
+    LZ_CUDA(cudaMalloc((void**)&sl.val, stored ? (size_t)stored * 8 : 16));
+    sell_fill_kernel<<<cgrid, kThreads, 0, q>>>(indptr, indices, data, sl.row_of, sl.chunk_off, nchunks, sl.col, sl.val);
+    LZ_CUDA(cudaGetLastError());
+    LZ_CUDA(cudaStreamSynchronize(q));
+    return LZ_OK;
+}
+
 }  // namespace lz

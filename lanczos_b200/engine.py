@@ -196,6 +196,31 @@ class DeviceOperator:
             indices.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p), f, int(sigma), C.byref(h)))
         return cls(ctx, h, A.shape[0], fmt)
 
+    @classmethod
+    def from_device_csr(cls, ctx: Context, indptr, indices, data, ncols: Optional[int] = None,
+                        fmt: str = "auto", sigma: int = 0) -> "DeviceOperator":
+        """CSR arrays that already live on the GPU (CUDA tensors: int32 indptr/indices, fp64 data) -
+        the counterpart of the cupyx matrix the reference holds in GPU mode (Lanczos.py:88).
+        Converted on the device (lz_op_csr_create_dev); `ncols` > M makes a row shard."""
+        torch = _torch()
+        M = int(indptr.numel()) - 1
+        nnz = int(indices.numel())
+        for t, dt in ((indptr, torch.int32), (indices, torch.int32), (data, torch.float64)):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dt and t.is_contiguous()):
+                raise TypeError("from_device_csr: contiguous CUDA tensors (int32 indptr/indices, float64 data)")
+            if t.device.index != ctx.device:
+                raise ValueError("from_device_csr: the arrays live on another device than the context")
+        if fmt == "auto":
+            fmt = "sell"
+        f = {"csr": LZ_FMT_CSR, "sell": LZ_FMT_SELL}[fmt]
+        h = C.c_void_p()
+        torch.cuda.current_stream(ctx.device).synchronize()      # the arrays were produced on torch's stream
+        _capi.check(ctx.lib.lz_op_csr_create_dev(
+            ctx.handle, M, M if ncols is None else int(ncols), nnz, C.c_void_p(indptr.data_ptr()),
+            C.c_void_p(indices.data_ptr() if nnz else 0), C.c_void_p(data.data_ptr() if nnz else 0),
+            f, int(sigma), C.byref(h)))
+        return cls(ctx, h, M, fmt)
+
     def nnz(self):
         t, s = C.c_int64(), C.c_int64()
         _capi.check(self.ctx.lib.lz_op_nnz(self.handle, C.byref(t), C.byref(s)))
@@ -235,6 +260,30 @@ class DeviceOperator:
             pass
 
 
+@dataclass(eq=False)
+class DeviceCSR:
+    """A square sparse operator whose CSR arrays are CUDA tensors (int32 indptr / indices, fp64 data):
+    what `cupyx.scipy.sparse.csr_matrix` is to the reference's GPU mode (Lanczos.py:88)."""
+    indptr: object
+    indices: object
+    data: object
+
+    @property
+    def shape(self):
+        M = int(self.indptr.numel()) - 1
+        return (M, M)
+
+    @property
+    def nnz(self):
+        return int(self.indices.numel())
+
+    def get(self):
+        """Host scipy matrix (the `.get()` of a cupyx matrix, Lanczos.py:137)."""
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(), self.indptr.cpu().numpy()),
+                             shape=self.shape)
+
+
 def as_device_operator(H, ctx: Context, fmt: str = "auto", sigma: int = 0) -> DeviceOperator:
     """Map what the reference accepts as `H` onto a device operator.  scipy.sparse matrices
     (CSR as in Regular, CSC as IrrHamiltonian produces) and StencilOperator descriptors are
@@ -244,6 +293,8 @@ def as_device_operator(H, ctx: Context, fmt: str = "auto", sigma: int = 0) -> De
         return H
     if isinstance(H, StencilOperator):
         return H.device_handle(ctx)
+    if isinstance(H, DeviceCSR):
+        return DeviceOperator.from_device_csr(ctx, H.indptr, H.indices, H.data, fmt=fmt, sigma=sigma)
     if sp.issparse(H):
         return DeviceOperator.from_scipy(ctx, H, fmt=fmt, sigma=sigma)
     raise TypeError(
@@ -254,6 +305,8 @@ def as_device_operator(H, ctx: Context, fmt: str = "auto", sigma: int = 0) -> De
 def operator_rows(H) -> int:
     if isinstance(H, (StencilOperator, DeviceOperator)):
         return H.M
+    if isinstance(H, DeviceCSR):
+        return H.shape[0]
     return int(np.shape(H)[0])
 
 

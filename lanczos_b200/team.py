@@ -146,6 +146,14 @@ class RowBlockPlan:
         return indptr, local.astype(np.int32), np.ascontiguousarray(A.data[lo:hi], dtype=np.float64), \
             (r1 - r0) + len(self.ghost_cols[rank])
 
+    def make_op(self, lib, ctx: Context, rank: int, fmt: int, sigma: int):
+        indptr, indices, data, ncols = self.local_csr(rank)
+        h = C.c_void_p()
+        _capi.check(lib.lz_op_csr_shard_create(
+            ctx.handle, self.local_rows(rank), ncols, len(data), indptr.ctypes.data_as(C.c_void_p),
+            indices.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p), fmt, sigma, C.byref(h)))
+        return h
+
     def send_lists(self, rank: int):
         """What `rank` sends: (send_idx, seg_start[world+1], dst_off[world]).  For destination q the
         entries are q's ghost columns owned by `rank` (as local row indices), and they land at the
@@ -163,6 +171,111 @@ class RowBlockPlan:
             off.append(a)
         send = np.concatenate(idx).astype(np.int32) if idx else np.zeros(0, dtype=np.int32)
         return send, np.asarray(seg, dtype=np.int32), np.asarray(off, dtype=np.int64)
+
+
+@dataclass(eq=False)
+class RowBlock:
+    """Rows [starts[rank], starts[rank + 1]) of a square sparse operator with M rows, as CSR with
+    GLOBAL column indices.  The arrays are NumPy arrays, CPU tensors or CUDA tensors (int32
+    indptr / indices, fp64 data); a rank only ever holds its own block, so operators that do not
+    fit one host or one GPU (BASELINE config 4: 5e7 rows, 7e8 entries) can still be sharded."""
+    M: int
+    starts: Sequence[int]
+    rank: int
+    indptr: object
+    indices: object
+    data: object
+
+    @property
+    def shape(self):
+        return (self.M, self.M)
+
+
+def _as_tensor(a, dtype):
+    import torch
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(dtype).contiguous()
+
+
+class BlockPlan:
+    """RowBlockPlan for operators given block by block: the same numbering contract (owned columns
+    first, then the rank's sorted ghost list; every owner's run of a ghost list is contiguous), but
+    each rank derives its part from its own block and only the ghost lists travel (`gather`: a
+    function that turns this process's {rank: ghost list} into the lists of all ranks -
+    torch.distributed.all_gather_object under torchrun, identity when one process holds every block).
+    The index work runs in torch on whatever device holds the block (plumbing, not arithmetic)."""
+
+    def __init__(self, blocks: Sequence[RowBlock], world: int, gather=None):
+        import torch
+        self.world = int(world)
+        b0 = blocks[0]
+        self.M = int(b0.M)
+        self.starts = [int(x) for x in b0.starts]
+        self.plane = 0
+        if len(self.starts) != self.world + 1 or self.starts[0] != 0 or self.starts[-1] != self.M:
+            raise ValueError("RowBlock.starts must be world + 1 offsets from 0 to M")
+        if any(self.starts[r + 1] <= self.starts[r] for r in range(self.world)):
+            raise ValueError("every rank needs at least one row")
+        self.blocks, self._local, mine = {}, {}, {}
+        for b in blocks:
+            if [int(x) for x in b.starts] != self.starts or int(b.M) != self.M:
+                raise ValueError("row blocks disagree about the partition")
+            r0, r1 = self.rows(b.rank)
+            indptr = _as_tensor(b.indptr, torch.int32)
+            indices = _as_tensor(b.indices, torch.int32)
+            data = _as_tensor(b.data, torch.float64)
+            if indptr.numel() != r1 - r0 + 1:
+                raise ValueError(f"block of rank {b.rank}: indptr must have {r1 - r0 + 1} entries")
+            if self.world == 1:
+                ghosts = torch.zeros(0, dtype=torch.int64, device=indices.device)
+                local = indices
+            else:
+                own = (indices >= r0) & (indices < r1)
+                ghosts = torch.unique(indices[~own]).to(torch.int64)          # sorted
+                local = torch.where(own, indices - r0,
+                                    (r1 - r0) + torch.searchsorted(ghosts, indices.to(torch.int64)).to(torch.int32))
+                del own
+            self.blocks[b.rank] = b
+            self._local[b.rank] = (indptr, local.to(torch.int32).contiguous(), data, (r1 - r0) + int(ghosts.numel()))
+            mine[b.rank] = ghosts.cpu().numpy()
+        every = mine if gather is None else gather(mine)
+        if sorted(every) != list(range(self.world)):
+            raise ValueError("ghost lists of some ranks are missing")
+        self.ghost_cols = [np.asarray(every[r], dtype=np.int64) for r in range(self.world)]
+        self.nghost_max = max(len(g) for g in self.ghost_cols)
+
+    def rows(self, rank: int):
+        return self.starts[rank], self.starts[rank + 1]
+
+    def local_rows(self, rank: int) -> int:
+        return self.starts[rank + 1] - self.starts[rank]
+
+    owner_segments = RowBlockPlan.owner_segments
+    send_lists = RowBlockPlan.send_lists
+
+    def local_csr(self, rank: int):
+        """(indptr, indices, data, ncols) with renumbered columns, on the device that holds the block."""
+        return self._local[rank]
+
+    def make_op(self, lib, ctx: Context, rank: int, fmt: int, sigma: int):
+        indptr, indices, data, ncols = self._local[rank]
+        h = C.c_void_p()
+        nnz = int(indices.numel())
+        if indptr.is_cuda:
+            if indptr.device.index != ctx.device:
+                raise ValueError(f"the block of rank {rank} lives on another device than its shard")
+            import torch
+            torch.cuda.current_stream(ctx.device).synchronize()
+            _capi.check(lib.lz_op_csr_create_dev(
+                ctx.handle, self.local_rows(rank), ncols, nnz, C.c_void_p(indptr.data_ptr()),
+                C.c_void_p(indices.data_ptr() if nnz else 0), C.c_void_p(data.data_ptr() if nnz else 0),
+                fmt, sigma, C.byref(h)))
+        else:
+            _capi.check(lib.lz_op_csr_shard_create(
+                ctx.handle, self.local_rows(rank), ncols, nnz, C.c_void_p(indptr.data_ptr()),
+                C.c_void_p(indices.data_ptr() if nnz else 0), C.c_void_p(data.data_ptr() if nnz else 0),
+                fmt, sigma, C.byref(h)))
+        return h
 
 
 # --------------------------------------------------------------------------- device side
@@ -189,14 +302,22 @@ class _TeamBase:
         elif sp.issparse(H):
             self.plan = RowBlockPlan(H, self.world)
             self.sparse = True
+        elif isinstance(H, RowBlock) or (isinstance(H, (list, tuple)) and H and all(isinstance(b, RowBlock) for b in H)):
+            blocks = [H] if isinstance(H, RowBlock) else list(H)
+            self.plan = BlockPlan(blocks, self.world, gather=self._gather_ghost_lists)
+            self.sparse = True
         else:
-            raise TypeError("row-sharded runs take a StencilOperator or a scipy.sparse matrix")
+            raise TypeError("row-sharded runs take a StencilOperator, a scipy.sparse matrix or RowBlock(s)")
         self.M = self.plan.M
         self.lib = _capi.load()
         self.team = None
         self.max_steps = 0
         self.Lanczos_has_been_executed = False
         self._results = None
+
+    def _gather_ghost_lists(self, mine: dict) -> dict:
+        """{rank: ghost list} of every rank from those of this process (one process: identity)."""
+        return mine
 
     # subclasses: self.shards (list of _Shard), self._map_buffers(nbytes) -> per-shard list of `world` pointers
     def _ensure_team(self, n: int):
@@ -234,12 +355,7 @@ class _TeamBase:
         if self.sparse:
             f = {"csr": _capi.LZ_FMT_CSR, "sell": _capi.LZ_FMT_SELL, "auto": _capi.LZ_FMT_SELL}[self.fmt]
             for s in self.shards:
-                indptr, indices, data, ncols = plan.local_csr(s.rank)
-                h = C.c_void_p()
-                _capi.check(self.lib.lz_op_csr_shard_create(
-                    s.ctx.handle, plan.local_rows(s.rank), ncols, len(data), indptr.ctypes.data_as(C.c_void_p),
-                    indices.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p), f, self.sigma, C.byref(h)))
-                s.op_handle = h
+                s.op_handle = plan.make_op(self.lib, s.ctx, s.rank, f, self.sigma)
             return
         off3 = plan.off3(H.off)
         for s in self.shards:
@@ -381,6 +497,12 @@ class _TeamBase:
     def M_local(self):
         return self.plan.local_rows(self.shards[0].rank)
 
+    def nnz_local(self):
+        """(true, stored) entries of the first local shard of a sparse operator."""
+        t, s = C.c_int64(), C.c_int64()
+        _capi.check(self.lib.lz_op_nnz(self.shards[0].op_handle, C.byref(t), C.byref(s)))
+        return t.value, s.value
+
 
 class LocalTeamLanczos(_TeamBase):
     """All `world` shards driven by this process: on one GPU (tests of the exchange logic - the
@@ -456,6 +578,14 @@ class TeamLanczos(_TeamBase):
 
     def _pre_run_barrier(self):
         self.dist.barrier()
+
+    def _gather_ghost_lists(self, mine: dict) -> dict:
+        parts = [None] * self.dist.get_world_size()
+        self.dist.all_gather_object(parts, mine)
+        out = {}
+        for p in parts:
+            out.update(p)
+        return out
 
     def _unmap_buffers(self):
         s = self.shards[0]
