@@ -249,6 +249,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--step-kernel", default="auto", choices=["auto", "two_pass", "recompute", "fused"],
+                    help="auto = the library default (recompute for matrix-free operators)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.steps is None:
@@ -272,7 +274,7 @@ def main():
     K, W = int(args.steps), max(3, int(args.warmup))
     H, grid = build_operator(lz, args.workload, world, rank)
     M_total = int(np.prod(grid))
-    opts = dict(reorth=wl["reorth"], cgs_passes=wl["cgs_passes"], ref_compat=True)
+    opts = dict(reorth=wl["reorth"], cgs_passes=wl["cgs_passes"], ref_compat=True, step_kernel=args.step_kernel)
 
     if world > 1:
         from lanczos_b200 import team as lzteam
@@ -348,8 +350,10 @@ def main():
     # (per-kernel roofline).  Kept out of region A because the event records break up
     # back-to-back launches and cost several percent of step time.
     kern = {"apply": [0.0, 0], "update": [0.0, 0], "dots": [0.0, 0], "gs_update": [0.0, 0], "fused": [0.0, 0]}
+    step_kernel = "two_pass"
     for c in chunks:
         res = solve(c, v0_dev, profile=True)
+        step_kernel = res.step_kernel
         for k, (ms, cnt) in res.kernel_ms.items():
             acc = kern.setdefault(k, [0.0, 0])
             acc[0] += ms
@@ -379,13 +383,17 @@ def main():
     peak, peak_src = measured_peaks()
     N = M_local
     is_stencil = "grid" in wl
+    recompute = step_kernel == "recompute"
     if is_stencil:
-        apply_bytes = 16.0 * N                      # read v_j, write w  (alpha fused)
+        # two-pass: K1 reads v_j, writes w (alpha fused); recompute: KA reads v_j only
+        apply_bytes = 8.0 * N if recompute else 16.0 * N
     else:
         nnz_true, nnz_stored = solver.nnz_local() if world > 1 else solver._device_op.nnz()
         apply_bytes = 12.0 * nnz_true + 16.0 * N
     per_kernel = {}
-    alg = {"apply": apply_bytes, "update": 32.0 * N}
+    # K3 reads w, v_j, v_{j-1}, writes r; KB (recompute) reads v_j, v_{j-1}, writes r and applies H again
+    update_bytes = 24.0 * N if recompute else 32.0 * N
+    alg = {"apply": apply_bytes, "update": update_bytes}
     for k in ("apply", "update"):
         ms, cnt = kern[k]
         if cnt:
@@ -408,19 +416,23 @@ def main():
                                  "achieved_gbs": tot_b / ms / 1e6}
     gs_ms = kern["dots"][0] + kern["gs_update"][0]
     dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"] * per_kernel[k]["launches"]) if per_kernel else None
-    names = {"apply": "stencil_apply_dot_kernel" if is_stencil else "spmv_sell_dot_kernel",
-             "update": "update_norm_kernel", "dots": "cgs_dots_kernel", "gs_update": "cgs_update_kernel"}
+    names = {"apply": "stencil_apply_dot_kernel<MODE=1> (KA)" if recompute else ("stencil_apply_dot_kernel" if is_stencil else "spmv_sell_dot_kernel"),
+             "update": "stencil_apply_dot_kernel<MODE=2> (KB)" if recompute else "update_norm_kernel",
+             "dots": "cgs_dots_kernel", "gs_update": "cgs_update_kernel"}
+    ncu_names = {"apply": "stencil_apply_dot_kernel<2, 1, 1, 0, 1>" if recompute else names["apply"],
+                 "update": "stencil_apply_dot_kernel<2, 1, 1, 0, 2>" if recompute else names["update"],
+                 "dots": names["dots"], "gs_update": names["gs_update"]}
     roofline = None
     if dom:
         pk = per_kernel[dom]
-        traffic = ncu_traffic(names[dom]) if (args.workload in ("c3", "c3full") and M_local == 512 ** 3) else None
+        traffic = ncu_traffic(ncu_names[dom]) if (args.workload in ("c3", "c3full") and M_local == 512 ** 3) else None
         roofline = {"kernel": names[dom], "bound": "hbm", "achieved": pk["achieved_gbs"], "peak": peak,
                     "unit": "GB/s", "frac": pk["achieved_gbs"] / peak, "traffic": traffic,
                     "peak_source": peak_src, "alg_bytes_per_launch": pk["alg_bytes"],
                     "avg_launch_ms": pk["avg_ms"], "launches": pk["launches"],
                     "timing": "CUDA-event pair around every launch of a second K-step solve on the launching stream",
                     "frac_of_8TBs_nominal": pk["achieved_gbs"] / 8000.0}
-    step_bytes = apply_bytes + 32.0 * N
+    step_bytes = apply_bytes + update_bytes
     ms_per_step = ms_dev / K
     # whole-job aggregate: every rank advances its own 512^3-unknown shard K steps (weak scaling),
     # so the job processes world*K shard-steps; at N = 1 this is plain Lanczos steps/s.
@@ -429,7 +441,10 @@ def main():
     fused = {"alg_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / ms_per_step / 1e6 if reorths == 0 else None,
              "frac_of_measured_peak": step_bytes / ms_per_step / 1e6 / peak if reorths == 0 else None,
              "frac_of_8TBs_nominal": step_bytes / ms_per_step / 1e6 / 8000.0 if reorths == 0 else None,
-             "note": "48*N B/step two-pass fused step (SURVEY 8d); null when Gram-Schmidt sweeps ran"}
+             "step_kernel": step_kernel,
+             "note": "bytes per plain step: 32*N recompute step (KA 8N + KB 24N, matrix-free operators), 48*N two-pass step "
+                     "(SURVEY 8d), + the operator's own bytes for stored operators; null when Gram-Schmidt sweeps ran",
+             "frac_of_48N_at_measured_peak": 48.0 * N / ms_per_step / 1e6 / peak if (reorths == 0 and is_stencil) else None}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

@@ -136,9 +136,12 @@ typedef struct lz_run_opts {
                               before the sweep); 0: v0/|v0| is the first basis vector */
     int32_t profile;       /* 1: bracket the bandwidth kernels with CUDA events and report
                               their summed device times in lz_run_info (bench.py roofline) */
-    int32_t step_kernel;   /* 0 auto (= 1 today); 1 two-pass step (K1 apply+dot, K3 update+norm:
-                              48*M B); 2 single-pass fused step KF (40*M B; 3-D structured
-                              grids with nx % 64 == 0, ny % 8 == 0, one GPU, reorth != full)  */
+    int32_t step_kernel;   /* 0 auto (3 for matrix-free operators, else 1); 1 two-pass step (K1
+                              apply+dot, K3 update+norm: 48*M B + the operator's own bytes);
+                              2 single-pass fused step KF (40*M B; 3-D structured grids with
+                              nx % 64 == 0, ny % 8 == 0, one GPU, reorth != full);
+                              3 recompute step (matrix-free operators: KA reduces alpha without
+                              writing H v, KB applies H again inside the update: 32*M B)       */
     int32_t reserved;
     double  breakdown_tol; /* stop when beta <= breakdown_tol * |alpha_0| (0: only 0/NaN) */
     double  select_tol;    /* selective: orthogonality level that triggers (0 -> sqrt(eps)) */
@@ -154,11 +157,12 @@ typedef struct lz_run_info {
     int32_t gsupd_launches;
     int32_t fused_launches;
     float   gpu_ms;        /* device time of the loop (CUDA events on the stream)    */
-    float   apply_ms;      /* ... K1/K2 operator apply + alpha dot                   */
-    float   update_ms;     /* ... K3 three-term update + norm                        */
+    float   apply_ms;      /* ... K1/K2 operator apply + alpha dot (KA when step_kernel == 3) */
+    float   update_ms;     /* ... K3 three-term update + norm (KB when step_kernel == 3)      */
     float   dots_ms;       /* ... K4a Gram-Schmidt dots                              */
     float   gsupd_ms;      /* ... K4b Gram-Schmidt update                            */
     float   fused_ms;      /* ... KF single-pass fused step                          */
+    int32_t step_kernel;   /* the step kernel that ran (1, 2 or 3 as in lz_run_opts)  */
 } lz_run_info;
 
 /* Runs n steps from v0_dev (M doubles).  Outputs: alpha_host[n], beta_host[n-1]

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblanczos_b200.so")
+# LANCZOS_B200_LIB: load another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("LANCZOS_B200_LIB") or os.path.join(_HERE, "liblanczos_b200.so")
 
 LZ_OK, LZ_ERR_INVALID, LZ_ERR_CUDA, LZ_ERR_NOMEM, LZ_ERR_BREAKDOWN, LZ_ERR_UNSUPPORTED, LZ_ERR_PEER = range(7)
 LZ_BC_PERIODIC, LZ_BC_DIRICHLET = 0, 1
@@ -39,7 +40,8 @@ class RunInfo(C.Structure):
                 ("dots_launches", C.c_int32), ("gsupd_launches", C.c_int32),
                 ("fused_launches", C.c_int32),
                 ("gpu_ms", C.c_float), ("apply_ms", C.c_float), ("update_ms", C.c_float),
-                ("dots_ms", C.c_float), ("gsupd_ms", C.c_float), ("fused_ms", C.c_float)]
+                ("dots_ms", C.c_float), ("gsupd_ms", C.c_float), ("fused_ms", C.c_float),
+                ("step_kernel", C.c_int32)]
 
 
 _vp, _i32, _i64, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double

@@ -25,6 +25,10 @@ int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double*
                     int* nparts, const int* flag_dev);
 int launch_stencil27_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
                                double* partials, int* nparts, const int* flag_dev);
+int launch_stencil_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
+                               double* out, double* partials, int* nparts);
+int launch_stencil27_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
+                                 double* out, double* partials, int* nparts);
 int build_csr(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const int32_t* indices,
               const double* data);
 int build_sell(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const int32_t* indices,
@@ -39,6 +43,20 @@ int launch_apply_dot(lz_op* op, const double* x, const double* scale_dev, double
         return launch_stencil27_apply_dot(op, x, scale_dev, y, partials, nparts, flag_dev);
     if (op->kind == LZ_OP_STENCIL) return launch_stencil_apply_dot(op, x, scale_dev, y, partials, nparts, flag_dev);
     return launch_spmv_dot(op, x, scale_dev, y, partials, nparts, flag_dev);
+}
+
+// Matrix-free operators can re-evaluate H x inside the update instead of storing it (KA + KB).
+bool recompute_step_supported(const lz_op* op) { return op->kind == LZ_OP_STENCIL; }
+
+int launch_apply_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
+                             double* out, double* partials, int* nparts, int* launches) {
+    if (launches) *launches = 1;
+    if (op->kind != LZ_OP_STENCIL) {
+        set_error("the recompute step needs a matrix-free operator");
+        return LZ_ERR_UNSUPPORTED;
+    }
+    if (op->st.points == 27) return launch_stencil27_update_norm(op, x, scale_dev, upd, out, partials, nparts);
+    return launch_stencil_update_norm(op, x, scale_dev, upd, out, partials, nparts);
 }
 
 // sum of np partials -> out[0] (one CTA, fixed order)

@@ -83,6 +83,20 @@ struct HaloPush {
 int launch_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
                      double* partials, int* nparts, int* launches, const int* flag_dev = nullptr);
 
+// ---- "recompute" step of matrix-free operators (stencil.cu, stencil27.cu) -------------------
+// KA: launch_apply_dot with y == nullptr reduces alpha without writing w.
+// KB: out = s * (H x) - (ca*sa) * x - (cb*sb) * b, partials[cta] = sum out^2 (b nullable).
+struct StencilUpdate {
+    const double* b = nullptr;
+    const double* ca = nullptr;
+    const double* sa = nullptr;
+    const double* cb = nullptr;
+    const double* sb = nullptr;
+};
+bool recompute_step_supported(const lz_op* op);
+int launch_apply_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
+                             double* out, double* partials, int* nparts, int* launches);
+
 // ---- single-pass fused step (fused.cu) ---------------------------------------------------
 bool fused_step_supported(const lz_op* op);
 int launch_fused_step(lz_op* op, const double* u, const double* rj, const double* rjm1,

@@ -415,6 +415,14 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     // (opt-in: measured on par with the two-pass step on B200, see fused.cu)
     const bool fused = !team && nl == 1 && ops[0] && opts->step_kernel == 2 && reorth != LZ_REORTH_FULL &&
                        n >= 2 && fused_step_supported(ops[0]);
+    // "recompute" step KA + KB (32*M B): matrix-free operators only; the default for them
+    bool recompute = (opts->step_kernel == 0 || opts->step_kernel == 3);
+    for (int s = 0; s < nl && recompute; ++s) recompute = ops[s] && recompute_step_supported(ops[s]);
+    if (opts->step_kernel == 3 && !recompute) {
+        set_error("lz_lanczos_run: the recompute step needs matrix-free (stencil) operators");
+        return LZ_ERR_UNSUPPORTED;
+    }
+    LZ_REQUIRE(opts->step_kernel >= 0 && opts->step_kernel <= 3, "lz_lanczos_run: unknown step_kernel %d", opts->step_kernel);
     if (opts->step_kernel == 2 && !fused) {
         set_error("lz_lanczos_run: the fused single-pass step needs a 3-D structured grid with nx %% 64 == 0, "
                   "ny %% 8 == 0 on one GPU and reorth != full");
@@ -558,13 +566,24 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
             bind_ghosts(team, r, 1);
             bind_gather(team, r, 1);
             int l2 = 0;
-            const int rc = launch_apply_dot(r.op, r.v0, r.st.v0scale, r.w, r.ctx->partials, &r.np, &l2, nullptr);
+            const int rc = launch_apply_dot(r.op, r.v0, r.st.v0scale, recompute ? nullptr : r.w, r.ctx->partials,
+                                            &r.np, &l2, nullptr);
             launches += l2;
             return rc;
         }));
         LZ_CHECK(fin_scalar(FIN_ALPHA, [](ShardRun& r) { return r.st.alpha_pre; }, 0, 0.0, nul));
         LZ_CHECK(each([&](ShardRun& r) {
             HaloPush h = halo_for(team, r, 0);
+            if (recompute) {
+                StencilUpdate u;
+                u.ca = r.st.alpha_pre;
+                u.sa = r.st.v0scale;
+                int l2 = 0;
+                LZ_CHECK(launch_apply_update_norm(r.op, r.v0, r.st.v0scale, &u, r.row(0), r.ctx->partials, &r.np, &l2));
+                launches += l2;
+                if (h.lo_dst || h.hi_dst) ++launches;
+                return launch_halo_push(r.ctx, r.row(0), r.M, &h);
+            }
             ++launches;
             LZ_CHECK(launch_update_norm(r.ctx, r.w, r.v0, nullptr, r.st.alpha_pre, r.st.v0scale, nullptr, nullptr,
                                         r.row(0), r.M, r.ctx->partials, &r.np, &h));
@@ -688,7 +707,8 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
             bind_gather(team, r, par);
             int l2 = 0;
             r.kt.begin(K_APPLY);
-            const int rc = launch_apply_dot(r.op, r.row(j), r.st.scale + j, r.w, r.ctx->partials, &r.np, &l2, nullptr);
+            const int rc = launch_apply_dot(r.op, r.row(j), r.st.scale + j, recompute ? nullptr : r.w, r.ctx->partials,
+                                            &r.np, &l2, nullptr);
             r.kt.end();
             launches += l2;
             return rc;
@@ -698,6 +718,23 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         LZ_CHECK(each([&](ShardRun& r) {
             double* out = (j + 1 < n) ? r.row(j + 1) : r.w;
             HaloPush h = (j + 1 < n) ? halo_for(team, r, (j + 1) & 1) : HaloPush{};
+            if (recompute) {
+                StencilUpdate u;
+                u.b = j > 0 ? r.row(j - 1) : nullptr;
+                u.ca = r.st.alpha + j;
+                u.sa = r.st.scale + j;
+                u.cb = r.st.beta + j;
+                u.sb = j > 0 ? r.st.scale + j - 1 : nullptr;
+                int l2 = 0;
+                r.kt.begin(K_UPDATE);
+                const int rc2 = launch_apply_update_norm(r.op, r.row(j), r.st.scale + j, &u, out, r.ctx->partials,
+                                                         &r.np, &l2);
+                r.kt.end();
+                launches += l2;
+                LZ_CHECK(rc2);
+                if (h.lo_dst || h.hi_dst) ++launches;
+                return launch_halo_push(r.ctx, out, r.M, &h);
+            }
             r.kt.begin(K_UPDATE);
             const int rc = launch_update_norm(r.ctx, r.w, r.row(j), j > 0 ? r.row(j - 1) : nullptr, r.st.alpha + j,
                                               r.st.scale + j, r.st.beta + j, j > 0 ? r.st.scale + j - 1 : nullptr,
@@ -786,6 +823,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         info->dots_ms = kms[K_DOTS];     info->dots_launches = kcnt[K_DOTS];
         info->gsupd_ms = kms[K_GSUPD];   info->gsupd_launches = kcnt[K_GSUPD];
         info->fused_ms = kms[K_FUSED];   info->fused_launches = kcnt[K_FUSED];
+        info->step_kernel = fused ? 2 : (recompute ? 3 : 1);
     }
     return status;
 }

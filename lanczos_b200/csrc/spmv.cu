@@ -12,7 +12,6 @@
 //     coalesced 128 B / 256 B transaction and the x gathers of a warp hit nearby sectors
 //     when the vertex numbering has locality.
 // Both are HBM/L2-gather bound: 12 B per stored entry + 16 B per row.
-#include <stdlib.h>
 #include <algorithm>
 #include <numeric>
 #include <vector>
@@ -65,126 +64,64 @@ __device__ __forceinline__ int32_t ld_stream_i32(const int32_t* p) {
     return v;
 }
 
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ int32_t ld_stream_i32_hint(const int32_t* p, uint64_t pol) {
-    int32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ double ld_stream_f64_hint(const double* p, uint64_t pol) {
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ double ld_gather_f64_hint(const double* p, uint64_t pol) {
-    double v;
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-    return v;
-}
-
-// VAR (tuning variants, see tools/tune_sell.py):
-//   0  grid-stride over chunks, column indices through L1
-//   1  grid-stride, column indices streamed (L1 is left to the x gathers)
-//   2  as 1, but every CTA walks a contiguous range of chunks (its x footprint slides along the
-//      numbering instead of jumping: neighbouring rows' gathers are reused out of L1)
-//   3  as 2, and the col/val streams carry an L2 evict-first policy (they are read once; x is not)
-//   4  as 3, and the x gathers carry an L2 evict-last policy
-template <int VAR>
+// One warp per chunk of 32 rows.  The CTA takes "spans" of `span` consecutive chunks (whole sorting
+// windows), dealt round-robin over the grid: all resident CTAs work on neighbouring spans (the x
+// entries they gather stay in L2), a CTA stays inside one span for span/8 iterations (its x
+// footprint - the window's rows and their neighbours - is reused out of L1), and the static deal
+// keeps the partial sums deterministic.  Column indices and values are streamed past L1, which is
+// left to the gathers.  Measured on the 50M-vertex config-4 graph (tools/tune_sell.py, B200):
+// 3.27 ms with a plain grid-stride over chunks and sigma = 1024, 1.93 ms with spans, sigma = 2048;
+// L2 evict-first hints on the streams made it slower and are not used.
 __global__ void __launch_bounds__(kThreads)
 spmv_sell_dot_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __restrict__ col,
                      const double* __restrict__ val, const int32_t* __restrict__ row_of,
                      const double* __restrict__ x, const double* __restrict__ scale,
                      double* __restrict__ y, int64_t nchunks, double* __restrict__ partials,
-                     const double* __restrict__ xg, int32_t M) {
+                     const double* __restrict__ xg, int32_t M, int span) {
     __shared__ double red[kWarps];
     const double s = scale ? __ldg(scale) : 1.0;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const double* const xgs = xg ? xg - M : x;        // ghost columns (>= M) of a sharded operator
-    int64_t c_begin, c_end, c_step;
-    const uint64_t pol_stream = VAR >= 3 ? l2_policy_evict_first() : 0;
-    const uint64_t pol_x = VAR >= 4 ? l2_policy_evict_last() : 0;
-    if (VAR >= 2) {
-        const int64_t per = (nchunks + gridDim.x - 1) / gridDim.x;
-        c_begin = (int64_t)blockIdx.x * per + warp;
-        c_end = min(nchunks, (int64_t)(blockIdx.x + 1) * per);
-        c_step = kWarps;
-    } else {
-        c_begin = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
-        c_end = nchunks;
-        c_step = ((int64_t)gridDim.x * kThreads) >> 5;
-    }
+    const int64_t nspans = (nchunks + span - 1) / span;
     double acc = 0.0;
-    for (int64_t c = c_begin; c < c_end; c += c_step) {
-        const int64_t o0 = __ldg(chunk_off + c), o1 = __ldg(chunk_off + c + 1);
-        const int width = (int)((o1 - o0) >> 5);
-        const int32_t* pc = col + o0 + lane;
-        const double* pv = val + o0 + lane;
-        double sum = 0.0;
-        // blocks of 8 entries with predication (no serial remainder loop): all column indices of a
-        // block are in flight together, then all gathers of x - rows of 7..14 entries are one or two
-        // blocks deep instead of a chain of dependent load pairs
-        constexpr int U = 8;
-        for (int k = 0; k < width; k += U) {
-            int32_t cc[U];
-            double vv[U];
+    for (int64_t sp = blockIdx.x; sp < nspans; sp += gridDim.x) {
+        const int64_t c_end = min(nchunks, (sp + 1) * span);
+        for (int64_t c = sp * span + warp; c < c_end; c += kWarps) {
+            const int64_t o0 = __ldg(chunk_off + c), o1 = __ldg(chunk_off + c + 1);
+            const int width = (int)((o1 - o0) >> 5);
+            const int32_t* pc = col + o0 + lane;
+            const double* pv = val + o0 + lane;
+            double sum = 0.0;
+            // blocks of 8 entries with predication (no serial remainder loop): all column indices of
+            // a block are in flight together, then all gathers of x - rows of 7..14 entries are one
+            // or two blocks deep instead of a chain of dependent load pairs
+            constexpr int U = 8;
+            for (int k = 0; k < width; k += U) {
+                int32_t cc[U];
+                double vv[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const bool on = k + u < width;
-                if (VAR >= 3) {
-                    cc[u] = on ? ld_stream_i32_hint(pc + (k + u) * 32, pol_stream) : 0;
-                    vv[u] = on ? ld_stream_f64_hint(pv + (k + u) * 32, pol_stream) : 0.0;
-                } else {
-                    cc[u] = on ? (VAR == 0 ? __ldg(pc + (k + u) * 32) : ld_stream_i32(pc + (k + u) * 32)) : 0;
+                for (int u = 0; u < U; ++u) {
+                    const bool on = k + u < width;
+                    cc[u] = on ? ld_stream_i32(pc + (k + u) * 32) : 0;
                     vv[u] = on ? ld_stream1(pv + (k + u) * 32) : 0.0;
                 }
-            }
-            double xx[U];
+                double xx[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (VAR >= 4) xx[u] = (k + u < width) ? ld_gather_f64_hint((cc[u] < M ? x : xgs) + cc[u], pol_x) : 0.0;
-                else xx[u] = (k + u < width) ? __ldg((cc[u] < M ? x : xgs) + cc[u]) : 0.0;
-            }
+                for (int u = 0; u < U; ++u) xx[u] = (k + u < width) ? __ldg((cc[u] < M ? x : xgs) + cc[u]) : 0.0;
 #pragma unroll
-            for (int u = 0; u < U; ++u) sum = fma(vv[u], xx[u], sum);
-        }
-        const int32_t row = __ldg(row_of + c * 32 + lane);
-        if (row >= 0) {
-            const double yi = s * sum;
-            y[row] = yi;
-            acc = fma(yi, s * __ldg(x + row), acc);
+                for (int u = 0; u < U; ++u) sum = fma(vv[u], xx[u], sum);
+            }
+            const int32_t row = __ldg(row_of + c * 32 + lane);
+            if (row >= 0) {
+                const double yi = s * sum;
+                y[row] = yi;
+                acc = fma(yi, s * __ldg(x + row), acc);
+            }
         }
     }
     const double tot = block_sum(acc, red);
     if (threadIdx.x == 0 && partials) partials[blockIdx.x] = tot;
-}
-
-static int sell_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("LZ_SELL_VARIANT");
-        v = e ? atoi(e) : 1;
-        if (v < 0 || v > 4) v = 1;
-    }
-    return v;
-}
-static int sell_ctas_per_sm() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("LZ_SELL_CTAS");
-        v = e ? atoi(e) : 8;
-        if (v < 1 || v > 32) v = 8;
-    }
-    return v;
 }
 
 int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
@@ -213,20 +150,16 @@ int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double*
         return LZ_OK;
     }
     const lz_sell& sl = op->sell;
-    const int64_t cap_sell = std::min<int64_t>((int64_t)ctx->sms * sell_ctas_per_sm(), kMaxPartials);
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((sl.nchunks + kWarps - 1) / kWarps, cap_sell));
-#define LZ_SELL_LAUNCH(V)                                                                             \
-    spmv_sell_dot_kernel<V><<<grid, kThreads, 0, ctx->stream>>>(sl.chunk_off, sl.col, sl.val, sl.row_of, x, \
-                                                                scale_dev, y, sl.nchunks, partials, op->xghost, \
-                                                                (int32_t)op->M)
-    switch (sell_variant()) {
-        case 0: LZ_SELL_LAUNCH(0); break;
-        case 2: LZ_SELL_LAUNCH(2); break;
-        case 3: LZ_SELL_LAUNCH(3); break;
-        case 4: LZ_SELL_LAUNCH(4); break;
-        default: LZ_SELL_LAUNCH(1); break;
-    }
-#undef LZ_SELL_LAUNCH
+    // spans: one sorting window each; shorter (down to one chunk per warp) when the operator is too
+    // small to give every resident CTA a few spans
+    int span = std::max(kWarps, sl.sigma / 32);
+    while (span > kWarps && (sl.nchunks + span - 1) / span < (int64_t)ctx->sms * 16) span /= 2;
+    span = std::max(span, kWarps);
+    const int64_t nspans = (sl.nchunks + span - 1) / span;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nspans, std::min<int64_t>((int64_t)ctx->sms * 16, kMaxPartials)));
+    spmv_sell_dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(sl.chunk_off, sl.col, sl.val, sl.row_of, x,
+                                                             scale_dev, y, sl.nchunks, partials, op->xghost,
+                                                             (int32_t)op->M, span);
     LZ_CUDA(cudaGetLastError());
     if (nparts) *nparts = grid;
     return LZ_OK;
@@ -297,7 +230,7 @@ int build_csr(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const in
 int build_sell(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const int32_t* indices,
                const double* data, int sigma) {
     lz_ctx* ctx = op->ctx;
-    if (sigma <= 0) sigma = 1024;
+    if (sigma <= 0) sigma = 2048;
     sigma = (sigma + 31) / 32 * 32;
     const int64_t nchunks = (M + 31) / 32;
     std::vector<int32_t> row_of((size_t)nchunks * 32, -1);
@@ -484,7 +417,7 @@ int build_from_device(lz_op* op, int64_t M, int64_t ncols, int64_t nnz, const in
         LZ_CUDA(cudaStreamSynchronize(q));
         return LZ_OK;
     }
-    if (sigma <= 0) sigma = 1024;
+    if (sigma <= 0) sigma = 2048;
     sigma = (sigma + 31) / 32 * 32;
     LZ_REQUIRE(sigma <= 8192, "lz_op_csr_create_dev: sigma must be <= 8192 rows");
     const int64_t nchunks = (M + 31) / 32;

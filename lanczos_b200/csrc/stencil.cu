@@ -1,6 +1,14 @@
 // K1: matrix-free 3-/5-/7-point stencil apply with the Lanczos alpha dot fused in.
 //
-//   y = s * (H x),   partial[cta] = sum_i y_i * (s * x_i)
+//   MODE 0 (K1):  y = s * (H x),   partial[cta] = sum_i y_i * (s * x_i)
+//   MODE 1 (KA):  the same partial, y is NOT written                         (8*N bytes)
+//   MODE 2 (KB):  out = s * (H x) - fa * x - fb * b,  partial[cta] = sum out^2   (24*N bytes)
+//
+// KA + KB are the "recompute" Lanczos step: a matrix-free operator costs no HBM traffic of its own,
+// so w = H v_j is evaluated twice - once to reduce alpha_j, once inside the three-term update -
+// instead of being written (8*N) and read back (8*N): 32*N bytes per step instead of 48*N
+// (Lanczos.py:116-119 folded into two passes over v_j).  The arithmetic of w and of the update is
+// operation for operation that of K1 followed by K3 (vecops.cu).
 //
 // replaces `r = H*V[j]` + `alpha[j] = np.dot(V[j], r)` (Lanczos.py:116,118) for operators
 // with the reference's structured-grid pattern (Hamiltonian.py:73-99).  `s` is the lazy
@@ -27,6 +35,11 @@ struct StencilArgs {
     const double* zlo;    // plane below local plane 0 (nullptr: zero)
     const double* zhi;    // plane above local plane nz-1
     const double* scale;  // device scalar, nullptr: 1
+    const double* b;      // MODE 2: v_{j-1} (nullable)
+    const double* ca;     // MODE 2: device scalars, fa = ca * sa, fb = cb * sb (nullable => 1)
+    const double* sa;
+    const double* cb;
+    const double* sb;
     const int* skip;      // device flag, nullptr or *skip != 0: run
     double* partials;
     int tiles_x, tiles_y, chunks_z, zc;
@@ -53,13 +66,18 @@ __device__ __forceinline__ void zero_vec(double (&v)[VEC]) {
 // Occupancy matters more than unrolling here (the kernel is latency-bound): 6 CTAs/SM (40
 // registers, 48 warps) and no unrolling measured 0.376 ms at 512^3 against 0.403 ms for the
 // compiler's default 48 registers / 5 CTAs; forcing 7-8 CTAs spills and is slower.
-template <int VEC, bool HAS_Y, bool HAS_Z, bool HAS_DIAG>
-__global__ void __launch_bounds__(kThreads, 6)
+#ifndef LZ_KB_MINBLOCKS
+#define LZ_KB_MINBLOCKS 5
+#endif
+template <int VEC, bool HAS_Y, bool HAS_Z, bool HAS_DIAG, int MODE>
+__global__ void __launch_bounds__(kThreads, MODE == 2 ? LZ_KB_MINBLOCKS : 6)
 stencil_apply_dot_kernel(const StencilArgs a) {
     if (a.skip && *a.skip == 0) return;
     __shared__ double red[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double s = a.scale ? __ldg(a.scale) : 1.0;
+    const double fa = MODE == 2 ? (a.ca ? __ldg(a.ca) : 1.0) * (a.sa ? __ldg(a.sa) : 1.0) : 0.0;
+    const double fb = (MODE == 2 && a.b) ? (a.cb ? __ldg(a.cb) : 1.0) * (a.sb ? __ldg(a.sb) : 1.0) : 0.0;
     constexpr int TX = 32 * VEC;
     double acc_alpha = 0.0;
 
@@ -125,6 +143,15 @@ stencil_apply_dot_kernel(const StencilArgs a) {
             if (HAS_DIAG) {
                 if (act) load_vec<VEC>(a.diag + (int64_t)z * a.plane + off_c, dg);
             }
+            double bv[VEC];
+            zero_vec<VEC>(bv);
+            if (MODE == 2) {
+                if (act && a.b) {
+                    const double* pb = a.b + (int64_t)z * a.plane + off_c;
+                    if constexpr (VEC == 2) { const double2 t = ld_stream2(pb); bv[0] = t.x; bv[1] = t.y; }
+                    else bv[0] = ld_stream1(pb);
+                }
+            }
             if (act) {
                 double out[VEC];
 #pragma unroll
@@ -140,12 +167,20 @@ stencil_apply_dot_kernel(const StencilArgs a) {
                     r = fma(a.oy, yp[e], r);
                     r = fma(a.oz, vp[e], r);
                     r *= s;
+                    if (MODE == 2) {
+                        r = fma(-fa, vc[e], r);             // K3: w - fa * v_j - fb * v_{j-1}
+                        if (a.b) r = fma(-fb, bv[e], r);
+                        acc_alpha = fma(r, r, acc_alpha);
+                    } else {
+                        acc_alpha = fma(r, s * vc[e], acc_alpha);
+                    }
                     out[e] = r;
-                    acc_alpha = fma(r, s * vc[e], acc_alpha);
                 }
-                double* py = a.y + (int64_t)z * a.plane + off_c;
-                if constexpr (VEC == 2) st_stream2(py, make_double2(out[0], out[1]));
-                else st_stream1(py, out[0]);
+                if (MODE != 1) {
+                    double* py = a.y + (int64_t)z * a.plane + off_c;
+                    if constexpr (VEC == 2) st_stream2(py, make_double2(out[0], out[1]));
+                    else st_stream1(py, out[0]);
+                }
             }
 #pragma unroll
             for (int e = 0; e < VEC; ++e) { vm[e] = vc[e]; vc[e] = vp[e]; }
@@ -156,21 +191,40 @@ stencil_apply_dot_kernel(const StencilArgs a) {
     if (threadIdx.x == 0 && a.partials) a.partials[blockIdx.x] = tot;
 }
 
-template <int VEC, bool HAS_Y, bool HAS_Z>
+template <int VEC, bool HAS_Y, bool HAS_Z, int MODE>
 static const void* pick_diag(bool has_diag) {
-    if (has_diag) return (const void*)stencil_apply_dot_kernel<VEC, HAS_Y, HAS_Z, true>;
-    return (const void*)stencil_apply_dot_kernel<VEC, HAS_Y, HAS_Z, false>;
+    if (has_diag) return (const void*)stencil_apply_dot_kernel<VEC, HAS_Y, HAS_Z, true, MODE>;
+    return (const void*)stencil_apply_dot_kernel<VEC, HAS_Y, HAS_Z, false, MODE>;
+}
+template <int VEC, int MODE>
+static const void* pick_yz(bool has_y, bool has_z, bool has_diag) {
+    if (has_y && has_z) return pick_diag<VEC, true, true, MODE>(has_diag);
+    if (has_y) return pick_diag<VEC, true, false, MODE>(has_diag);
+    if (has_z) return pick_diag<VEC, false, true, MODE>(has_diag);
+    return pick_diag<VEC, false, false, MODE>(has_diag);
 }
 template <int VEC>
-static const void* pick_kernel(bool has_y, bool has_z, bool has_diag) {
-    if (has_y && has_z) return pick_diag<VEC, true, true>(has_diag);
-    if (has_y) return pick_diag<VEC, true, false>(has_diag);
-    if (has_z) return pick_diag<VEC, false, true>(has_diag);
-    return pick_diag<VEC, false, false>(has_diag);
+static const void* pick_kernel(bool has_y, bool has_z, bool has_diag, int mode) {
+    if (mode == 1) return pick_yz<VEC, 1>(has_y, has_z, has_diag);
+    if (mode == 2) return pick_yz<VEC, 2>(has_y, has_z, has_diag);
+    return pick_yz<VEC, 0>(has_y, has_z, has_diag);
 }
+
+static int launch_stencil(lz_op* op, int mode, const double* x, const double* scale_dev, double* y,
+                          const StencilUpdate* upd, double* partials, int* nparts, const int* flag_dev);
 
 int launch_stencil_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
                              double* partials, int* nparts, const int* flag_dev) {
+    return launch_stencil(op, y ? 0 : 1, x, scale_dev, y, nullptr, partials, nparts, flag_dev);
+}
+
+int launch_stencil_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
+                               double* out, double* partials, int* nparts) {
+    return launch_stencil(op, 2, x, scale_dev, out, upd, partials, nparts, nullptr);
+}
+
+static int launch_stencil(lz_op* op, int mode, const double* x, const double* scale_dev, double* y,
+                          const StencilUpdate* upd, double* partials, int* nparts, const int* flag_dev) {
     const lz_stencil& st = op->st;
     lz_ctx* ctx = op->ctx;
     StencilArgs a;
@@ -180,6 +234,9 @@ int launch_stencil_apply_dot(lz_op* op, const double* x, const double* scale_dev
     a.c = st.center; a.ox = st.offx; a.oy = st.offy; a.oz = st.offz;
     a.x = x; a.y = y; a.diag = st.diag;
     a.scale = scale_dev; a.partials = partials; a.skip = flag_dev;
+    a.b = upd ? upd->b : nullptr;
+    a.ca = upd ? upd->ca : nullptr; a.sa = upd ? upd->sa : nullptr;
+    a.cb = upd ? upd->cb : nullptr; a.sb = upd ? upd->sb : nullptr;
     const bool has_y = (st.offy != 0.0);
     const bool has_z = (st.offz != 0.0);
     if (st.sharded) {
@@ -193,7 +250,7 @@ int launch_stencil_apply_dot(lz_op* op, const double* x, const double* scale_dev
         a.zhi = nullptr;
     }
     const bool aligned = ((st.nx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.b) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(st.diag) & 15) == 0) &&
                          (!st.sharded || (((reinterpret_cast<uintptr_t>(st.ghost_lo) |
                                             reinterpret_cast<uintptr_t>(st.ghost_hi)) & 15) == 0));
@@ -201,8 +258,8 @@ int launch_stencil_apply_dot(lz_op* op, const double* x, const double* scale_dev
     const int TX = 32 * vec;
     a.tiles_x = (int)((st.nx + TX - 1) / TX);
     a.tiles_y = (int)((st.ny + kWarps - 1) / kWarps);
-    const void* fn = (vec == 2) ? pick_kernel<2>(has_y, has_z, st.diag != nullptr)
-                                : pick_kernel<1>(has_y, has_z, st.diag != nullptr);
+    const void* fn = (vec == 2) ? pick_kernel<2>(has_y, has_z, st.diag != nullptr, mode)
+                                : pick_kernel<1>(has_y, has_z, st.diag != nullptr, mode);
     int per_sm = 0;
     LZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
     if (per_sm < 1) per_sm = 1;

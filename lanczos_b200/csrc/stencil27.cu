@@ -29,6 +29,11 @@ struct Stencil27Args {
     const double* zlo;
     const double* zhi;
     const double* scale;
+    const double* b;      // MODE 2 (KB, see stencil.cu): v_{j-1} and the update coefficients
+    const double* ca;
+    const double* sa;
+    const double* cb;
+    const double* sb;
     const int* skip;
     double* partials;
     int tiles_x, tiles_y, chunks_z, zc;
@@ -48,13 +53,17 @@ __device__ __forceinline__ void load_row(const double* p, double (&v)[VEC]) {
 
 // 5 CTAs/SM (48 registers, a few spilled words) measured 0.81 ms at 512^3 against 1.11 ms for the
 // compiler's default 72 registers / 3 CTAs: like K1 this kernel is latency-bound.
-template <int VEC, bool HAS_DIAG>
-__global__ void __launch_bounds__(kThreads, 5)
+// MODE as in stencil.cu: 0 apply + alpha partial, 1 alpha partial only (KA), 2 apply fused with the
+// three-term update and the norm partial (KB).
+template <int VEC, bool HAS_DIAG, int MODE>
+__global__ void __launch_bounds__(kThreads, MODE == 2 ? 4 : 5)
 stencil27_apply_dot_kernel(const Stencil27Args a) {
     if (a.skip && *a.skip == 0) return;
     __shared__ double red[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double s = a.scale ? __ldg(a.scale) : 1.0;
+    const double fa = MODE == 2 ? (a.ca ? __ldg(a.ca) : 1.0) * (a.sa ? __ldg(a.sa) : 1.0) : 0.0;
+    const double fb = (MODE == 2 && a.b) ? (a.cb ? __ldg(a.cb) : 1.0) * (a.sb ? __ldg(a.sb) : 1.0) : 0.0;
     constexpr int TX = 32 * VEC;
     double acc_alpha = 0.0;
 
@@ -135,17 +144,34 @@ stencil27_apply_dot_kernel(const Stencil27Args a) {
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) dg[e] = 0.0;
                 if (HAS_DIAG) load_row<VEC>(a.diag + at, dg);
+                double bv[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) bv[e] = 0.0;
+                if (MODE == 2) {
+                    if (a.b) {
+                        if constexpr (VEC == 2) { const double2 t = ld_stream2(a.b + at); bv[0] = t.x; bv[1] = t.y; }
+                        else bv[0] = ld_stream1(a.b + at);
+                    }
+                }
                 double out[VEC];
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
                     double r = (P1m[e] + P1p[e]) + P0c[e];
                     r = fma(dg[e], cc[e], r);
                     r *= s;
+                    if (MODE == 2) {
+                        r = fma(-fa, cc[e], r);
+                        if (a.b) r = fma(-fb, bv[e], r);
+                        acc_alpha = fma(r, r, acc_alpha);
+                    } else {
+                        acc_alpha = fma(r, s * cc[e], acc_alpha);
+                    }
                     out[e] = r;
-                    acc_alpha = fma(r, s * cc[e], acc_alpha);
                 }
-                if constexpr (VEC == 2) st_stream2(a.y + at, make_double2(out[0], out[1]));
-                else st_stream1(a.y + at, out[0]);
+                if (MODE != 1) {
+                    if constexpr (VEC == 2) st_stream2(a.y + at, make_double2(out[0], out[1]));
+                    else st_stream1(a.y + at, out[0]);
+                }
             }
 #pragma unroll
             for (int e = 0; e < VEC; ++e) { P1m[e] = P1c[e]; P0c[e] = P0p[e]; P1c[e] = P1p[e]; cc[e] = cp[e]; }
@@ -155,8 +181,27 @@ stencil27_apply_dot_kernel(const Stencil27Args a) {
     if (threadIdx.x == 0 && a.partials) a.partials[blockIdx.x] = tot;
 }
 
+template <int VEC, int MODE>
+static const void* pick27(bool has_diag) {
+    return has_diag ? (const void*)stencil27_apply_dot_kernel<VEC, true, MODE>
+                    : (const void*)stencil27_apply_dot_kernel<VEC, false, MODE>;
+}
+
+static int launch_stencil27(lz_op* op, int mode, const double* x, const double* scale_dev, double* y,
+                            const StencilUpdate* upd, double* partials, int* nparts, const int* flag_dev);
+
 int launch_stencil27_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
                                double* partials, int* nparts, const int* flag_dev) {
+    return launch_stencil27(op, y ? 0 : 1, x, scale_dev, y, nullptr, partials, nparts, flag_dev);
+}
+
+int launch_stencil27_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
+                                 double* out, double* partials, int* nparts) {
+    return launch_stencil27(op, 2, x, scale_dev, out, upd, partials, nparts, nullptr);
+}
+
+static int launch_stencil27(lz_op* op, int mode, const double* x, const double* scale_dev, double* y,
+                            const StencilUpdate* upd, double* partials, int* nparts, const int* flag_dev) {
     const lz_stencil& st = op->st;
     lz_ctx* ctx = op->ctx;
     Stencil27Args a;
@@ -166,11 +211,14 @@ int launch_stencil27_apply_dot(lz_op* op, const double* x, const double* scale_d
     a.w0 = st.w27[0]; a.w1 = st.w27[1]; a.w2 = st.w27[2]; a.w3 = st.w27[3];
     a.x = x; a.y = y; a.diag = st.diag;
     a.scale = scale_dev; a.partials = partials; a.skip = flag_dev;
+    a.b = upd ? upd->b : nullptr;
+    a.ca = upd ? upd->ca : nullptr; a.sa = upd ? upd->sa : nullptr;
+    a.cb = upd ? upd->cb : nullptr; a.sb = upd ? upd->sb : nullptr;
     if (st.sharded) { a.zlo = st.ghost_lo; a.zhi = st.ghost_hi; }
     else if (a.periodic) { a.zlo = x + (st.nz - 1) * a.plane; a.zhi = x; }
     else { a.zlo = nullptr; a.zhi = nullptr; }
     const bool aligned = ((st.nx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.b) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(st.diag) & 15) == 0) &&
                          (!st.sharded || (((reinterpret_cast<uintptr_t>(st.ghost_lo) |
                                             reinterpret_cast<uintptr_t>(st.ghost_hi)) & 15) == 0));
@@ -179,8 +227,9 @@ int launch_stencil27_apply_dot(lz_op* op, const double* x, const double* scale_d
     a.tiles_x = (int)((st.nx + TX - 1) / TX);
     a.tiles_y = (int)((st.ny + kWarps - 1) / kWarps);
     const void* fn;
-    if (vec == 2) fn = st.diag ? (const void*)stencil27_apply_dot_kernel<2, true> : (const void*)stencil27_apply_dot_kernel<2, false>;
-    else fn = st.diag ? (const void*)stencil27_apply_dot_kernel<1, true> : (const void*)stencil27_apply_dot_kernel<1, false>;
+    const bool hd = st.diag != nullptr;
+    if (vec == 2) fn = mode == 2 ? pick27<2, 2>(hd) : mode == 1 ? pick27<2, 1>(hd) : pick27<2, 0>(hd);
+    else fn = mode == 2 ? pick27<1, 2>(hd) : mode == 1 ? pick27<1, 1>(hd) : pick27<1, 0>(hd);
     int per_sm = 0;
     LZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
     if (per_sm < 1) per_sm = 1;

@@ -19,7 +19,8 @@ _REORTH = {"none": LZ_REORTH_NONE, "full": LZ_REORTH_FULL, "selective": LZ_REORT
            None: LZ_REORTH_NONE, False: LZ_REORTH_NONE, True: LZ_REORTH_FULL}
 
 
-STEP_KERNEL = {"auto": 0, "two_pass": 1, "fused": 2, 0: 0, 1: 1, 2: 2}
+STEP_KERNEL = {"auto": 0, "two_pass": 1, "fused": 2, "recompute": 3, 0: 0, 1: 1, 2: 2, 3: 3}
+STEP_KERNEL_NAME = {1: "two_pass", 2: "fused", 3: "recompute"}
 
 
 def _torch():
@@ -333,6 +334,7 @@ class LanczosResult:
         self.reorth_count = info.reorth_count
         self.launches = info.launches
         self.gpu_ms = float(info.gpu_ms)
+        self.step_kernel = STEP_KERNEL_NAME.get(info.step_kernel, "two_pass")
         # per-kernel device times (only when run with profile=True)
         self.kernel_ms = {"apply": (float(info.apply_ms), info.apply_launches),
                           "update": (float(info.update_ms), info.update_launches),

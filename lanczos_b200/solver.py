@@ -95,7 +95,7 @@ class LanczosBase:
         reorth 'full' | 'selective' | 'none'; cgs_passes 1 | 2; ref_compat (the v0-discarding
         pre-step and the (2-|v|^2) sweep form of the reference); fmt 'auto' | 'csr' | 'sell' and
         sigma for sparse operators; device index; keep_basis; breakdown_tol; select_tol;
-        profile (per-kernel CUDA-event timing); step_kernel 'auto' | 'two_pass' | 'fused';
+        profile (per-kernel CUDA-event timing); step_kernel 'auto' | 'two_pass' | 'fused' | 'recompute';
         verbose (the reference's '+++' banners)."""
         if n > self.M:
             raise ValueError("n cannot be larger than M!")                  # Lanczos.py:76-77

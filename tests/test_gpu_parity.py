@@ -360,6 +360,85 @@ def test_large_grid_invariants(lz):
 
 # ---- KF: the single-pass fused step (structured grids, nx % 64 == 0, ny % 8 == 0) ----------------
 
+RECOMPUTE_CASES = [((7,), "periodic"), ((9,), "dirichlet"), ((6, 5), "periodic"), ((70, 3), "dirichlet"),
+                   ((4, 3, 5), "periodic"), ((5, 3, 2), "dirichlet"), ((2, 2, 2), "periodic"), ((66, 9, 3), "periodic"),
+                   ((130, 17, 4), "dirichlet"), ((64, 16, 12), "periodic")]
+
+
+@pytest.mark.parametrize("grid,bc", RECOMPUTE_CASES)
+@pytest.mark.parametrize("reorth", ["full", "none"])
+def test_recompute_step_matches_two_pass_and_oracle(lz, grid, bc, reorth):
+    """KA + KB (H v re-evaluated inside the update, 32 M bytes) against K1 + K3 (48 M bytes): the
+    arithmetic of w and of the update is the same operation for operation, so alpha agrees to the
+    last bits and beta up to the order of its partial sums; both against the oracle."""
+    dim = len(grid)
+    off = [-1.0, -0.7, -1.2][:dim]
+    op = lz.StencilOperator(grid, 2.0 * dim + 0.5, off, bc=bc)
+    M = int(np.prod(grid))
+    n = min(16, M)
+    if n < 2:
+        pytest.skip("n >= 2")
+    runs = {}
+    for kern in ("two_pass", "recompute", "auto"):
+        L = lz.Lanczos(op)
+        L.execute_Lanczos(n, seed=13, reorth=reorth, keep_basis=True, step_kernel=kern)
+        runs[kern] = (np.diag(L.H_eff).copy(), np.diag(L.H_eff, 1).copy(), L.V.copy(), L.result.step_kernel)
+    assert runs["two_pass"][3] == "two_pass" and runs["recompute"][3] == "recompute"
+    assert runs["auto"][3] == "recompute"                 # the default for matrix-free operators
+    a2, b2, V2, _ = runs["two_pass"]
+    ar, br, Vr, _ = runs["recompute"]
+    k = n if reorth == "full" else min(n, 6)              # without sweeps round-off differences grow
+    assert rel(ar[:k], a2[:k]) < 1e-12 and rel(br[:k], b2[:k]) < 1e-12
+    assert np.array_equal(runs["auto"][0], ar) and np.array_equal(runs["auto"][1], br)
+    if reorth == "full" and M > n:
+        H = orc.laplacian_csr(grid, 2.0 * dim + 0.5, off, periodic=(bc == "periodic"))
+        ref = orc.lanczos(H, n, seed=13)
+        assert rel(ar, ref["alpha"]) < 1e-12 and rel(br, ref["beta"]) < 1e-12
+        assert np.max(np.abs(Vr - ref["V"])) < 1e-12
+
+
+def test_recompute_step_with_potential_27pt_and_ring(lz):
+    H, c, o, pot = orc.deuteron_hamiltonian(12)
+    n = 40
+    ref = orc.lanczos(H, n, seed=78)
+    op = lz.StencilOperator((12, 12, 12), c, o, diag=pot)
+    for kern in ("recompute", "two_pass"):
+        L = lz.Lanczos(op)
+        L.execute_Lanczos(n, seed=78, step_kernel=kern)
+        assert rel(np.diag(L.H_eff), ref["alpha"]) < 1e-12 and rel(np.diag(L.H_eff, 1), ref["beta"]) < 1e-12
+    # selective sweeps and the three-row ring
+    a = {}
+    for kern in ("recompute", "two_pass"):
+        L = lz.Lanczos(op)
+        L.execute_Lanczos(n, seed=78, reorth="selective", cgs_passes=2, step_kernel=kern)
+        a[kern] = np.linalg.eigvalsh(L.H_eff)[:3]
+        R = lz.Lanczos(op)
+        R.execute_Lanczos(10, seed=78, reorth="none", keep_basis=False, step_kernel=kern)
+        a[kern + "_ring"] = np.diag(R.H_eff).copy()
+    assert rel(a["recompute"], a["two_pass"]) < 1e-9
+    assert rel(a["recompute_ring"][:6], a["two_pass_ring"][:6]) < 1e-11
+    # the reference's 27-point Laplacian
+    w = lz.reference_T27_weights(-1.0)
+    grid = (10, 9, 8)
+    op27 = lz.StencilOperator(grid, 0.0, 0.0, weights27=w, diag=np.linspace(0.0, 1.0, 720))
+    H27 = orc.laplacian27_csr(grid, w, periodic=True, diag=np.linspace(0.0, 1.0, 720))
+    ref27 = orc.lanczos(H27, 20, seed=5)
+    for kern in ("recompute", "two_pass"):
+        L = lz.Lanczos(op27)
+        L.execute_Lanczos(20, seed=5, step_kernel=kern)
+        assert L.result.step_kernel == kern
+        assert rel(np.diag(L.H_eff), ref27["alpha"]) < 1e-12 and rel(np.diag(L.H_eff, 1), ref27["beta"]) < 1e-12
+
+
+def test_recompute_step_rejected_for_stored_operators(lz):
+    H = orc.laplacian_csr((8, 8, 8), 6.0, -1.0)
+    L = lz.Lanczos(H)
+    with pytest.raises(RuntimeError):
+        L.execute_Lanczos(5, step_kernel="recompute")
+    L.execute_Lanczos(5, step_kernel="auto")
+    assert L.result.step_kernel == "two_pass"
+
+
 @pytest.mark.parametrize("grid,bc", [((64, 16, 12), "periodic"), ((128, 8, 9), "dirichlet"), ((64, 24, 2), "periodic")])
 def test_fused_step_matches_two_pass_and_oracle(lz, grid, bc):
     op = lz.StencilOperator(grid, 6.5, [-1.0, -0.7, -1.2], bc=bc)

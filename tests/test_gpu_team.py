@@ -63,6 +63,24 @@ def test_local_team_matches_single_gpu(lz, grid, bc, world, reorth, passes):
         assert np.max(np.abs(V - ref["V"].T)) < 1e-12
 
 
+@pytest.mark.parametrize("grid,bc,world", [((16, 12, 20), "periodic", 4), ((16, 12, 10), "dirichlet", 3), ((40, 36), "periodic", 4),
+                                           ((15, 6, 8), "periodic", 2)])
+def test_local_team_step_kernels_agree(lz, grid, bc, world):
+    """Sharded runs: the recompute step (default for stencils; halo planes pushed after KB) and the
+    two-pass step (halo planes stored by K3 itself) give the same tridiagonal matrix."""
+    from lanczos_b200.team import LocalTeamLanczos
+    dim = len(grid)
+    op = lz.StencilOperator(grid, 2.0 * dim + 0.25, [-1.0, -0.8, -1.1][:dim], bc=bc)
+    T = {}
+    for kern in ("recompute", "two_pass"):
+        team = LocalTeamLanczos(op, world)
+        team.execute_Lanczos(20, seed=7, step_kernel=kern)
+        assert team.result.step_kernel == kern
+        T[kern] = team.H_eff.copy()
+    assert rel(np.diag(T["recompute"]), np.diag(T["two_pass"])) < 1e-12
+    assert rel(np.diag(T["recompute"], 1), np.diag(T["two_pass"], 1)) < 1e-12
+
+
 def test_local_team_with_potential_and_clean_start(lz):
     from lanczos_b200.team import LocalTeamLanczos
     H, c, o, pot = orc.deuteron_hamiltonian(12)
