@@ -92,6 +92,7 @@ struct StencilUpdate {
     const double* sa = nullptr;
     const double* cb = nullptr;
     const double* sb = nullptr;
+    HaloPush halo;             // sharded structured grids: boundary planes of `out` -> the neighbours' ghost buffers
 };
 bool recompute_step_supported(const lz_op* op);
 int launch_apply_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,

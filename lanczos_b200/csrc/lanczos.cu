@@ -578,11 +578,11 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
                 StencilUpdate u;
                 u.ca = r.st.alpha_pre;
                 u.sa = r.st.v0scale;
+                u.halo = h;                       // KB stores the boundary planes of row 0 to the neighbours
                 int l2 = 0;
                 LZ_CHECK(launch_apply_update_norm(r.op, r.v0, r.st.v0scale, &u, r.row(0), r.ctx->partials, &r.np, &l2));
                 launches += l2;
-                if (h.lo_dst || h.hi_dst) ++launches;
-                return launch_halo_push(r.ctx, r.row(0), r.M, &h);
+                return LZ_OK;
             }
             ++launches;
             LZ_CHECK(launch_update_norm(r.ctx, r.w, r.v0, nullptr, r.st.alpha_pre, r.st.v0scale, nullptr, nullptr,
@@ -725,15 +725,14 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
                 u.sa = r.st.scale + j;
                 u.cb = r.st.beta + j;
                 u.sb = j > 0 ? r.st.scale + j - 1 : nullptr;
+                u.halo = h;
                 int l2 = 0;
                 r.kt.begin(K_UPDATE);
                 const int rc2 = launch_apply_update_norm(r.op, r.row(j), r.st.scale + j, &u, out, r.ctx->partials,
                                                          &r.np, &l2);
                 r.kt.end();
                 launches += l2;
-                LZ_CHECK(rc2);
-                if (h.lo_dst || h.hi_dst) ++launches;
-                return launch_halo_push(r.ctx, out, r.M, &h);
+                return rc2;
             }
             r.kt.begin(K_UPDATE);
             const int rc = launch_update_norm(r.ctx, r.w, r.row(j), j > 0 ? r.row(j - 1) : nullptr, r.st.alpha + j,

@@ -40,6 +40,8 @@ struct StencilArgs {
     const double* sa;
     const double* cb;
     const double* sb;
+    double* halo_lo;      // MODE 2, sharded: plane 0 of `out` also goes to the lower neighbour's ghost buffer,
+    double* halo_hi;      // plane nz-1 to the upper neighbour's (NVLink peer stores, as K3 does)
     const int* skip;      // device flag, nullptr or *skip != 0: run
     double* partials;
     int tiles_x, tiles_y, chunks_z, zc;
@@ -66,11 +68,22 @@ __device__ __forceinline__ void zero_vec(double (&v)[VEC]) {
 // Occupancy matters more than unrolling here (the kernel is latency-bound): 6 CTAs/SM (40
 // registers, 48 warps) and no unrolling measured 0.376 ms at 512^3 against 0.403 ms for the
 // compiler's default 48 registers / 5 CTAs; forcing 7-8 CTAs spills and is slower.
+// Resident CTAs per SM the register budget is cut for (best measured on B200 at 512^3: K1 / KA
+// 6 x 40 registers, KB 4 x 64 registers without spills: 0.555 ms against 0.623 ms at 5 x 48).
+// A register queue of planes further ahead (loads of z+2.. in flight) was tried and is slower
+// (KA 0.25 -> 0.35-0.41 ms, KB 0.55 -> 0.89 ms): the y-neighbour rows are served by L1, and more
+// planes in flight per CTA push them out.
+#ifndef LZ_K1_MINBLOCKS
+#define LZ_K1_MINBLOCKS 6
+#endif
+#ifndef LZ_KA_MINBLOCKS
+#define LZ_KA_MINBLOCKS 6
+#endif
 #ifndef LZ_KB_MINBLOCKS
-#define LZ_KB_MINBLOCKS 5
+#define LZ_KB_MINBLOCKS 4
 #endif
 template <int VEC, bool HAS_Y, bool HAS_Z, bool HAS_DIAG, int MODE>
-__global__ void __launch_bounds__(kThreads, MODE == 2 ? LZ_KB_MINBLOCKS : 6)
+__global__ void __launch_bounds__(kThreads, MODE == 2 ? LZ_KB_MINBLOCKS : (MODE == 1 ? LZ_KA_MINBLOCKS : LZ_K1_MINBLOCKS))
 stencil_apply_dot_kernel(const StencilArgs a) {
     if (a.skip && *a.skip == 0) return;
     __shared__ double red[kWarps];
@@ -127,6 +140,15 @@ stencil_apply_dot_kernel(const StencilArgs a) {
                 const double* pp = (z + 1 < a.nz) ? (pc + a.plane) : a.zhi;
                 if (act && pp) load_vec<VEC>(pp + off_c, vp);
             }
+            double bv[VEC];
+            zero_vec<VEC>(bv);
+            if (MODE == 2) {
+                if (act && a.b) {
+                    const double* pb = a.b + (int64_t)z * a.plane + off_c;
+                    if constexpr (VEC == 2) { const double2 t = ld_stream2(pb); bv[0] = t.x; bv[1] = t.y; }
+                    else bv[0] = ld_stream1(pb);
+                }
+            }
             double ym[VEC], yp[VEC];
             zero_vec<VEC>(ym);
             zero_vec<VEC>(yp);
@@ -142,15 +164,6 @@ stencil_apply_dot_kernel(const StencilArgs a) {
             zero_vec<VEC>(dg);
             if (HAS_DIAG) {
                 if (act) load_vec<VEC>(a.diag + (int64_t)z * a.plane + off_c, dg);
-            }
-            double bv[VEC];
-            zero_vec<VEC>(bv);
-            if (MODE == 2) {
-                if (act && a.b) {
-                    const double* pb = a.b + (int64_t)z * a.plane + off_c;
-                    if constexpr (VEC == 2) { const double2 t = ld_stream2(pb); bv[0] = t.x; bv[1] = t.y; }
-                    else bv[0] = ld_stream1(pb);
-                }
             }
             if (act) {
                 double out[VEC];
@@ -180,6 +193,16 @@ stencil_apply_dot_kernel(const StencilArgs a) {
                     double* py = a.y + (int64_t)z * a.plane + off_c;
                     if constexpr (VEC == 2) st_stream2(py, make_double2(out[0], out[1]));
                     else st_stream1(py, out[0]);
+                }
+                if (MODE == 2) {
+                    if (a.halo_lo && z == 0) {
+                        if constexpr (VEC == 2) *reinterpret_cast<double2*>(a.halo_lo + off_c) = make_double2(out[0], out[1]);
+                        else a.halo_lo[off_c] = out[0];
+                    }
+                    if (a.halo_hi && z == a.nz - 1) {
+                        if constexpr (VEC == 2) *reinterpret_cast<double2*>(a.halo_hi + off_c) = make_double2(out[0], out[1]);
+                        else a.halo_hi[off_c] = out[0];
+                    }
                 }
             }
 #pragma unroll
@@ -237,6 +260,8 @@ static int launch_stencil(lz_op* op, int mode, const double* x, const double* sc
     a.b = upd ? upd->b : nullptr;
     a.ca = upd ? upd->ca : nullptr; a.sa = upd ? upd->sa : nullptr;
     a.cb = upd ? upd->cb : nullptr; a.sb = upd ? upd->sb : nullptr;
+    a.halo_lo = upd ? upd->halo.lo_dst : nullptr;
+    a.halo_hi = upd ? upd->halo.hi_dst : nullptr;
     const bool has_y = (st.offy != 0.0);
     const bool has_z = (st.offz != 0.0);
     if (st.sharded) {
@@ -251,6 +276,7 @@ static int launch_stencil(lz_op* op, int mode, const double* x, const double* sc
     }
     const bool aligned = ((st.nx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.b) & 15) == 0) &&
+                         (((reinterpret_cast<uintptr_t>(a.halo_lo) | reinterpret_cast<uintptr_t>(a.halo_hi)) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(st.diag) & 15) == 0) &&
                          (!st.sharded || (((reinterpret_cast<uintptr_t>(st.ghost_lo) |
                                             reinterpret_cast<uintptr_t>(st.ghost_hi)) & 15) == 0));

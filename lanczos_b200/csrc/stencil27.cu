@@ -34,6 +34,8 @@ struct Stencil27Args {
     const double* sa;
     const double* cb;
     const double* sb;
+    double* halo_lo;      // MODE 2, sharded: plane 0 of `out` also goes to the lower neighbour's ghost buffer,
+    double* halo_hi;      // plane nz-1 to the upper neighbour's (NVLink peer stores, as K3 does)
     const int* skip;
     double* partials;
     int tiles_x, tiles_y, chunks_z, zc;
@@ -172,6 +174,17 @@ stencil27_apply_dot_kernel(const Stencil27Args a) {
                     if constexpr (VEC == 2) st_stream2(a.y + at, make_double2(out[0], out[1]));
                     else st_stream1(a.y + at, out[0]);
                 }
+                if (MODE == 2) {
+                    const int64_t inpl = (int64_t)iy * a.nx + ix;
+                    if (a.halo_lo && z == 0) {
+                        if constexpr (VEC == 2) *reinterpret_cast<double2*>(a.halo_lo + inpl) = make_double2(out[0], out[1]);
+                        else a.halo_lo[inpl] = out[0];
+                    }
+                    if (a.halo_hi && z == a.nz - 1) {
+                        if constexpr (VEC == 2) *reinterpret_cast<double2*>(a.halo_hi + inpl) = make_double2(out[0], out[1]);
+                        else a.halo_hi[inpl] = out[0];
+                    }
+                }
             }
 #pragma unroll
             for (int e = 0; e < VEC; ++e) { P1m[e] = P1c[e]; P0c[e] = P0p[e]; P1c[e] = P1p[e]; cc[e] = cp[e]; }
@@ -214,11 +227,14 @@ static int launch_stencil27(lz_op* op, int mode, const double* x, const double* 
     a.b = upd ? upd->b : nullptr;
     a.ca = upd ? upd->ca : nullptr; a.sa = upd ? upd->sa : nullptr;
     a.cb = upd ? upd->cb : nullptr; a.sb = upd ? upd->sb : nullptr;
+    a.halo_lo = upd ? upd->halo.lo_dst : nullptr;
+    a.halo_hi = upd ? upd->halo.hi_dst : nullptr;
     if (st.sharded) { a.zlo = st.ghost_lo; a.zhi = st.ghost_hi; }
     else if (a.periodic) { a.zlo = x + (st.nz - 1) * a.plane; a.zhi = x; }
     else { a.zlo = nullptr; a.zhi = nullptr; }
     const bool aligned = ((st.nx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.b) & 15) == 0) &&
+                         (((reinterpret_cast<uintptr_t>(a.halo_lo) | reinterpret_cast<uintptr_t>(a.halo_hi)) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(st.diag) & 15) == 0) &&
                          (!st.sharded || (((reinterpret_cast<uintptr_t>(st.ghost_lo) |
                                             reinterpret_cast<uintptr_t>(st.ghost_hi)) & 15) == 0));
