@@ -214,6 +214,109 @@ stencil_apply_dot_kernel(const StencilArgs a) {
     if (threadIdx.x == 0 && a.partials) a.partials[blockIdx.x] = tot;
 }
 
+// KA2: alpha_j alone for a full 3-D 7-point operator, from the symmetric form
+//     x.Hx = sum_i (c + d_i) x_i^2 + 2 sum_i x_i (ox x_{i+ex} + oy x_{i+ey} + oz x_{i+ez})
+// (every edge is counted once, from its lower end; a Dirichlet wall drops the edge, a periodic one
+// wraps it, a slab boundary takes the upper ghost plane - the edge below the slab belongs to the
+// lower neighbour's sum).  Only "forward" neighbours are needed: a thread owns 2 x-points on 2
+// consecutive rows, so per plane it issues two 128-bit loads of its own points and ONE of the row
+// above its pair (K1/KA issue one own load and two neighbour-row loads per 2 points), all for the
+// plane after the one being reduced - a full iteration of latency hiding with twice the HBM bytes
+// in flight per thread.  Used for KA when nx is even, all three axes couple and the vector is
+// 16-byte aligned; otherwise MODE 1 of the general kernel runs.  The value differs from K1's
+// sum_i y_i x_i only in rounding.
+#ifndef LZ_KA2_MINBLOCKS
+#define LZ_KA2_MINBLOCKS 5
+#endif
+template <bool HAS_DIAG>
+__global__ void __launch_bounds__(kThreads, LZ_KA2_MINBLOCKS)
+stencil_alpha_kernel(const StencilArgs a) {
+    if (a.skip && *a.skip == 0) return;
+    __shared__ double red[kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double s = a.scale ? __ldg(a.scale) : 1.0;
+    constexpr int TX = 64, TY = 2 * kWarps;
+    const double ox2 = 2.0 * a.ox, oy2 = 2.0 * a.oy, oz2 = 2.0 * a.oz;
+    double acc = 0.0;
+
+    for (int64_t item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+        const int tx = (int)(item % a.tiles_x);
+        const int64_t t = item / a.tiles_x;
+        const int ty = (int)(t % a.tiles_y);
+        const int cz = (int)(t / a.tiles_y);
+        const int ix = tx * TX + 2 * lane;
+        const int iy0 = ty * TY + 2 * warp;                 // rows iy0, iy0 + 1; the row above: iy0 + 2
+        const bool act0 = (ix < a.nx) && (iy0 < a.ny);
+        const bool act1 = (ix < a.nx) && (iy0 + 1 < a.ny);
+        // forward y neighbours: row iy0 + 1 is the thread's own second row (or the wrap of a last odd row)
+        int iy1 = iy0 + 1, iyu = iy0 + 2;
+        bool h1 = act0, hu = act1;
+        if (iy1 >= a.ny) { if (a.periodic) iy1 -= a.ny; else h1 = false; }
+        if (iyu >= a.ny) { if (a.periodic) iyu -= a.ny; else hu = false; }
+        const bool own1 = act1;                             // row iy0 + 1 exists and is this thread's
+        const int64_t off0 = (int64_t)iy0 * a.nx + ix;
+        const int64_t off1 = (int64_t)iy1 * a.nx + ix;
+        const int64_t offu = (int64_t)iyu * a.nx + ix;
+        // forward x neighbour off the warp / off the row
+        const bool edge_r = (lane == 31) || (ix + 2 >= a.nx);
+        int ixr = ix + 2;
+        bool hxr = true;
+        if (ixr >= a.nx) { if (a.periodic) ixr -= a.nx; else hxr = false; }
+        const int z0 = cz * a.zc;
+        const int z1 = min(z0 + a.zc, a.nz);
+
+        auto plane_of = [&](int p) -> const double* {       // p in [z0, z1]; p == nz: the plane above the slab
+            return (p < a.nz) ? a.x + (int64_t)p * a.plane : a.zhi;
+        };
+        double2 c0 = make_double2(0.0, 0.0), c1 = c0, cu = c0;   // plane z: rows iy0, iy0+1 (or its wrap), iy0+2
+        double cr0 = 0.0, cr1 = 0.0;                              // right neighbours of the edge lane
+        auto fetch = [&](const double* pl, double2& r0, double2& r1, double2& ru, double& e0, double& e1) {
+            r0 = r1 = ru = make_double2(0.0, 0.0);
+            e0 = e1 = 0.0;
+            if (!pl) return;
+            if (act0) r0 = ld_cached2(pl + off0);
+            if (h1) r1 = ld_cached2(pl + off1);
+            if (hu) ru = ld_cached2(pl + offu);
+            if (edge_r && hxr) {
+                if (act0) e0 = __ldg(pl + (int64_t)iy0 * a.nx + ixr);
+                if (own1) e1 = __ldg(pl + (int64_t)iy1 * a.nx + ixr);
+            }
+        };
+        fetch(plane_of(z0), c0, c1, cu, cr0, cr1);
+#pragma unroll 1
+        for (int z = z0; z < z1; ++z) {
+            double2 n0, n1, nu;
+            double nr0, nr1;
+            fetch(plane_of(z + 1), n0, n1, nu, nr0, nr1);   // consumed next iteration (and as the z+1 term now)
+            double2 d0 = make_double2(0.0, 0.0), d1 = d0;
+            if (HAS_DIAG) {
+                const double* pd = a.diag + (int64_t)z * a.plane;
+                if (act0) d0 = ld_stream2(pd + off0);
+                if (own1) d1 = ld_stream2(pd + off1);
+            }
+            double r0 = __shfl_down_sync(0xffffffffu, c0.x, 1);
+            double r1 = __shfl_down_sync(0xffffffffu, c1.x, 1);
+            if (edge_r) { r0 = cr0; r1 = cr1; }
+            // row iy0: up neighbour is c1 (own second row, or the periodic wrap when ny is odd)
+            {
+                double tx0 = fma(oz2, n0.x, fma(oy2, c1.x, fma(ox2, c0.y, (a.c + d0.x) * c0.x)));
+                double tx1 = fma(oz2, n0.y, fma(oy2, c1.y, fma(ox2, r0, (a.c + d0.y) * c0.y)));
+                acc = fma(c0.x, tx0, acc);
+                acc = fma(c0.y, tx1, acc);
+            }
+            if (own1) {
+                double tx0 = fma(oz2, n1.x, fma(oy2, cu.x, fma(ox2, c1.y, (a.c + d1.x) * c1.x)));
+                double tx1 = fma(oz2, n1.y, fma(oy2, cu.y, fma(ox2, r1, (a.c + d1.y) * c1.y)));
+                acc = fma(c1.x, tx0, acc);
+                acc = fma(c1.y, tx1, acc);
+            }
+            c0 = n0; c1 = n1; cu = nu; cr0 = nr0; cr1 = nr1;
+        }
+    }
+    const double tot = block_sum(acc * (s * s), red);
+    if (threadIdx.x == 0 && a.partials) a.partials[blockIdx.x] = tot;
+}
+
 template <int VEC, bool HAS_Y, bool HAS_Z, int MODE>
 static const void* pick_diag(bool has_diag) {
     if (has_diag) return (const void*)stencil_apply_dot_kernel<VEC, HAS_Y, HAS_Z, true, MODE>;
@@ -282,10 +385,13 @@ static int launch_stencil(lz_op* op, int mode, const double* x, const double* sc
                                             reinterpret_cast<uintptr_t>(st.ghost_hi)) & 15) == 0));
     const int vec = aligned ? 2 : 1;
     const int TX = 32 * vec;
+    // KA2: the symmetric-form alpha kernel for full 3-D couplings (2 rows per thread)
+    const bool alpha_only = (mode == 1) && aligned && has_y && has_z && (st.offx != 0.0);
     a.tiles_x = (int)((st.nx + TX - 1) / TX);
-    a.tiles_y = (int)((st.ny + kWarps - 1) / kWarps);
+    a.tiles_y = (int)((st.ny + (alpha_only ? 2 * kWarps : kWarps) - 1) / (alpha_only ? 2 * kWarps : kWarps));
     const void* fn = (vec == 2) ? pick_kernel<2>(has_y, has_z, st.diag != nullptr, mode)
                                 : pick_kernel<1>(has_y, has_z, st.diag != nullptr, mode);
+    if (alpha_only) fn = st.diag ? (const void*)stencil_alpha_kernel<true> : (const void*)stencil_alpha_kernel<false>;
     int per_sm = 0;
     LZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
@@ -303,7 +409,7 @@ static int launch_stencil(lz_op* op, int mode, const double* x, const double* sc
         const int64_t g = std::min<int64_t>(items, gmax);
         const int64_t rounds = (items + g - 1) / g;
         // time ~ rounds * zc * (1 + halo), normalised by the ideal items*zc/gmax
-        const double cost = (double)rounds * (zc + (has_z ? 2.0 : 0.0)) / ((double)st.nz * tiles / gmax);
+        const double cost = (double)rounds * (zc + (has_z ? (alpha_only ? 1.0 : 2.0) : 0.0)) / ((double)st.nz * tiles / gmax);
         if (cost < best_cost - 1e-12) { best_cost = cost; best_chunks = chunks; }
         if (zc <= 8) break;
     }
