@@ -34,10 +34,10 @@ WORKLOADS = {
                grid=(512, 512, 512), steps=100, reorth="selective", cgs_passes=2),
     "c3full": dict(desc="3D 7-point periodic Laplacian 512^3 fp64, full reorth (reference form)",
                    grid=(512, 512, 512), steps=60, reorth="full", cgs_passes=1),
-    "c2": dict(desc="graph Laplacian of a 2D Delaunay mesh, 1M vertices, SELL-32-1024, full reorth",
+    "c2": dict(desc="graph Laplacian of a 2D Delaunay mesh, 1M vertices, SELL-32-2048, full reorth",
                npts=1_000_000, steps=200, reorth="full", cgs_passes=1),
     "c4": dict(desc="graph Laplacian of a 3D random geometric graph (Poisson points, mean degree 13, ~14 nnz/row), "
-                    "~50M vertices in cell order, SELL-32-1024, selective reorth, z-slabs of cells over the GPUs (strong scaling)",
+                    "~50M vertices in cell order, SELL-32-2048, selective reorth, z-slabs of cells over the GPUs (strong scaling)",
                cells=(253, 253, 252), steps=100, reorth="selective", cgs_passes=2, strong=True),
     "c5": dict(desc="3D 7-point periodic Laplacian 1024^3 (1.07 B unknowns) fp64, CGS2 every step, z-slabs over the GPUs (strong scaling)",
                grid=(1024, 1024, 1024), steps=60, reorth="full", cgs_passes=2, strong=True),
@@ -126,15 +126,17 @@ class ClockSampler:
 
 def ncu_traffic(kernel_name):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel_name` from the
-    committed `ncu --set full` summary (profiles/r1_ncu_traffic.json; captured at the 512^3 config)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
-            t = json.load(f)
-        for k, v in t.items():
-            if k.startswith(kernel_name):
-                return v["dram_bytes_per_launch"]
-    except Exception:
-        pass
+    committed `ncu --set full` summaries (profiles/r1b_ncu_traffic.json, then r1_ncu_traffic.json;
+    captured at the 512^3 config / the 50M-vertex graph)."""
+    for name in ("r1b_ncu_traffic.json", "r1_ncu_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            for k, v in t.items():
+                if k.startswith(kernel_name):
+                    return v["dram_bytes_per_launch"]
+        except Exception:
+            pass
     return None
 
 
@@ -416,16 +418,17 @@ def main():
                                  "achieved_gbs": tot_b / ms / 1e6}
     gs_ms = kern["dots"][0] + kern["gs_update"][0]
     dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"] * per_kernel[k]["launches"]) if per_kernel else None
-    names = {"apply": "stencil_apply_dot_kernel<MODE=1> (KA)" if recompute else ("stencil_apply_dot_kernel" if is_stencil else "spmv_sell_dot_kernel"),
+    names = {"apply": "stencil_alpha_kernel (KA2)" if recompute else ("stencil_apply_dot_kernel" if is_stencil else "spmv_sell_dot_kernel"),
              "update": "stencil_apply_dot_kernel<MODE=2> (KB)" if recompute else "update_norm_kernel",
              "dots": "cgs_dots_kernel", "gs_update": "cgs_update_kernel"}
-    ncu_names = {"apply": "stencil_apply_dot_kernel<2, 1, 1, 0, 1>" if recompute else names["apply"],
+    ncu_names = {"apply": "stencil_alpha_kernel<0>" if recompute else names["apply"],
                  "update": "stencil_apply_dot_kernel<2, 1, 1, 0, 2>" if recompute else names["update"],
                  "dots": names["dots"], "gs_update": names["gs_update"]}
     roofline = None
     if dom:
         pk = per_kernel[dom]
-        traffic = ncu_traffic(ncu_names[dom]) if (args.workload in ("c3", "c3full") and M_local == 512 ** 3) else None
+        traffic = ncu_traffic(ncu_names[dom]) if ((args.workload in ("c3", "c3full") and M_local == 512 ** 3) or
+                                                  (args.workload == "c4" and world == 1)) else None
         roofline = {"kernel": names[dom], "bound": "hbm", "achieved": pk["achieved_gbs"], "peak": peak,
                     "unit": "GB/s", "frac": pk["achieved_gbs"] / peak, "traffic": traffic,
                     "peak_source": peak_src, "alg_bytes_per_launch": pk["alg_bytes"],
