@@ -40,6 +40,26 @@ def test_binding_table_matches_header(lib):
     assert sorted(_capi.SIGNATURES) == declared_symbols()
 
 
+def _struct_fields(name):
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, flags=re.S).group(1)
+    return [(t, f) for t, f in re.findall(r"\b(int32_t|float|double)\s+(\w+)\s*;", body)]
+
+
+def test_struct_layouts_match_header_and_integration_stub():
+    """lz_run_opts / lz_run_info: the ctypes mirrors (and the stub shown in INTEGRATION.md) carry the
+    header's fields in the header's order."""
+    from lanczos_b200 import _capi
+    ctype = {"int32_t": ctypes.c_int32, "float": ctypes.c_float, "double": ctypes.c_double}
+    for cname, mirror in (("lz_run_opts", _capi.RunOpts), ("lz_run_info", _capi.RunInfo)):
+        want = [(f, ctype[t]) for t, f in _struct_fields(cname)]
+        assert [(f, t) for f, t in mirror._fields_] == want
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for cname in ("lz_run_opts", "lz_run_info"):
+        for _, f in _struct_fields(cname):
+            assert '"%s"' % f in doc, f"INTEGRATION.md stub lacks field {f} of {cname}"
+
+
 def test_abi_version_and_error_string(lib):
     lib.lz_abi_version.restype = ctypes.c_int
     assert lib.lz_abi_version() == 1
