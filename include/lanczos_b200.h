@@ -136,7 +136,7 @@ typedef struct lz_run_opts {
                               before the sweep); 0: v0/|v0| is the first basis vector */
     int32_t profile;       /* 1: bracket the bandwidth kernels with CUDA events and report
                               their summed device times in lz_run_info (bench.py roofline) */
-    int32_t step_kernel;   /* 0 auto (3 for matrix-free operators, else 1); 1 two-pass step (K1
+    int32_t step_kernel;   /* 0 auto (3 for matrix-free 3/5/7-point operators, else 1); 1 two-pass step (K1
                               apply+dot, K3 update+norm: 48*M B + the operator's own bytes);
                               2 single-pass fused step KF (40*M B; 3-D structured grids with
                               nx % 64 == 0, ny % 8 == 0, one GPU, reorth != full);

@@ -47,6 +47,10 @@ int launch_apply_dot(lz_op* op, const double* x, const double* scale_dev, double
 
 // Matrix-free operators can re-evaluate H x inside the update instead of storing it (KA + KB).
 bool recompute_step_supported(const lz_op* op) { return op->kind == LZ_OP_STENCIL; }
+// ... and it pays where applying H is cheap next to the 16*M bytes it saves: the 7-point family.  The
+// 27-point kernel is latency/issue-bound (0.8 ms per apply at 512^3): two applies measured 2.07 ms per
+// step against 1.62 ms for K1b + K3, so `auto` keeps the two-pass step there.
+bool recompute_step_preferred(const lz_op* op) { return op->kind == LZ_OP_STENCIL && op->st.points == 7; }
 
 int launch_apply_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
                              double* out, double* partials, int* nparts, int* launches) {

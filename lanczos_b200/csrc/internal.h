@@ -95,6 +95,7 @@ struct StencilUpdate {
     HaloPush halo;             // sharded structured grids: boundary planes of `out` -> the neighbours' ghost buffers
 };
 bool recompute_step_supported(const lz_op* op);
+bool recompute_step_preferred(const lz_op* op);
 int launch_apply_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
                              double* out, double* partials, int* nparts, int* launches);
 

@@ -417,7 +417,8 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
                        n >= 2 && fused_step_supported(ops[0]);
     // "recompute" step KA + KB (32*M B): matrix-free operators only; the default for them
     bool recompute = (opts->step_kernel == 0 || opts->step_kernel == 3);
-    for (int s = 0; s < nl && recompute; ++s) recompute = ops[s] && recompute_step_supported(ops[s]);
+    for (int s = 0; s < nl && recompute; ++s)
+        recompute = ops[s] && (opts->step_kernel == 3 ? recompute_step_supported(ops[s]) : recompute_step_preferred(ops[s]));
     if (opts->step_kernel == 3 && !recompute) {
         set_error("lz_lanczos_run: the recompute step needs matrix-free (stencil) operators");
         return LZ_ERR_UNSUPPORTED;

@@ -430,6 +430,9 @@ def test_recompute_step_with_potential_27pt_and_ring(lz):
         L.execute_Lanczos(20, seed=5, step_kernel=kern)
         assert L.result.step_kernel == kern
         assert rel(np.diag(L.H_eff), ref27["alpha"]) < 1e-12 and rel(np.diag(L.H_eff, 1), ref27["beta"]) < 1e-12
+    L = lz.Lanczos(op27)
+    L.execute_Lanczos(20, seed=5)
+    assert L.result.step_kernel == "two_pass"        # auto: two applies of the 27-point kernel do not pay
 
 
 def test_recompute_step_rejected_for_stored_operators(lz):
