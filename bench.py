@@ -251,6 +251,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cgs-fusion", action="store_true", help="CGS2 as four separate sweeps (comparison runs)")
     ap.add_argument("--step-kernel", default="auto", choices=["auto", "two_pass", "recompute", "fused"],
                     help="auto = the library default (recompute for matrix-free operators)")
     args = ap.parse_args()
@@ -276,7 +277,8 @@ def main():
     K, W = int(args.steps), max(3, int(args.warmup))
     H, grid = build_operator(lz, args.workload, world, rank)
     M_total = int(np.prod(grid))
-    opts = dict(reorth=wl["reorth"], cgs_passes=wl["cgs_passes"], ref_compat=True, step_kernel=args.step_kernel)
+    opts = dict(reorth=wl["reorth"], cgs_passes=wl["cgs_passes"], ref_compat=True, step_kernel=args.step_kernel,
+                cgs_fused=not args.no_cgs_fusion)
 
     if world > 1:
         from lanczos_b200 import team as lzteam
@@ -351,7 +353,8 @@ def main():
     # ---- region A2: the same K steps again with a CUDA-event pair around every bandwidth kernel
     # (per-kernel roofline).  Kept out of region A because the event records break up
     # back-to-back launches and cost several percent of step time.
-    kern = {"apply": [0.0, 0], "update": [0.0, 0], "dots": [0.0, 0], "gs_update": [0.0, 0], "fused": [0.0, 0]}
+    kern = {"apply": [0.0, 0], "update": [0.0, 0], "dots": [0.0, 0], "gs_update": [0.0, 0], "fused": [0.0, 0],
+            "gs_fused": [0.0, 0]}
     step_kernel = "two_pass"
     for c in chunks:
         res = solve(c, v0_dev, profile=True)
@@ -405,25 +408,32 @@ def main():
     # re-orthogonalisation the schedule is known: at step j every sweep reads the j rows before row j
     # and row j itself ((2k+3)*8*N bytes per sweep against k vectors).
     if wl["reorth"] == "full":
-        dots_b = upd_b = 0.0
+        dots_b = upd_b = fus_b = 0.0
+        gs_fused = kern["gs_fused"][1] > 0                    # CGS2: K4c = update of sweep 1 + dots of sweep 2
         for c in chunks:
             for j in range(c):
                 for p_ in range(wl["cgs_passes"]):
-                    dots_b += (j + 1) * 8.0 * N               # j basis rows + the target row
-                    upd_b += (j + 2) * 8.0 * N                # j rows + target in, target out
-        for k, tot_b in (("dots", dots_b), ("gs_update", upd_b)):
+                    if gs_fused and j >= 1 and p_ == 0:
+                        dots_b += (j + 1) * 8.0 * N
+                        fus_b += (j + 2) * 8.0 * N            # j rows + target in, target out, dots of sweep 2 for free
+                    elif gs_fused and j >= 1 and p_ == 1:
+                        upd_b += (j + 2) * 8.0 * N
+                    else:
+                        dots_b += (j + 1) * 8.0 * N           # j basis rows + the target row
+                        upd_b += (j + 2) * 8.0 * N            # j rows + target in, target out
+        for k, tot_b in (("dots", dots_b), ("gs_update", upd_b), ("gs_fused", fus_b)):
             ms, cnt = kern[k]
             if cnt:
                 per_kernel[k] = {"launches": cnt, "avg_ms": ms / cnt, "alg_bytes": tot_b / cnt,
                                  "achieved_gbs": tot_b / ms / 1e6}
-    gs_ms = kern["dots"][0] + kern["gs_update"][0]
+    gs_ms = kern["dots"][0] + kern["gs_update"][0] + kern["gs_fused"][0]
     dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"] * per_kernel[k]["launches"]) if per_kernel else None
     names = {"apply": "stencil_alpha_kernel (KA2)" if recompute else ("stencil_apply_dot_kernel" if is_stencil else "spmv_sell_dot_kernel"),
              "update": "stencil_apply_dot_kernel<MODE=2> (KB)" if recompute else "update_norm_kernel",
-             "dots": "cgs_dots_kernel", "gs_update": "cgs_update_kernel"}
+             "dots": "cgs_dots_kernel", "gs_update": "cgs_update_kernel", "gs_fused": "cgs_update_dots_kernel"}
     ncu_names = {"apply": "stencil_alpha_kernel<0>" if recompute else names["apply"],
                  "update": "stencil_apply_dot_kernel<2, 1, 1, 0, 2>" if recompute else names["update"],
-                 "dots": names["dots"], "gs_update": names["gs_update"]}
+                 "dots": names["dots"], "gs_update": names["gs_update"], "gs_fused": names["gs_fused"]}
     roofline = None
     if dom:
         pk = per_kernel[dom]

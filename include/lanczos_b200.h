@@ -142,7 +142,8 @@ typedef struct lz_run_opts {
                               nx % 64 == 0, ny % 8 == 0, one GPU, reorth != full);
                               3 recompute step (matrix-free operators: KA reduces alpha without
                               writing H v, KB applies H again inside the update: 32*M B)       */
-    int32_t reserved;
+    int32_t flags;         /* bit 0: do not fuse the middle of CGS2 (K4c: update of sweep 1 + dots of
+                              sweep 2 from one read of the basis); 0 = defaults                  */
     double  breakdown_tol; /* stop when beta <= breakdown_tol * |alpha_0| (0: only 0/NaN) */
     double  select_tol;    /* selective: orthogonality level that triggers (0 -> sqrt(eps)) */
 } lz_run_opts;
@@ -163,6 +164,8 @@ typedef struct lz_run_info {
     float   gsupd_ms;      /* ... K4b Gram-Schmidt update                            */
     float   fused_ms;      /* ... KF single-pass fused step                          */
     int32_t step_kernel;   /* the step kernel that ran (1, 2 or 3 as in lz_run_opts)  */
+    int32_t gsfused_launches; /* ... K4c fused Gram-Schmidt update + dots              */
+    float   gsfused_ms;
 } lz_run_info;
 
 /* Runs n steps from v0_dev (M doubles).  Outputs: alpha_host[n], beta_host[n-1]

@@ -30,7 +30,7 @@ class LanczosBreakdown(ArithmeticError):
 
 class RunOpts(C.Structure):
     _fields_ = [("reorth", C.c_int32), ("cgs_passes", C.c_int32), ("ref_compat", C.c_int32),
-                ("profile", C.c_int32), ("step_kernel", C.c_int32), ("reserved", C.c_int32),
+                ("profile", C.c_int32), ("step_kernel", C.c_int32), ("flags", C.c_int32),
                 ("breakdown_tol", C.c_double), ("select_tol", C.c_double)]
 
 
@@ -41,7 +41,7 @@ class RunInfo(C.Structure):
                 ("fused_launches", C.c_int32),
                 ("gpu_ms", C.c_float), ("apply_ms", C.c_float), ("update_ms", C.c_float),
                 ("dots_ms", C.c_float), ("gsupd_ms", C.c_float), ("fused_ms", C.c_float),
-                ("step_kernel", C.c_int32)]
+                ("step_kernel", C.c_int32), ("gsfused_launches", C.c_int32), ("gsfused_ms", C.c_float)]
 
 
 _vp, _i32, _i64, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double

@@ -127,6 +127,12 @@ int launch_cgs_dots(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, const 
 int launch_cgs_update(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, const double* target,
                       const double* coef_dev, const double* cself_dev, double* out, int64_t M,
                       const int* flag_dev, const HaloPush* halo = nullptr);
+// fused middle of CGS2 (K4c): target <- cself * target - V_k coef in place, and the partials of
+// V_k^T target_new, from one read of the k basis rows staged in shared memory
+bool cgs_update_dots_supported(const double* V, int64_t ldv, int k, const double* target);
+int launch_cgs_update_dots(lz_ctx* ctx, const double* V, int64_t ldv, int k, double* target,
+                           const double* coef_dev, const double* cself_dev, int64_t M, double* part,
+                           int* ncg_out, const int* flag_dev);
 // Y[c,:] = sum_r S[r + c*n] * V[r,:]  (S on the device, n x k column-major)
 int launch_ritz_lift(lz_ctx* ctx, const double* V, int64_t ldv, int n, int64_t M,
                      const double* S_dev, int k, double* Y, int64_t ldy);

@@ -495,7 +495,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         r.kt.ctx = r.ctx;
         r.kt.on = (opts->profile != 0);
         if (r.kt.on) {   // create the pool outside the timed loop
-            while (r.ctx->event_pool.size() < (size_t)(2 * (3 + 2 * passes) * n + 8)) {
+            while (r.ctx->event_pool.size() < (size_t)(2 * (4 + 2 * passes) * n + 8)) {
                 cudaEvent_t e = nullptr;
                 LZ_CUDA(cudaEventCreate(&e));
                 r.ctx->event_pool.push_back(e);
@@ -509,7 +509,8 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     const double delta = opts->select_tol > 0.0 ? opts->select_tol : sqrt(eps);
     const double eps1 = eps * 1.5;      // noise floor of the omega recurrence
     const double psi = eps * sqrt(M_global);
-    enum { K_APPLY = 0, K_UPDATE = 1, K_DOTS = 2, K_GSUPD = 3, K_FUSED = 4, K_NKINDS = 5 };
+    enum { K_APPLY = 0, K_UPDATE = 1, K_DOTS = 2, K_GSUPD = 3, K_FUSED = 4, K_GSFUSED = 5, K_NKINDS = 6 };
+    const bool allow_gs_fusion = passes == 2 && !(opts->flags & 1);
 
     // run `fn(shard)` on every local shard, on its device
     auto each = [&](auto&& fn) -> int {
@@ -668,18 +669,24 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         if (maybe_reorth && (j > 0 || ref)) {
             const bool sel = (reorth == LZ_REORTH_SELECTIVE);
             bool pushed = false;
+            // CGS2: the update of the first sweep and the dots of the second read the same j rows -
+            // one fused kernel (K4c) when the staged tile fits shared memory
+            bool fuse = allow_gs_fusion && j >= 1;
+            for (int s = 0; s < nl && fuse; ++s) fuse = cgs_update_dots_supported(R[s].V, R[s].ldv, j, R[s].row(j));
             for (int p = 0; p < passes; ++p) {
                 const int ref_form = (ref && p == 0) ? 1 : 0;
                 const int nrows = ref_form ? j + 1 : j;      // the reference's sum includes row j itself
                 if (nrows == 0) continue;
-                LZ_CHECK(each([&](ShardRun& r) {
-                    r.kt.begin(K_DOTS);
-                    const int rc = launch_cgs_dots(r.ctx, r.V, r.ldv, nrows, r.row(j), r.M, r.gs_part, &r.ncg,
-                                                   sel ? r.st.flags + 1 : nullptr);
-                    r.kt.end();
-                    ++launches;
-                    return rc;
-                }));
+                if (!(fuse && p == 1)) {
+                    LZ_CHECK(each([&](ShardRun& r) {
+                        r.kt.begin(K_DOTS);
+                        const int rc = launch_cgs_dots(r.ctx, r.V, r.ldv, nrows, r.row(j), r.M, r.gs_part, &r.ncg,
+                                                       sel ? r.st.flags + 1 : nullptr);
+                        r.kt.end();
+                        ++launches;
+                        return rc;
+                    }));
+                }
                 LZ_CHECK(exchange([&](ShardRun& r, unsigned long long seq, int mode) -> int {
                     fin_ip_kernel<<<1, kThreads, 0, r.ctx->stream>>>(r.gs_part, r.ncg, j, ref_form, ref_form, r.st, r.pc,
                                                                      seq, mode, sel ? r.st.flags + 1 : nullptr,
@@ -687,6 +694,17 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
                     ++launches;
                     return LZ_OK;
                 }));
+                if (fuse && p == 0) {
+                    LZ_CHECK(each([&](ShardRun& r) {
+                        r.kt.begin(K_GSFUSED);
+                        const int rc = launch_cgs_update_dots(r.ctx, r.V, r.ldv, j, r.row(j), r.st.coef, r.st.cself, r.M,
+                                                              r.gs_part, &r.ncg, sel ? r.st.flags + 1 : nullptr);
+                        r.kt.end();
+                        ++launches;
+                        return rc;
+                    }));
+                    continue;                 // its halo planes / ghost entries travel after the second sweep
+                }
                 LZ_CHECK(each([&](ShardRun& r) {
                     HaloPush h = halo_for(team, r, par);
                     r.kt.begin(K_GSUPD);
@@ -783,8 +801,8 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     if (row_scale_host)
         for (int j = 0; j < n; ++j) row_scale_host[j] = h_scale[j];
     float ms = 0.f;
-    float kms[K_NKINDS] = {0, 0, 0, 0, 0};
-    int kcnt[K_NKINDS] = {0, 0, 0, 0, 0};
+    float kms[K_NKINDS] = {0, 0, 0, 0, 0, 0};
+    int kcnt[K_NKINDS] = {0, 0, 0, 0, 0, 0};
     for (int s = 0; s < nl; ++s) {
         ShardRun& r = R[s];
         if (nl > 1) LZ_CUDA(cudaSetDevice(r.ctx->device));
@@ -824,6 +842,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         info->gsupd_ms = kms[K_GSUPD];   info->gsupd_launches = kcnt[K_GSUPD];
         info->fused_ms = kms[K_FUSED];   info->fused_launches = kcnt[K_FUSED];
         info->step_kernel = fused ? 2 : (recompute ? 3 : 1);
+        info->gsfused_ms = kms[K_GSFUSED]; info->gsfused_launches = kcnt[K_GSFUSED];
     }
     return status;
 }

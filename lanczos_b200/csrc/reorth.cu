@@ -186,6 +186,126 @@ int launch_cgs_update(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, cons
     return LZ_OK;
 }
 
+// K4c: the middle of CGS2 from ONE read of the basis.  Classical Gram-Schmidt applied twice is
+//     h1 = V^T v;  v' = c v - V h1;  h2 = V^T v';  v'' = v' - V h2
+// i.e. four sweeps over the k basis rows, (4k + 6) * 8 * M bytes.  The update of the first pass and the
+// dots of the second touch the same rows: here a CTA stages a tile of TC columns of all k rows (and of
+// v) in shared memory with 16-byte cp.async copies, forms v' for the tile (thread <-> column, rows in
+// order: the same bits as K4b), stores it, and reduces V_tile . v'_tile for every row (warp <-> rows,
+// lanes <-> columns) into per-lane accumulators that live across the CTA's tiles.  CGS2 then moves
+// (3k + 5) * 8 * M bytes.  Two or three CTAs per SM overlap one CTA's copy with another's arithmetic;
+// the bytes in flight are the staged tiles, not registers.
+template <int TC, int RMAX>
+__global__ void __launch_bounds__(TC)
+cgs_update_dots_kernel(const double* __restrict__ V, int64_t ldv, int k, double* target,
+                       const double* __restrict__ coef, const double* __restrict__ cself_p, int64_t M,
+                       int64_t ntiles, double* __restrict__ part, const int* __restrict__ flag) {
+    if (flag && *flag == 0) return;
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;                          // [k + 1][TC]: rows 0..k-1 of the basis, row k = v
+    double* vp = sm + (size_t)(k + 1) * TC;  // [TC]: v' of the tile
+    double* sh = vp + TC;                    // [k]: h1
+    constexpr int NW = TC / 32;
+    constexpr int CPL = TC / 32;             // columns per lane in the reduction
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int r = t; r < k; r += TC) sh[r] = coef[r];
+    const double cself = __ldg(cself_p);
+    double acc[RMAX];
+#pragma unroll
+    for (int q = 0; q < RMAX; ++q) acc[q] = 0.0;
+    constexpr int UPR = TC / 2;              // 16-byte units per row of the tile
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t c0 = tile * TC;
+        __syncthreads();                     // the previous tile's reduction has finished reading S / vp
+        for (int u = t; u < (k + 1) * UPR; u += TC) {
+            const int r = u / UPR, cu = u - r * UPR;
+            const int64_t col = c0 + 2 * cu;
+            const double* src = (r < k ? V + (int64_t)r * ldv : target) + col;
+            const int valid = col + 1 < M ? 16 : (col < M ? 8 : 0);      // zero-fill beyond M
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(S + (size_t)r * TC + 2 * cu);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(valid ? src : V), "r"(valid) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        {   // v' for column t of the tile (rows in order, like cgs_update_kernel)
+            double a = cself * S[(size_t)k * TC + t];
+            for (int r = 0; r < k; ++r) a = fma(-sh[r], S[(size_t)r * TC + t], a);
+            vp[t] = a;
+            if (c0 + t < M) st_stream1(target + c0 + t, a);
+        }
+        __syncthreads();
+        double vl[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) vl[c] = vp[lane + 32 * c];
+#pragma unroll
+        for (int q = 0; q < RMAX; ++q) {
+            const int r = warp + q * NW;
+            if (r < k) {
+                const double* row = S + (size_t)r * TC + lane;
+                double a = acc[q];
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) a = fma(row[32 * c], vl[c], a);
+                acc[q] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < RMAX; ++q) {
+        const int r = warp + q * NW;
+        const double tot = warp_sum(acc[q]);
+        if (lane == 0 && r < k) part[(int64_t)r * gridDim.x + blockIdx.x] = tot;
+    }
+}
+
+struct UpdDotsCfg { int tc, rmax; size_t smem; };
+static bool update_dots_config(int k, UpdDotsCfg* cfg) {
+    // TC = 256 while two CTAs of (k + 2) * 2 KB fit an SM, else TC = 128; rows per warp <= RMAX
+    const size_t cap = 100 * 1024;
+    for (int tc : {256, 128}) {
+        const size_t bytes = ((size_t)(k + 1) * tc + tc + k + 2) * 8;
+        const int nw = tc / 32;
+        const int need = (k + nw - 1) / nw;
+        if (bytes <= cap && need <= 26) {
+            cfg->tc = tc;
+            cfg->rmax = need <= 8 ? 8 : (need <= 16 ? 16 : 26);
+            cfg->smem = bytes;
+            return true;
+        }
+    }
+    return false;
+}
+
+bool cgs_update_dots_supported(const double* V, int64_t ldv, int k, const double* target) {
+    UpdDotsCfg c;
+    return k >= 1 && ((((uintptr_t)V | (uintptr_t)target) & 15) == 0) && ((ldv & 1) == 0) && update_dots_config(k, &c);
+}
+
+// target <- cself * target - V_k coef (in place), part[r * ncg + g] = partial of V[r, :] . target_new
+int launch_cgs_update_dots(lz_ctx* ctx, const double* V, int64_t ldv, int k, double* target,
+                           const double* coef_dev, const double* cself_dev, int64_t M, double* part,
+                           int* ncg_out, const int* flag_dev) {
+    UpdDotsCfg c;
+    LZ_REQUIRE(cgs_update_dots_supported(V, ldv, k, target), "fused Gram-Schmidt update+dots: unsupported shape (k = %d)", k);
+    update_dots_config(k, &c);
+    const void* fn = nullptr;
+#define LZ_UD(TCV, RM) if (c.tc == TCV && c.rmax == RM) fn = (const void*)cgs_update_dots_kernel<TCV, RM>
+    LZ_UD(256, 8); LZ_UD(256, 16); LZ_UD(256, 26); LZ_UD(128, 8); LZ_UD(128, 16); LZ_UD(128, 26);
+#undef LZ_UD
+    LZ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    int per_sm = 0;
+    LZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, c.tc, c.smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t ntiles = (M + c.tc - 1) / c.tc;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, std::min<int64_t>((int64_t)ctx->sms * per_sm, kMaxPartials)));
+    int kk = k;
+    void* args[] = {(void*)&V, (void*)&ldv, (void*)&kk, (void*)&target, (void*)&coef_dev, (void*)&cself_dev,
+                    (void*)&M, (void*)&ntiles, (void*)&part, (void*)&flag_dev};
+    LZ_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(c.tc), args, c.smem, ctx->stream));
+    if (ncg_out) *ncg_out = grid;
+    return LZ_OK;
+}
+
 // K5: Y[c, :] (+)= sum_{r < n} S[r + c*lds] * V[r, :]  for a block of kLiftCols columns per
 // sweep; the basis is read once per block of columns.  n <= kLiftRowsSmem per launch.
 constexpr int kLiftCols = 4;

@@ -340,7 +340,8 @@ class LanczosResult:
                           "update": (float(info.update_ms), info.update_launches),
                           "dots": (float(info.dots_ms), info.dots_launches),
                           "gs_update": (float(info.gsupd_ms), info.gsupd_launches),
-                          "fused": (float(info.fused_ms), info.fused_launches)}
+                          "fused": (float(info.fused_ms), info.fused_launches),
+                          "gs_fused": (float(info.gsfused_ms), info.gsfused_launches)}
 
     def tridiagonal(self) -> np.ndarray:
         """Dense H_eff like Lanczos.py:121-130."""
@@ -386,7 +387,7 @@ class LanczosResult:
 
 def run_lanczos(op: DeviceOperator, v0, n: int, *, reorth="full", cgs_passes=1, ref_compat=True,
                 keep_basis=True, breakdown_tol=0.0, select_tol=0.0, V_dev=None,
-                profile=False, step_kernel="auto") -> LanczosResult:
+                profile=False, step_kernel="auto", cgs_fused=True) -> LanczosResult:
     """Enqueue and run the n-step loop (lz_lanczos_run).  `v0` is a host array (copied through
     pinned memory) or a CUDA tensor of M doubles."""
     torch = _torch()
@@ -416,7 +417,7 @@ def run_lanczos(op: DeviceOperator, v0, n: int, *, reorth="full", cgs_passes=1, 
         beta = np.zeros(max(n - 1, 0))
         scale = np.ones(n)
         opts = RunOpts(mode, int(cgs_passes), 1 if ref_compat else 0, 1 if profile else 0,
-                       STEP_KERNEL[step_kernel], 0, float(breakdown_tol), float(select_tol))
+                       STEP_KERNEL[step_kernel], 0 if cgs_fused else 1, float(breakdown_tol), float(select_tol))
         info = RunInfo()
         status = ctx.lib.lz_lanczos_run(
             ctx.handle, op.handle, C.c_void_p(v0_dev.data_ptr()), n, C.byref(opts),

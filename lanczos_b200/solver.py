@@ -90,12 +90,13 @@ class LanczosBase:
     # ---- the loop ---------------------------------------------------------------------------
     def _execute(self, n, seed, use_cuda, v0, *, reorth="full", cgs_passes=1, ref_compat=True,
                  fmt="auto", sigma=0, device=None, keep_basis=True, breakdown_tol=0.0,
-                 select_tol=0.0, profile=False, step_kernel="auto", verbose=True):
+                 select_tol=0.0, profile=False, step_kernel="auto", cgs_fused=True, verbose=True):
         """Keyword-only extras (all default to the reference's behaviour):
         reorth 'full' | 'selective' | 'none'; cgs_passes 1 | 2; ref_compat (the v0-discarding
         pre-step and the (2-|v|^2) sweep form of the reference); fmt 'auto' | 'csr' | 'sell' and
         sigma for sparse operators; device index; keep_basis; breakdown_tol; select_tol;
         profile (per-kernel CUDA-event timing); step_kernel 'auto' | 'two_pass' | 'fused' | 'recompute';
+        cgs_fused (CGS2: one read of the basis for the update of sweep 1 and the dots of sweep 2);
         verbose (the reference's '+++' banners)."""
         if n > self.M:
             raise ValueError("n cannot be larger than M!")                  # Lanczos.py:76-77
@@ -129,7 +130,7 @@ class LanczosBase:
         self._result = engine.run_lanczos(op, start, n, reorth=reorth, cgs_passes=cgs_passes,
                                           ref_compat=ref_compat, keep_basis=keep_basis,
                                           breakdown_tol=breakdown_tol, select_tol=select_tol,
-                                          profile=profile, step_kernel=step_kernel)
+                                          profile=profile, step_kernel=step_kernel, cgs_fused=cgs_fused)
         self._H_eff = self._result.tridiagonal()
         self._V_host = None
         self.H_eigs_have_been_found = False

@@ -360,6 +360,45 @@ def test_large_grid_invariants(lz):
 
 # ---- KF: the single-pass fused step (structured grids, nx % 64 == 0, ny % 8 == 0) ----------------
 
+@pytest.mark.parametrize("grid,n", [((20, 18, 16), 30), ((33, 7, 5), 60), ((64, 48, 6), 112), ((257,), 40)])
+def test_cgs2_fused_middle_matches_four_sweeps(lz, grid, n):
+    """K4c (update of sweep 1 + dots of sweep 2 from one staged read of the basis) against the four
+    separate sweeps: v' is formed with the same operations in the same order, the second sweep's
+    coefficients differ only in the order of their partial sums.  n = 112 crosses every tile
+    configuration (TC = 256 up to 48 rows, TC = 128 up to ~98) and the unfused fallback beyond."""
+    dim = len(grid)
+    op = lz.StencilOperator(grid, 2.0 * dim + 0.3, [-1.0, -0.9, -1.1][:dim], bc="dirichlet")
+    out = {}
+    for fused in (True, False):
+        L = lz.Lanczos(op)
+        L.execute_Lanczos(n, seed=21, reorth="full", cgs_passes=2, cgs_fused=fused, profile=True)
+        out[fused] = (np.diag(L.H_eff).copy(), np.diag(L.H_eff, 1).copy(), L.V.copy(), L.result.kernel_ms["gs_fused"][1])
+    assert out[True][3] > 0 and out[False][3] == 0
+    assert rel(out[True][0], out[False][0]) < 1e-12 and rel(out[True][1], out[False][1]) < 1e-12
+    assert np.max(np.abs(out[True][2] - out[False][2])) < 1e-12
+    V = out[True][2]
+    assert np.max(np.abs(V.T @ V - np.eye(n))) < 5e-14
+
+
+def test_cgs2_fused_middle_sparse_and_selective(lz):
+    G = orc.delaunay_graph_laplacian(5001, seed=6)          # odd row count: the zero-filled tail of the last tile
+    T = {}
+    for fused in (True, False):
+        L = lz.IrrLanczos(G)
+        L.execute_LanczosOld(40, seed=2, cgs_passes=2, cgs_fused=fused)
+        T[fused] = L.H_eff.copy()
+    assert rel(np.diag(T[True]), np.diag(T[False])) < 1e-12 and rel(np.diag(T[True], 1), np.diag(T[False], 1)) < 1e-12
+    H, c, o, pot = orc.deuteron_hamiltonian(12)
+    op = lz.StencilOperator((12, 12, 12), c, o, diag=pot)
+    th = {}
+    for fused in (True, False):
+        L = lz.Lanczos(op)
+        L.execute_Lanczos(80, seed=78, reorth="selective", cgs_passes=2, cgs_fused=fused)
+        assert L.result.reorth_count > 0
+        th[fused] = np.linalg.eigvalsh(L.H_eff)[:4]
+    assert rel(th[True], th[False]) < 1e-10
+
+
 RECOMPUTE_CASES = [((7,), "periodic"), ((9,), "dirichlet"), ((6, 5), "periodic"), ((70, 3), "dirichlet"),
                    ((4, 3, 5), "periodic"), ((5, 3, 2), "dirichlet"), ((2, 2, 2), "periodic"), ((66, 9, 3), "periodic"),
                    ((130, 17, 4), "dirichlet"), ((64, 16, 12), "periodic")]
