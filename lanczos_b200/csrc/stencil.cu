@@ -317,6 +317,100 @@ stencil_alpha_kernel(const StencilArgs a) {
     if (threadIdx.x == 0 && a.partials) a.partials[blockIdx.x] = tot;
 }
 
+// KA2, lean form for grids made of whole tiles (nx % 64 == 0, ny % 16 == 0, plane < 4 GB): every
+// thread is active, so nothing is predicated.  Boundary cases are folded into data instead of control
+// flow: an absent neighbour (Dirichlet wall, missing plane) is read from a clamped valid address and
+// its coupling coefficient is zero; the plane base is a uniform pointer bumped once per plane and the
+// per-thread offsets are 32-bit.  The general kernel above spends ~130 instructions per plane and
+// thread (address arithmetic, re-materialised constants, zeroing for predicated loads) and runs at
+// 66 % issue utilisation; this loop needs ~45.
+template <bool HAS_DIAG>
+__global__ void __launch_bounds__(kThreads, 4)
+stencil_alpha_fast_kernel(const StencilArgs a) {
+    if (a.skip && *a.skip == 0) return;
+    __shared__ double red[kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double s = a.scale ? __ldg(a.scale) : 1.0;
+    constexpr int TX = 64, TY = 2 * kWarps;
+    const double cc = a.c, ox2 = 2.0 * a.ox, oy2 = 2.0 * a.oy, oz2 = 2.0 * a.oz;
+    const uint32_t plane_b = (uint32_t)(a.plane * 8);
+    double acc = 0.0;
+
+    for (int64_t item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+        const int tx = (int)(item % a.tiles_x);
+        const int64_t t = item / a.tiles_x;
+        const int ty = (int)(t % a.tiles_y);
+        const int cz = (int)(t / a.tiles_y);
+        const int ix = tx * TX + 2 * lane;
+        const int iy0 = ty * TY + 2 * warp;
+        int iyu = iy0 + 2;
+        double oy2u = oy2;                                   // coupling of row iy0 + 1 to the row above the pair
+        if (iyu >= a.ny) { if (a.periodic) iyu -= a.ny; else { iyu = iy0 + 1; oy2u = 0.0; } }
+        const bool edge_r = (lane == 31);
+        int ixr = ix + 2;
+        double ox2r = ox2;                                   // coupling of the pair's second point to its right neighbour
+        if (ixr >= a.nx) { if (a.periodic) ixr -= a.nx; else { ixr = ix; ox2r = 0.0; } }
+        const uint32_t o0 = (uint32_t)(iy0 * a.nx + ix) * 8u;
+        const uint32_t o1 = o0 + (uint32_t)a.nx * 8u;
+        const uint32_t ou = (uint32_t)(iyu * a.nx + ix) * 8u;
+        const uint32_t oe0 = (uint32_t)(iy0 * a.nx + ixr) * 8u;
+        const uint32_t oe1 = oe0 + (uint32_t)a.nx * 8u;
+        const int z0 = cz * a.zc;
+        const int z1 = min(z0 + a.zc, a.nz);
+        const char* pl = reinterpret_cast<const char*>(a.x) + (int64_t)z0 * plane_b;
+        const char* pd = HAS_DIAG ? reinterpret_cast<const char*>(a.diag) + (int64_t)z0 * plane_b : nullptr;
+
+        double2 c0 = ld_cached2(reinterpret_cast<const double*>(pl + o0));
+        double2 c1 = ld_cached2(reinterpret_cast<const double*>(pl + o1));
+        double2 cu = ld_cached2(reinterpret_cast<const double*>(pl + ou));
+        double cr0 = 0.0, cr1 = 0.0;
+        if (edge_r) {
+            cr0 = __ldg(reinterpret_cast<const double*>(pl + oe0));
+            cr1 = __ldg(reinterpret_cast<const double*>(pl + oe1));
+        }
+        auto step = [&](const char* pn, double ozn) {
+            const double2 n0 = ld_cached2(reinterpret_cast<const double*>(pn + o0));
+            const double2 n1 = ld_cached2(reinterpret_cast<const double*>(pn + o1));
+            const double2 nu = ld_cached2(reinterpret_cast<const double*>(pn + ou));
+            double nr0 = 0.0, nr1 = 0.0;
+            if (edge_r) {
+                nr0 = __ldg(reinterpret_cast<const double*>(pn + oe0));
+                nr1 = __ldg(reinterpret_cast<const double*>(pn + oe1));
+            }
+            double d00 = cc, d01 = cc, d10 = cc, d11 = cc;
+            if (HAS_DIAG) {
+                const double2 e0 = ld_stream2(reinterpret_cast<const double*>(pd + o0));
+                const double2 e1 = ld_stream2(reinterpret_cast<const double*>(pd + o1));
+                d00 += e0.x; d01 += e0.y; d10 += e1.x; d11 += e1.y;
+                pd += plane_b;
+            }
+            double r0 = __shfl_down_sync(0xffffffffu, c0.x, 1);
+            double r1 = __shfl_down_sync(0xffffffffu, c1.x, 1);
+            if (edge_r) { r0 = cr0; r1 = cr1; }
+            const double t00 = fma(ozn, n0.x, fma(oy2, c1.x, fma(ox2, c0.y, d00 * c0.x)));
+            const double t01 = fma(ozn, n0.y, fma(oy2, c1.y, fma(ox2r, r0, d01 * c0.y)));
+            const double t10 = fma(ozn, n1.x, fma(oy2u, cu.x, fma(ox2, c1.y, d10 * c1.x)));
+            const double t11 = fma(ozn, n1.y, fma(oy2u, cu.y, fma(ox2r, r1, d11 * c1.y)));
+            acc = fma(c0.x, t00, acc);
+            acc = fma(c0.y, t01, acc);
+            acc = fma(c1.x, t10, acc);
+            acc = fma(c1.y, t11, acc);
+            c0 = n0; c1 = n1; cu = nu; cr0 = nr0; cr1 = nr1;
+        };
+#pragma unroll 2
+        for (int z = z0; z < z1 - 1; ++z) {
+            pl += plane_b;
+            step(pl, oz2);
+        }
+        // last plane of the chunk: its upper neighbour is the next chunk's first plane, the plane above
+        // the slab (periodic wrap / ghost plane), or absent
+        const char* pn = (z1 < a.nz) ? pl + plane_b : reinterpret_cast<const char*>(a.zhi);
+        step(pn ? pn : pl, pn ? oz2 : 0.0);
+    }
+    const double tot = block_sum(acc * (s * s), red);
+    if (threadIdx.x == 0 && a.partials) a.partials[blockIdx.x] = tot;
+}
+
 template <int VEC, bool HAS_Y, bool HAS_Z, int MODE>
 static const void* pick_diag(bool has_diag) {
     if (has_diag) return (const void*)stencil_apply_dot_kernel<VEC, HAS_Y, HAS_Z, true, MODE>;
@@ -391,7 +485,11 @@ static int launch_stencil(lz_op* op, int mode, const double* x, const double* sc
     a.tiles_y = (int)((st.ny + (alpha_only ? 2 * kWarps : kWarps) - 1) / (alpha_only ? 2 * kWarps : kWarps));
     const void* fn = (vec == 2) ? pick_kernel<2>(has_y, has_z, st.diag != nullptr, mode)
                                 : pick_kernel<1>(has_y, has_z, st.diag != nullptr, mode);
-    if (alpha_only) fn = st.diag ? (const void*)stencil_alpha_kernel<true> : (const void*)stencil_alpha_kernel<false>;
+    if (alpha_only) {
+        const bool whole_tiles = (st.nx % 64 == 0) && (st.ny % (2 * kWarps) == 0) && (st.nx * st.ny * 8 < (int64_t)1 << 32);
+        if (whole_tiles) fn = st.diag ? (const void*)stencil_alpha_fast_kernel<true> : (const void*)stencil_alpha_fast_kernel<false>;
+        else fn = st.diag ? (const void*)stencil_alpha_kernel<true> : (const void*)stencil_alpha_kernel<false>;
+    }
     int per_sm = 0;
     LZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
     if (per_sm < 1) per_sm = 1;

@@ -401,7 +401,8 @@ def test_cgs2_fused_middle_sparse_and_selective(lz):
 
 RECOMPUTE_CASES = [((7,), "periodic"), ((9,), "dirichlet"), ((6, 5), "periodic"), ((70, 3), "dirichlet"),
                    ((4, 3, 5), "periodic"), ((5, 3, 2), "dirichlet"), ((2, 2, 2), "periodic"), ((66, 9, 3), "periodic"),
-                   ((130, 17, 4), "dirichlet"), ((64, 16, 12), "periodic")]
+                   ((130, 17, 4), "dirichlet"), ((64, 16, 12), "periodic"), ((128, 32, 5), "dirichlet"),
+                   ((64, 48, 1), "periodic"), ((64, 16, 2), "dirichlet")]      # whole tiles: the lean KA2 kernel
 
 
 @pytest.mark.parametrize("grid,bc", RECOMPUTE_CASES)
@@ -472,6 +473,20 @@ def test_recompute_step_with_potential_27pt_and_ring(lz):
     L = lz.Lanczos(op27)
     L.execute_Lanczos(20, seed=5)
     assert L.result.step_kernel == "two_pass"        # auto: two applies of the 27-point kernel do not pay
+
+
+def test_recompute_step_whole_tiles_with_potential(lz):
+    """The lean KA2 kernel (nx % 64 == 0, ny % 16 == 0) with a potential array, both boundary types."""
+    grid = (64, 32, 6)
+    pot = np.random.RandomState(8).uniform(0.0, 2.0, int(np.prod(grid)))
+    for bc in ("periodic", "dirichlet"):
+        op = lz.StencilOperator(grid, 6.2, [-1.0, -0.7, -1.3], bc=bc, diag=pot)
+        H = orc.laplacian_csr(grid, 6.2, [-1.0, -0.7, -1.3], periodic=(bc == "periodic"), diag=pot)
+        ref = orc.lanczos(H, 16, seed=3)
+        for kern in ("recompute", "two_pass"):
+            L = lz.Lanczos(op)
+            L.execute_Lanczos(16, seed=3, step_kernel=kern)
+            assert rel(np.diag(L.H_eff), ref["alpha"]) < 1e-12 and rel(np.diag(L.H_eff, 1), ref["beta"]) < 1e-12
 
 
 def test_recompute_step_rejected_for_stored_operators(lz):

@@ -64,7 +64,7 @@ def test_local_team_matches_single_gpu(lz, grid, bc, world, reorth, passes):
 
 
 @pytest.mark.parametrize("grid,bc,world", [((16, 12, 20), "periodic", 4), ((16, 12, 10), "dirichlet", 3), ((40, 36), "periodic", 4),
-                                           ((15, 6, 8), "periodic", 2)])
+                                           ((15, 6, 8), "periodic", 2), ((64, 16, 9), "periodic", 3), ((64, 32, 4), "dirichlet", 4)])
 def test_local_team_step_kernels_agree(lz, grid, bc, world):
     """Sharded runs: the recompute step (default for stencils; halo planes pushed after KB) and the
     two-pass step (halo planes stored by K3 itself) give the same tridiagonal matrix."""
