@@ -323,15 +323,21 @@ stencil_alpha_kernel(const StencilArgs a) {
 // its coupling coefficient is zero; the plane base is a uniform pointer bumped once per plane and the
 // per-thread offsets are 32-bit.  The general kernel above spends ~130 instructions per plane and
 // thread (address arithmetic, re-materialised constants, zeroing for predicated loads) and runs at
-// 66 % issue utilisation; this loop needs ~45.
+// 66 % issue utilisation; this loop needs ~60.  Measured at 512^3: 0.215 ms either way, and the same
+// for CTA tiles of 64x16, 128x8, 256x4 and 512x2 points (LZ_KA2_WX) - the kernel is bound by the
+// latency of the HBM stream at ~5.0 TB/s, not by issue slots or by the tile shape.
+#ifndef LZ_KA2_WX
+#define LZ_KA2_WX 1          // warps side by side in x: the CTA tile is (64 * WX) x (16 / WX) points
+#endif
 template <bool HAS_DIAG>
 __global__ void __launch_bounds__(kThreads, 4)
 stencil_alpha_fast_kernel(const StencilArgs a) {
+    constexpr int WX = LZ_KA2_WX;
     if (a.skip && *a.skip == 0) return;
     __shared__ double red[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double s = a.scale ? __ldg(a.scale) : 1.0;
-    constexpr int TX = 64, TY = 2 * kWarps;
+    constexpr int TX = 64 * WX, TY = 2 * kWarps / WX;
     const double cc = a.c, ox2 = 2.0 * a.ox, oy2 = 2.0 * a.oy, oz2 = 2.0 * a.oz;
     const uint32_t plane_b = (uint32_t)(a.plane * 8);
     double acc = 0.0;
@@ -341,8 +347,8 @@ stencil_alpha_fast_kernel(const StencilArgs a) {
         const int64_t t = item / a.tiles_x;
         const int ty = (int)(t % a.tiles_y);
         const int cz = (int)(t / a.tiles_y);
-        const int ix = tx * TX + 2 * lane;
-        const int iy0 = ty * TY + 2 * warp;
+        const int ix = tx * TX + 64 * (warp % WX) + 2 * lane;
+        const int iy0 = ty * TY + 2 * (warp / WX);
         int iyu = iy0 + 2;
         double oy2u = oy2;                                   // coupling of row iy0 + 1 to the row above the pair
         if (iyu >= a.ny) { if (a.periodic) iyu -= a.ny; else { iyu = iy0 + 1; oy2u = 0.0; } }
@@ -486,7 +492,12 @@ static int launch_stencil(lz_op* op, int mode, const double* x, const double* sc
     const void* fn = (vec == 2) ? pick_kernel<2>(has_y, has_z, st.diag != nullptr, mode)
                                 : pick_kernel<1>(has_y, has_z, st.diag != nullptr, mode);
     if (alpha_only) {
-        const bool whole_tiles = (st.nx % 64 == 0) && (st.ny % (2 * kWarps) == 0) && (st.nx * st.ny * 8 < (int64_t)1 << 32);
+        const bool whole_tiles = (st.nx % (64 * LZ_KA2_WX) == 0) && (st.ny % (2 * kWarps / LZ_KA2_WX) == 0) &&
+                                 (st.nx * st.ny * 8 < (int64_t)1 << 32);
+        if (whole_tiles) {
+            a.tiles_x = (int)(st.nx / (64 * LZ_KA2_WX));
+            a.tiles_y = (int)(st.ny / (2 * kWarps / LZ_KA2_WX));
+        }
         if (whole_tiles) fn = st.diag ? (const void*)stencil_alpha_fast_kernel<true> : (const void*)stencil_alpha_fast_kernel<false>;
         else fn = st.diag ? (const void*)stencil_alpha_kernel<true> : (const void*)stencil_alpha_kernel<false>;
     }
