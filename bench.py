@@ -271,7 +271,19 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the communicator comes up; stdout carries
+        # exactly one JSON line, so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     import lanczos_b200 as lz
 
     K, W = int(args.steps), max(3, int(args.warmup))
@@ -317,7 +329,8 @@ def main():
         torch.cuda.synchronize()
 
     def solve(n, v0, profile=False):
-        execute(n, v0=v0, profile=profile, **opts)
+        # a 1-step solve (--steps 1) cannot follow the reference loop, which needs n >= 2 (Lanczos.py:107,112)
+        execute(n, v0=v0, profile=profile, **dict(opts, ref_compat=opts["ref_compat"] and n >= 2))
         return solver.result
 
     # ---- warm-up: W untimed steps (also sizes the workspace arena and the allocator cache) ----
