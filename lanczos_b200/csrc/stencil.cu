@@ -329,8 +329,11 @@ stencil_alpha_kernel(const StencilArgs a) {
 #ifndef LZ_KA2_WX
 #define LZ_KA2_WX 1          // warps side by side in x: the CTA tile is (64 * WX) x (16 / WX) points
 #endif
+#ifndef LZ_KA2F_MINBLOCKS
+#define LZ_KA2F_MINBLOCKS 4
+#endif
 template <bool HAS_DIAG>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, LZ_KA2F_MINBLOCKS)
 stencil_alpha_fast_kernel(const StencilArgs a) {
     constexpr int WX = LZ_KA2_WX;
     if (a.skip && *a.skip == 0) return;
@@ -366,23 +369,20 @@ stencil_alpha_fast_kernel(const StencilArgs a) {
         const char* pl = reinterpret_cast<const char*>(a.x) + (int64_t)z0 * plane_b;
         const char* pd = HAS_DIAG ? reinterpret_cast<const char*>(a.diag) + (int64_t)z0 * plane_b : nullptr;
 
-        double2 c0 = ld_cached2(reinterpret_cast<const double*>(pl + o0));
-        double2 c1 = ld_cached2(reinterpret_cast<const double*>(pl + o1));
-        double2 cu = ld_cached2(reinterpret_cast<const double*>(pl + ou));
-        double cr0 = 0.0, cr1 = 0.0;
-        if (edge_r) {
-            cr0 = __ldg(reinterpret_cast<const double*>(pl + oe0));
-            cr1 = __ldg(reinterpret_cast<const double*>(pl + oe1));
-        }
-        auto step = [&](const char* pn, double ozn) {
-            const double2 n0 = ld_cached2(reinterpret_cast<const double*>(pn + o0));
-            const double2 n1 = ld_cached2(reinterpret_cast<const double*>(pn + o1));
-            const double2 nu = ld_cached2(reinterpret_cast<const double*>(pn + ou));
-            double nr0 = 0.0, nr1 = 0.0;
+        // three planes ride in registers: c = plane z (being reduced), n = plane z + 1 (its z-coupling;
+        // loaded one iteration ago), m = plane z + 2 (in flight while plane z is reduced)
+        double2 c0, c1, cu, n0, n1, nu, m0, m1, mu;
+        double cr0 = 0.0, cr1 = 0.0, nr0 = 0.0, nr1 = 0.0, mr0 = 0.0, mr1 = 0.0;
+        auto loadp = [&](const char* p, double2& q0, double2& q1, double2& qu, double& e0, double& e1) {
+            q0 = ld_cached2(reinterpret_cast<const double*>(p + o0));
+            q1 = ld_cached2(reinterpret_cast<const double*>(p + o1));
+            qu = ld_cached2(reinterpret_cast<const double*>(p + ou));
             if (edge_r) {
-                nr0 = __ldg(reinterpret_cast<const double*>(pn + oe0));
-                nr1 = __ldg(reinterpret_cast<const double*>(pn + oe1));
+                e0 = __ldg(reinterpret_cast<const double*>(p + oe0));
+                e1 = __ldg(reinterpret_cast<const double*>(p + oe1));
             }
+        };
+        auto reduce_plane = [&](double ozn) {
             double d00 = cc, d01 = cc, d10 = cc, d11 = cc;
             if (HAS_DIAG) {
                 const double2 e0 = ld_stream2(reinterpret_cast<const double*>(pd + o0));
@@ -401,17 +401,34 @@ stencil_alpha_fast_kernel(const StencilArgs a) {
             acc = fma(c0.y, t01, acc);
             acc = fma(c1.x, t10, acc);
             acc = fma(c1.y, t11, acc);
-            c0 = n0; c1 = n1; cu = nu; cr0 = nr0; cr1 = nr1;
         };
-#pragma unroll 2
-        for (int z = z0; z < z1 - 1; ++z) {
-            pl += plane_b;
-            step(pl, oz2);
+        auto rotate = [&]() {
+            c0 = n0; c1 = n1; cu = nu; cr0 = nr0; cr1 = nr1;
+            n0 = m0; n1 = m1; nu = mu; nr0 = mr0; nr1 = mr1;
+        };
+        // the plane above the chunk: the next chunk's first plane, the plane above the slab (periodic
+        // wrap / ghost plane), or absent (then a valid plane is read and its coupling is zero)
+        const char* pz1 = (z1 < a.nz) ? reinterpret_cast<const char*>(a.x) + (int64_t)z1 * plane_b
+                                      : reinterpret_cast<const char*>(a.zhi);
+        const double oz_last = pz1 ? oz2 : 0.0;
+        if (!pz1) pz1 = pl;
+        loadp(pl, c0, c1, cu, cr0, cr1);
+        loadp((z0 + 1 < z1) ? pl + plane_b : pz1, n0, n1, nu, nr0, nr1);
+        const char* pm = pl + 2 * (int64_t)plane_b;              // plane z + 2
+        int z = z0;
+#pragma unroll 3
+        for (; z < z1 - 2; ++z) {
+            loadp(pm, m0, m1, mu, mr0, mr1);
+            pm += plane_b;
+            reduce_plane(oz2);
+            rotate();
         }
-        // last plane of the chunk: its upper neighbour is the next chunk's first plane, the plane above
-        // the slab (periodic wrap / ghost plane), or absent
-        const char* pn = (z1 < a.nz) ? pl + plane_b : reinterpret_cast<const char*>(a.zhi);
-        step(pn ? pn : pl, pn ? oz2 : 0.0);
+        if (z < z1 - 1) {                                        // z == z1 - 2: plane z + 2 is the one above the chunk
+            loadp(pz1, m0, m1, mu, mr0, mr1);
+            reduce_plane(oz2);
+            rotate();
+        }
+        reduce_plane(oz_last);                                   // z == z1 - 1
     }
     const double tot = block_sum(acc * (s * s), red);
     if (threadIdx.x == 0 && a.partials) a.partials[blockIdx.x] = tot;
