@@ -371,7 +371,8 @@ stencil_alpha_fast_kernel(const StencilArgs a) {
 
         // three planes ride in registers: c = plane z (being reduced), n = plane z + 1 (its z-coupling;
         // loaded one iteration ago), m = plane z + 2 (in flight while plane z is reduced)
-        double2 c0, c1, cu, n0, n1, nu, m0, m1, mu;
+        const double2 zz = make_double2(0.0, 0.0);
+        double2 c0 = zz, c1 = zz, cu = zz, n0 = zz, n1 = zz, nu = zz, m0 = zz, m1 = zz, mu = zz;
         double cr0 = 0.0, cr1 = 0.0, nr0 = 0.0, nr1 = 0.0, mr0 = 0.0, mr1 = 0.0;
         auto loadp = [&](const char* p, double2& q0, double2& q1, double2& qu, double& e0, double& e1) {
             q0 = ld_cached2(reinterpret_cast<const double*>(p + o0));
