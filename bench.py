@@ -126,9 +126,9 @@ class ClockSampler:
 
 def ncu_traffic(kernel_name):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel_name` from the
-    committed `ncu --set full` summaries (profiles/r1b_ncu_traffic.json, then r1_ncu_traffic.json;
+    committed `ncu --set full` summaries (profiles/r1c_ncu_traffic.json, then r1b_, then r1_ncu_traffic.json;
     captured at the 512^3 config / the 50M-vertex graph)."""
-    for name in ("r1b_ncu_traffic.json", "r1_ncu_traffic.json"):
+    for name in ("r1c_ncu_traffic.json", "r1b_ncu_traffic.json", "r1_ncu_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 t = json.load(f)
@@ -444,7 +444,7 @@ def main():
     names = {"apply": "stencil_alpha_kernel (KA2)" if recompute else ("stencil_apply_dot_kernel" if is_stencil else "spmv_sell_dot_kernel"),
              "update": "stencil_apply_dot_kernel<MODE=2> (KB)" if recompute else "update_norm_kernel",
              "dots": "cgs_dots_kernel", "gs_update": "cgs_update_kernel", "gs_fused": "cgs_update_dots_kernel"}
-    ncu_names = {"apply": "stencil_alpha_kernel<0>" if recompute else names["apply"],
+    ncu_names = {"apply": "stencil_alpha_fast_kernel<0>" if recompute else names["apply"],
                  "update": "stencil_apply_dot_kernel<2, 1, 1, 0, 2>" if recompute else names["update"],
                  "dots": names["dots"], "gs_update": names["gs_update"], "gs_fused": names["gs_fused"]}
     roofline = None
