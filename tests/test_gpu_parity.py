@@ -358,6 +358,46 @@ def test_large_grid_invariants(lz):
     assert rel(np.diag(L2.H_eff), np.diag(L3.H_eff)) < 1e-11
 
 
+def test_full_size_config3_properties(lz):
+    """BASELINE config 3 at its full size (512^3 = 134 M unknowns): the recompute step (lean KA2 + KB)
+    and the two-pass step (K1 + K3) give the same alpha/beta, the basis is orthonormal and satisfies the
+    three-term recurrence, and alpha/beta are invariant under a cyclic shift of the start vector."""
+    import torch
+    n, grid = 8, (512, 512, 512)
+    op = lz.StencilOperator(grid, 6.0, -1.0)
+    M = op.M
+    g = torch.Generator(device="cuda").manual_seed(5)
+    v0 = torch.rand(M, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    T = {}
+    for kern in ("two_pass", "recompute"):
+        L = lz.Lanczos(op)
+        L.execute_Lanczos(n, v0=v0, reorth="selective", cgs_passes=2, step_kernel=kern)
+        assert L.result.step_kernel == kern
+        T[kern] = L.H_eff.copy()
+        if kern == "two_pass":
+            del L
+            torch.cuda.empty_cache()
+    assert rel(np.diag(T["recompute"]), np.diag(T["two_pass"])) < 1e-12
+    assert rel(np.diag(T["recompute"], 1), np.diag(T["two_pass"], 1)) < 1e-12
+    res = L.result
+    res.normalize_basis()
+    V = res.V_dev[:, :M]
+    G = V @ V.T
+    assert (G - torch.eye(n, dtype=torch.float64, device="cuda")).abs().max().item() < 1e-10
+    Tm = torch.from_numpy(L.H_eff).cuda()
+    dev = op.device_handle(res.ctx)
+    for j in range(1, n - 1):
+        r = dev.apply(V[j].contiguous()) - Tm[j, j] * V[j] - Tm[j, j + 1] * V[j + 1] - Tm[j, j - 1] * V[j - 1]
+        assert r.norm().item() < 1e-11
+    del V, G, res, L
+    torch.cuda.empty_cache()
+    v0s = torch.roll(v0.view(512, 512, 512), shifts=(1, 17, 64), dims=(0, 1, 2)).reshape(-1).contiguous()
+    Ls = lz.Lanczos(op)
+    Ls.execute_Lanczos(n, v0=v0s, reorth="none", keep_basis=False)
+    assert Ls.result.step_kernel == "recompute"
+    assert rel(np.diag(Ls.H_eff)[:6], np.diag(T["recompute"])[:6]) < 1e-11
+
+
 # ---- KF: the single-pass fused step (structured grids, nx % 64 == 0, ny % 8 == 0) ----------------
 
 @pytest.mark.parametrize("grid,n", [((20, 18, 16), 30), ((33, 7, 5), 60), ((64, 48, 6), 112), ((257,), 40)])

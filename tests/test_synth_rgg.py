@@ -304,3 +304,43 @@ def test_rgg_at_scale_properties():
     assert float(torch.dot(x, Lx)) > 0.0
     t, s = sell.nnz()
     assert t == indices.numel() and s / t < 1.6
+
+
+@gpu
+def test_full_size_config4_properties():
+    """BASELINE config 4 at its full size (~50 M vertices, ~7e8 entries, generated and converted on the
+    device): L is symmetric and annihilates constants, the SELL kernel agrees with the CSR kernel, and a
+    short Lanczos run satisfies the three-term recurrence."""
+    import lanczos_b200 as lz
+    from lanczos_b200 import synth
+    from lanczos_b200.engine import DeviceCSR
+    g = synth.RggGenerator((253, 253, 252), seed=0)
+    assert abs(g.M - 50.0e6) < 0.2e6
+    indptr, indices, data = g.rows(0, g.M)
+    assert abs(indices.numel() / g.M - 14.0) < 0.2
+    ctx = lz.Context.default()
+    dev = ctx.torch_device
+    sell = lz.DeviceOperator.from_device_csr(ctx, indptr, indices, data, fmt="sell")
+    gen = torch.Generator(device=dev).manual_seed(3)
+    x = torch.rand(g.M, dtype=torch.float64, device=dev, generator=gen) - 0.5
+    y = torch.rand(g.M, dtype=torch.float64, device=dev, generator=gen) - 0.5
+    Lx, Ly = sell.apply(x), sell.apply(y)
+    assert float(sell.apply(torch.ones_like(x)).abs().max()) == 0.0
+    xLx = float(torch.dot(x, Lx))
+    assert xLx > 0.0 and abs(float(torch.dot(y, Lx) - torch.dot(x, Ly))) < 1e-10 * xLx
+    csr = lz.DeviceOperator.from_device_csr(ctx, indptr, indices, data, fmt="csr")
+    assert float((Lx - csr.apply(x)).abs().max()) < 1e-12
+    t, s = sell.nnz()
+    assert t == indices.numel() and s / t < 1.05
+    del csr, Lx, Ly, y
+    S = lz.IrrLanczos(DeviceCSR(indptr, indices, data))
+    n = 6
+    S.execute_LanczosOld(n, v0=x, reorth="selective", cgs_passes=2)
+    res = S.result
+    res.normalize_basis()
+    V = res.V_dev[:, :g.M]
+    T = torch.from_numpy(S.H_eff).to(dev)
+    assert ((V @ V.T) - torch.eye(n, dtype=torch.float64, device=dev)).abs().max().item() < 1e-10
+    for j in range(1, n - 1):
+        r = sell.apply(V[j].contiguous()) - T[j, j] * V[j] - T[j, j + 1] * V[j + 1] - T[j, j - 1] * V[j - 1]
+        assert r.norm().item() < 1e-10
