@@ -435,6 +435,9 @@ stencil_alpha_fast_kernel(const StencilArgs a) {
     if (threadIdx.x == 0 && a.partials) a.partials[blockIdx.x] = tot;
 }
 
+// KB with its two HBM streams (own values of the plane above, v_{j-1}) fetched 2-4 planes ahead by
+// per-thread cp.async copies into thread-private shared-memory slots was measured too: 0.550 ms at best
+// (ring of 4, 5 CTAs/SM) against 0.558 ms - within noise of the plain kernel, which is what runs.
 // A lean KB in the style of the lean KA2 kernel (2 x-points on 2 rows per thread, boundaries folded into
 // coefficients, own rows two planes ahead and neighbour rows / v_{j-1} one plane ahead in registers) was
 // built and measured: bit-identical results, 128 registers with spills at 2 CTAs per SM, 0.573 ms at 512^3
