@@ -133,6 +133,7 @@ class LanczosBase:
                                           profile=profile, step_kernel=step_kernel, cgs_fused=cgs_fused)
         self._H_eff = self._result.tridiagonal()
         self._V_host = None
+        self._Y_dev = None
         self.H_eigs_have_been_found = False
         if verbose:
             print("+++ Lanczos executed successfully.")
@@ -145,6 +146,7 @@ class LanczosBase:
         print("+++ Converting eigenvectors from H_eff to H basis.")
         theta, S = np.linalg.eigh(self.H_eff)                   # small n x n problem: host LAPACK
         Y = self._result.ritz_vectors_dev(S)                    # K5 on the device
+        self._Y_dev = Y                                         # kept for the residual diagnostics
         Yh = np.ascontiguousarray(Y[:, :self.M].cpu().numpy().T)   # (M, n) like the reference
         if check_vectors:
             self.test_is_normalized(Yh, tol=0.001)
@@ -169,13 +171,33 @@ class LanczosBase:
 
     # ---- diagnostics (Lanczos.py:166-222), host-side printing over device products ------------
     def _residual_cosines(self):
-        H, eigvecs = self.H, self.H_eigvecs
+        """cos^2 of the angle between H x and x for every Ritz vector (Lanczos.py:171-176:
+        `Hx = H*x; Hx /= norm(Hx); dot(Hx, x)**2`), with the products on the device: the operator
+        kernel on the Ritz vectors K5 left in HBM, two deterministic dots per vector."""
+        import ctypes as C
+        from . import _capi
+        torch = engine._torch()
+        eigvecs = self.H_eigvecs                                  # runs get_H_eigs when needed
+        ctx = Context.default()
+        op = getattr(self, "_device_op", None)
+        if op is None or op.ctx is not ctx:
+            op = as_device_operator(self.H, ctx)
+            self._device_op = op
+        Y = getattr(self, "_Y_dev", None)
+        if Y is None or Y.shape[0] != self.n:
+            ld = engine.padded_ld(self.M)
+            Y = torch.zeros((self.n, ld), dtype=torch.float64, device=ctx.torch_device)
+            Y[:, :self.M] = torch.from_numpy(np.ascontiguousarray(eigvecs.T)).to(ctx.torch_device)
+        u = torch.empty(Y.shape[1], dtype=torch.float64, device=ctx.torch_device)
         inner_prod = np.zeros(self.n)
+        ux, uu = C.c_double(), C.c_double()
+        torch.cuda.current_stream(ctx.device).synchronize()
         for i in range(self.n):
-            x = eigvecs[:, i]
-            Hx = H * x
-            Hx = Hx / np.linalg.norm(Hx)
-            inner_prod[i] = np.dot(Hx, x) ** 2
+            xi = Y[i]
+            _capi.check(ctx.lib.lz_op_apply(op.handle, C.c_void_p(xi.data_ptr()), C.c_void_p(u.data_ptr())))
+            _capi.check(ctx.lib.lz_dot(ctx.handle, C.c_void_p(u.data_ptr()), C.c_void_p(xi.data_ptr()), self.M, C.byref(ux)))
+            _capi.check(ctx.lib.lz_dot(ctx.handle, C.c_void_p(u.data_ptr()), C.c_void_p(u.data_ptr()), self.M, C.byref(uu)))
+            inner_prod[i] = ux.value ** 2 / uu.value if uu.value > 0.0 else 0.0
         return inner_prod
 
     def compare_eigs(self):

@@ -358,6 +358,31 @@ def test_large_grid_invariants(lz):
     assert rel(np.diag(L2.H_eff), np.diag(L3.H_eff)) < 1e-11
 
 
+def test_print_good_eigs_matches_the_reference_formula(lz, capsys):
+    """The residual diagnostic of print_good_eigs (Lanczos.py:166-185, IrrLanczos.py:331-353) runs on the
+    device; its numbers equal the reference's host formula on the oracle's Ritz vectors."""
+    H, c, o, pot = orc.deuteron_hamiltonian(10)
+    n = 30
+    ref = orc.lanczos(H, n, seed=78, vectors=True)
+    want = np.array([np.dot((H @ x) / np.linalg.norm(H @ x), x) ** 2 for x in ref["Y"].T])
+    for op, cls in ((lz.StencilOperator((10, 10, 10), c, o, diag=pot), lz.Lanczos), (H, lz.Lanczos), (sp_csc(H), lz.IrrLanczos)):
+        L = cls(op)
+        (L.execute_Lanczos if cls is lz.Lanczos else L.execute_LanczosOld)(n, seed=78)
+        got = L.print_good_eigs(tol=0.01, print_nr=5)
+        out = capsys.readouterr().out
+        assert "EIGENVALUE AND EIGVENVECTOR COMPARISON" in out
+        assert got.shape == (n,)
+        conv = np.abs(1 - want) < 1e-6                       # converged pairs: cos^2 = 1 to round-off
+        assert conv.sum() >= 3
+        assert np.max(np.abs(got[conv] - want[conv])) < 1e-10
+        assert np.max(np.abs(got - want)) < 1e-6             # unconverged ones: same value up to the Ritz vectors' accuracy
+
+
+def sp_csc(H):
+    import scipy.sparse as sp
+    return sp.csc_matrix(H)
+
+
 def test_full_size_config3_properties(lz):
     """BASELINE config 3 at its full size (512^3 = 134 M unknowns): the recompute step (lean KA2 + KB)
     and the two-pass step (K1 + K3) give the same alpha/beta, the basis is orthonormal and satisfies the
