@@ -10,6 +10,7 @@
 //
 // Rows of the basis may be stored un-normalised (lazy 1/beta); the scale factors are
 // folded into the coefficients by the scalar kernels in lanczos.cu, never into the data.
+#include <stdlib.h>
 #include "internal.h"
 
 namespace lz {
@@ -258,7 +259,150 @@ cgs_update_dots_kernel(const double* __restrict__ V, int64_t ldv, int k, double*
     }
 }
 
+// ---- K4c with TMA: the same computation, the tile staged by bulk asynchronous copies --------------
+// Every basis row contributes one contiguous segment of TC doubles to a tile: thread r issues ONE
+// cp.async.bulk (1-2 KB, global -> shared, completion counted in bytes on an mbarrier) for row r, thread 0
+// arms the barrier with the tile's byte count.  Two stages: the copies of the CTA's next tile are in
+// flight while the current one is reduced, so a single CTA keeps a whole tile (60-120 KB) of HBM reads
+// in flight without spending registers or issue slots on them (the cp.async form above issues
+// (k + 1) * TC / 2 sixteen-byte copies per tile and overlaps only across CTAs).
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// bounded wait: a lost completion traps instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        uint32_t done;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+template <int TC, int RMAX>
+__global__ void __launch_bounds__(TC)
+cgs_update_dots_tma_kernel(const double* __restrict__ V, int64_t ldv, int k, double* target,
+                           const double* __restrict__ coef, const double* __restrict__ cself_p, int64_t M,
+                           int64_t ntiles, double* __restrict__ part, const int* __restrict__ flag) {
+    if (flag && *flag == 0) return;
+    extern __shared__ __align__(128) double sm[];
+    const size_t stage_d = (size_t)(k + 1) * TC;
+    double* vp = sm + 2 * stage_d;           // [TC]
+    double* sh = vp + TC;                    // [k]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + ((k + 1) & ~1) + 2);   // 2 mbarriers, 16-byte aligned
+    constexpr int NW = TC / 32;
+    constexpr int CPL = TC / 32;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t bar0 = smem_addr(bars), bar1 = smem_addr(bars + 1);
+    if (t == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int r = t; r < k; r += TC) sh[r] = coef[r];
+    const double cself = __ldg(cself_p);
+    double acc[RMAX];
+#pragma unroll
+    for (int q = 0; q < RMAX; ++q) acc[q] = 0.0;
+    __syncthreads();
+
+    // thread r copies row r's segment of `tile` into stage `s`; thread 0 arms the barrier
+    auto issue = [&](int64_t tile, int s) {
+        const int64_t c0 = tile * TC;
+        const int64_t cend = min(c0 + TC, ldv);              // rows are ldv doubles long (ldv % 64 == 0)
+        const uint32_t row_bytes = (uint32_t)(cend - c0) * 8u;
+        const uint32_t bar = s ? bar1 : bar0;
+        if (t == 0) mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)(k + 1));
+        for (int r = t; r <= k; r += TC) {
+            const double* src = (r < k ? V + (int64_t)r * ldv : target) + c0;
+            bulk_g2s(smem_addr(sm + (size_t)s * stage_d + (size_t)r * TC), src, row_bytes, bar);
+        }
+    };
+    int64_t tile = blockIdx.x;
+    if (tile < ntiles) issue(tile, 0);
+    for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+        const int s = it & 1;
+        const int64_t c0 = tile * TC;
+        const int64_t next = tile + gridDim.x;
+        if (next < ntiles) {
+            // stage s^1 was last read (generic proxy) before the barrier that ended the previous iteration
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(next, s ^ 1);
+        }
+        mbar_wait(s ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
+        const double* S = sm + (size_t)s * stage_d;
+        {
+            double a = 0.0;
+            if (c0 + t < M) {
+                a = cself * S[(size_t)k * TC + t];
+                for (int r = 0; r < k; ++r) a = fma(-sh[r], S[(size_t)r * TC + t], a);
+                st_stream1(target + c0 + t, a);
+            }
+            vp[t] = a;
+        }
+        __syncthreads();
+        double vl[CPL];
+        bool on[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) { vl[c] = vp[lane + 32 * c]; on[c] = c0 + lane + 32 * c < M; }
+#pragma unroll
+        for (int q = 0; q < RMAX; ++q) {
+            const int r = warp + q * NW;
+            if (r < k) {
+                const double* row = S + (size_t)r * TC + lane;
+                double a = acc[q];
+#pragma unroll
+                for (int c = 0; c < CPL; ++c)
+                    if (on[c]) a = fma(row[32 * c], vl[c], a);
+                acc[q] = a;
+            }
+        }
+        __syncthreads();                     // stage s and vp are free again
+    }
+#pragma unroll
+    for (int q = 0; q < RMAX; ++q) {
+        const int r = warp + q * NW;
+        const double tot = warp_sum(acc[q]);
+        if (lane == 0 && r < k) part[(int64_t)r * gridDim.x + blockIdx.x] = tot;
+    }
+}
+
 struct UpdDotsCfg { int tc, rmax; size_t smem; };
+// TMA form: two stages of (k + 1) * TC doubles in one CTA; TC = 256 up to 48 rows, else 128
+static bool update_dots_tma_config(int k, UpdDotsCfg* cfg) {
+    const size_t cap = 200 * 1024;
+    for (int tc : {256, 128}) {
+        if (k + 1 > tc) continue;                                  // one bulk copy per thread
+        if (tc == 256 && k > 48) continue;
+        const size_t bytes = (2 * (size_t)(k + 1) * tc + tc + k + 8) * 8;
+        const int nw = tc / 32;
+        const int need = (k + nw - 1) / nw;
+        if (bytes <= cap && need <= 26) {
+            cfg->tc = tc;
+            cfg->rmax = need <= 8 ? 8 : (need <= 16 ? 16 : 26);
+            cfg->smem = bytes;
+            return true;
+        }
+    }
+    return false;
+}
+static int update_dots_use_tma() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LZ_K4C_TMA");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
 static bool update_dots_config(int k, UpdDotsCfg* cfg) {
     // TC = 256 while two CTAs of (k + 2) * 2 KB fit an SM, else TC = 128; rows per warp <= RMAX
     const size_t cap = 100 * 1024;
@@ -289,9 +433,18 @@ int launch_cgs_update_dots(lz_ctx* ctx, const double* V, int64_t ldv, int k, dou
     LZ_REQUIRE(cgs_update_dots_supported(V, ldv, k, target), "fused Gram-Schmidt update+dots: unsupported shape (k = %d)", k);
     update_dots_config(k, &c);
     const void* fn = nullptr;
+    UpdDotsCfg ct;
+    const bool tma = update_dots_use_tma() && (ldv % 64 == 0) && update_dots_tma_config(k, &ct);
+    if (tma) {
+        c = ct;
+#define LZ_UDT(TCV, RM) if (c.tc == TCV && c.rmax == RM) fn = (const void*)cgs_update_dots_tma_kernel<TCV, RM>
+        LZ_UDT(256, 8); LZ_UDT(256, 16); LZ_UDT(256, 26); LZ_UDT(128, 8); LZ_UDT(128, 16); LZ_UDT(128, 26);
+#undef LZ_UDT
+    } else {
 #define LZ_UD(TCV, RM) if (c.tc == TCV && c.rmax == RM) fn = (const void*)cgs_update_dots_kernel<TCV, RM>
-    LZ_UD(256, 8); LZ_UD(256, 16); LZ_UD(256, 26); LZ_UD(128, 8); LZ_UD(128, 16); LZ_UD(128, 26);
+        LZ_UD(256, 8); LZ_UD(256, 16); LZ_UD(256, 26); LZ_UD(128, 8); LZ_UD(128, 16); LZ_UD(128, 26);
 #undef LZ_UD
+    }
     LZ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     int per_sm = 0;
     LZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, c.tc, c.smem));
