@@ -10,6 +10,7 @@
 //
 // Rows of the basis may be stored un-normalised (lazy 1/beta); the scale factors are
 // folded into the coefficients by the scalar kernels in lanczos.cu, never into the data.
+#include <cuda.h>
 #include <stdlib.h>
 #include "internal.h"
 
@@ -202,7 +203,7 @@ cgs_update_dots_kernel(const double* __restrict__ V, int64_t ldv, int k, double*
                        const double* __restrict__ coef, const double* __restrict__ cself_p, int64_t M,
                        int64_t ntiles, double* __restrict__ part, const int* __restrict__ flag) {
     if (flag && *flag == 0) return;
-    extern __shared__ __align__(16) double sm[];
+    extern __shared__ __align__(128) double sm[];
     double* S = sm;                          // [k + 1][TC]: rows 0..k-1 of the basis, row k = v
     double* vp = sm + (size_t)(k + 1) * TC;  // [TC]: v' of the tile
     double* sh = vp + TC;                    // [k]: h1
@@ -259,13 +260,15 @@ cgs_update_dots_kernel(const double* __restrict__ V, int64_t ldv, int k, double*
     }
 }
 
-// ---- K4c with TMA: the same computation, the tile staged by bulk asynchronous copies --------------
-// Every basis row contributes one contiguous segment of TC doubles to a tile: thread r issues ONE
-// cp.async.bulk (1-2 KB, global -> shared, completion counted in bytes on an mbarrier) for row r, thread 0
-// arms the barrier with the tile's byte count.  Two stages: the copies of the CTA's next tile are in
-// flight while the current one is reduced, so a single CTA keeps a whole tile (60-120 KB) of HBM reads
-// in flight without spending registers or issue slots on them (the cp.async form above issues
-// (k + 1) * TC / 2 sixteen-byte copies per tile and overlaps only across CTAs).
+// ---- K4c with TMA: the same computation, the tile fetched by ONE tensor copy ----------------------
+// The k basis rows and the target (row k of the same array) are a 2-D tensor (M columns x (k + 1) rows,
+// row stride ldv); a tile is the box TC x (k + 1).  One elected thread arms an mbarrier with the box's
+// byte count and issues a single cp.async.bulk.tensor.2d; the TMA unit walks the rows, zero-fills the
+// columns past M and lands the box densely in shared memory.  Two stages: the box of the CTA's next
+// tile is in flight while the current one is reduced, so one CTA keeps 60-120 KB of HBM reads in flight
+// with no registers or issue slots spent on them.  (Per-row 1-D bulk copies, one per thread, were
+// measured first: 60 copies of 1 KB per tile made the fused kernel 1.7x slower than the cp.async
+// form - the per-copy cost of small bulk transfers dominates.)
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
@@ -273,9 +276,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
 }
 // bounded wait: a lost completion traps instead of hanging the device
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -290,19 +293,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 template <int TC, int RMAX>
 __global__ void __launch_bounds__(TC)
-cgs_update_dots_tma_kernel(const double* __restrict__ V, int64_t ldv, int k, double* target,
+cgs_update_dots_tma_kernel(const __grid_constant__ CUtensorMap tmap, int k, double* target,
                            const double* __restrict__ coef, const double* __restrict__ cself_p, int64_t M,
                            int64_t ntiles, double* __restrict__ part, const int* __restrict__ flag) {
     if (flag && *flag == 0) return;
     extern __shared__ __align__(128) double sm[];
-    const size_t stage_d = (size_t)(k + 1) * TC;
-    double* vp = sm + 2 * stage_d;           // [TC]
-    double* sh = vp + TC;                    // [k]
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + ((k + 1) & ~1) + 2);   // 2 mbarriers, 16-byte aligned
+    const size_t stage_d = (size_t)(k + 1) * TC;     // TC * 8 is a multiple of 128 B: every stage is 128-byte aligned
+    double* vp = sm + 2 * stage_d;                   // [TC]
+    double* sh = vp + TC;                            // [k]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + ((k + 1) & ~1) + 2);
     constexpr int NW = TC / 32;
     constexpr int CPL = TC / 32;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t bar0 = smem_addr(bars), bar1 = smem_addr(bars + 1);
+    const uint32_t box_bytes = (uint32_t)stage_d * 8u;
     if (t == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar1, 1);
@@ -315,45 +319,34 @@ cgs_update_dots_tma_kernel(const double* __restrict__ V, int64_t ldv, int k, dou
     for (int q = 0; q < RMAX; ++q) acc[q] = 0.0;
     __syncthreads();
 
-    // thread r copies row r's segment of `tile` into stage `s`; thread 0 arms the barrier
-    auto issue = [&](int64_t tile, int s) {
-        const int64_t c0 = tile * TC;
-        const int64_t cend = min(c0 + TC, ldv);              // rows are ldv doubles long (ldv % 64 == 0)
-        const uint32_t row_bytes = (uint32_t)(cend - c0) * 8u;
-        const uint32_t bar = s ? bar1 : bar0;
-        if (t == 0) mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)(k + 1));
-        for (int r = t; r <= k; r += TC) {
-            const double* src = (r < k ? V + (int64_t)r * ldv : target) + c0;
-            bulk_g2s(smem_addr(sm + (size_t)s * stage_d + (size_t)r * TC), src, row_bytes, bar);
-        }
-    };
     int64_t tile = blockIdx.x;
-    if (tile < ntiles) issue(tile, 0);
+    if (t == 0 && tile < ntiles) {
+        mbar_arrive_expect_tx(bar0, box_bytes);
+        tma_load_2d(smem_addr(sm), &tmap, (int)(tile * TC), 0, bar0);
+    }
     for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
         const int s = it & 1;
         const int64_t c0 = tile * TC;
         const int64_t next = tile + gridDim.x;
-        if (next < ntiles) {
+        if (t == 0 && next < ntiles) {
             // stage s^1 was last read (generic proxy) before the barrier that ended the previous iteration
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(next, s ^ 1);
+            const uint32_t bn = s ? bar0 : bar1;
+            mbar_arrive_expect_tx(bn, box_bytes);
+            tma_load_2d(smem_addr(sm + (size_t)(s ^ 1) * stage_d), &tmap, (int)(next * TC), 0, bn);
         }
         mbar_wait(s ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
         const double* S = sm + (size_t)s * stage_d;
-        {
-            double a = 0.0;
-            if (c0 + t < M) {
-                a = cself * S[(size_t)k * TC + t];
-                for (int r = 0; r < k; ++r) a = fma(-sh[r], S[(size_t)r * TC + t], a);
-                st_stream1(target + c0 + t, a);
-            }
+        {   // columns past M arrive as zeros: v' = 0 there and nothing is stored
+            double a = cself * S[(size_t)k * TC + t];
+            for (int r = 0; r < k; ++r) a = fma(-sh[r], S[(size_t)r * TC + t], a);
             vp[t] = a;
+            if (c0 + t < M) st_stream1(target + c0 + t, a);
         }
         __syncthreads();
         double vl[CPL];
-        bool on[CPL];
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) { vl[c] = vp[lane + 32 * c]; on[c] = c0 + lane + 32 * c < M; }
+        for (int c = 0; c < CPL; ++c) vl[c] = vp[lane + 32 * c];
 #pragma unroll
         for (int q = 0; q < RMAX; ++q) {
             const int r = warp + q * NW;
@@ -361,8 +354,7 @@ cgs_update_dots_tma_kernel(const double* __restrict__ V, int64_t ldv, int k, dou
                 const double* row = S + (size_t)r * TC + lane;
                 double a = acc[q];
 #pragma unroll
-                for (int c = 0; c < CPL; ++c)
-                    if (on[c]) a = fma(row[32 * c], vl[c], a);
+                for (int c = 0; c < CPL; ++c) a = fma(row[32 * c], vl[c], a);
                 acc[q] = a;
             }
         }
@@ -376,12 +368,30 @@ cgs_update_dots_tma_kernel(const double* __restrict__ V, int64_t ldv, int k, dou
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
 struct UpdDotsCfg { int tc, rmax; size_t smem; };
 // TMA form: two stages of (k + 1) * TC doubles in one CTA; TC = 256 up to 48 rows, else 128
 static bool update_dots_tma_config(int k, UpdDotsCfg* cfg) {
     const size_t cap = 200 * 1024;
     for (int tc : {256, 128}) {
-        if (k + 1 > tc) continue;                                  // one bulk copy per thread
+        if (k + 1 > 256) continue;                                 // box rows
         if (tc == 256 && k > 48) continue;
         const size_t bytes = (2 * (size_t)(k + 1) * tc + tc + k + 8) * 8;
         const int nw = tc / 32;
@@ -434,7 +444,19 @@ int launch_cgs_update_dots(lz_ctx* ctx, const double* V, int64_t ldv, int k, dou
     update_dots_config(k, &c);
     const void* fn = nullptr;
     UpdDotsCfg ct;
-    const bool tma = update_dots_use_tma() && (ldv % 64 == 0) && update_dots_tma_config(k, &ct);
+    // TMA form: the target must be row k of the same array (it is, in the Lanczos loop)
+    bool tma = update_dots_use_tma() && target == V + (int64_t)k * ldv && M <= 0x7fffffff && encode_tiled_fn() &&
+               update_dots_tma_config(k, &ct);
+    CUtensorMap tmap;
+    if (tma) {
+        const cuuint64_t gdim[2] = {(cuuint64_t)M, (cuuint64_t)(k + 1)};
+        const cuuint64_t gstride[1] = {(cuuint64_t)ldv * 8};
+        const cuuint32_t box[2] = {(cuuint32_t)ct.tc, (cuuint32_t)(k + 1)};
+        const cuuint32_t estr[2] = {1, 1};
+        tma = encode_tiled_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(V), gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
     if (tma) {
         c = ct;
 #define LZ_UDT(TCV, RM) if (c.tc == TCV && c.rmax == RM) fn = (const void*)cgs_update_dots_tma_kernel<TCV, RM>
@@ -452,9 +474,15 @@ int launch_cgs_update_dots(lz_ctx* ctx, const double* V, int64_t ldv, int k, dou
     const int64_t ntiles = (M + c.tc - 1) / c.tc;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, std::min<int64_t>((int64_t)ctx->sms * per_sm, kMaxPartials)));
     int kk = k;
-    void* args[] = {(void*)&V, (void*)&ldv, (void*)&kk, (void*)&target, (void*)&coef_dev, (void*)&cself_dev,
-                    (void*)&M, (void*)&ntiles, (void*)&part, (void*)&flag_dev};
-    LZ_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(c.tc), args, c.smem, ctx->stream));
+    if (tma) {
+        void* targs[] = {(void*)&tmap, (void*)&kk, (void*)&target, (void*)&coef_dev, (void*)&cself_dev,
+                         (void*)&M, (void*)&ntiles, (void*)&part, (void*)&flag_dev};
+        LZ_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(c.tc), targs, c.smem, ctx->stream));
+    } else {
+        void* args[] = {(void*)&V, (void*)&ldv, (void*)&kk, (void*)&target, (void*)&coef_dev, (void*)&cself_dev,
+                        (void*)&M, (void*)&ntiles, (void*)&part, (void*)&flag_dev};
+        LZ_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(c.tc), args, c.smem, ctx->stream));
+    }
     if (ncg_out) *ncg_out = grid;
     return LZ_OK;
 }
