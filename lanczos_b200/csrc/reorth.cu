@@ -408,8 +408,8 @@ static bool update_dots_tma_config(int k, UpdDotsCfg* cfg) {
 static int update_dots_use_tma() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("LZ_K4C_TMA");
-        v = e ? atoi(e) : 0;
+        const char* e = getenv("LZ_K4C_TMA");      // 0: force the cp.async form (comparison runs)
+        v = e ? atoi(e) : 1;
     }
     return v;
 }
