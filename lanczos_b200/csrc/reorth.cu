@@ -10,9 +10,9 @@
 //
 // Rows of the basis may be stored un-normalised (lazy 1/beta); the scale factors are
 // folded into the coefficients by the scalar kernels in lanczos.cu, never into the data.
-#include <cuda.h>
 #include <stdlib.h>
 #include "internal.h"
+#include "tma.cuh"
 
 namespace lz {
 
@@ -269,28 +269,6 @@ cgs_update_dots_kernel(const double* __restrict__ V, int64_t ldv, int k, double*
 // with no registers or issue slots spent on them.  (Per-row 1-D bulk copies, one per thread, were
 // measured first: 60 copies of 1 KB per tile made the fused kernel 1.7x slower than the cp.async
 // form - the per-copy cost of small bulk transfers dominates.)
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
-}
-// bounded wait: a lost completion traps instead of hanging the device
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
-        uint32_t done;
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-    }
-    __trap();
-}
-
 template <int TC, int RMAX>
 __global__ void __launch_bounds__(TC)
 cgs_update_dots_tma_kernel(const __grid_constant__ CUtensorMap tmap, int k, double* target,
@@ -366,24 +344,6 @@ cgs_update_dots_tma_kernel(const __grid_constant__ CUtensorMap tmap, int k, doub
         const double tot = warp_sum(acc[q]);
         if (lane == 0 && r < k) part[(int64_t)r * gridDim.x + blockIdx.x] = tot;
     }
-}
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
 }
 
 struct UpdDotsCfg { int tc, rmax; size_t smem; };
