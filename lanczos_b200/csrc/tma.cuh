@@ -29,6 +29,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return;
+        if (spin > 4) __nanosleep(spin < 64 ? 20 : 200);     // back off: pollers share issue slots with working warps
     }
     __trap();
 }
