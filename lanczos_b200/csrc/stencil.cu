@@ -20,9 +20,7 @@
 // the new z+1 values and two for the y-1 / y+1 rows (L1 hits except on the two tile-edge
 // rows); x neighbours travel by warp shuffle, only the two edge lanes load them.  HBM
 // traffic is the compulsory 8 B read + 8 B write per point (+ 2/zc for the chunk halo).
-#include <stdlib.h>
 #include "internal.h"
-#include "tma.cuh"
 
 namespace lz {
 
@@ -446,205 +444,14 @@ stencil_alpha_fast_kernel(const StencilArgs a) {
 // against 0.558 ms for MODE 2 of the general kernel at 4 CTAs per SM - the staging registers cost the
 // occupancy they were meant to replace, so KB stays with the general kernel.
 
-// KB-TMA: KB with its tiles staged by the TMA unit (3-D, all three couplings, nx % 64 == 0, ny % 8 == 0,
-// no potential array).  Eight consumer warps (thread <-> 2 x-points, warp <-> row, CTA tile 64 x 8,
-// marching in z like the general kernel) and one producer warp:
-//   * every plane tile of x (and of v_{j-1}) is fetched by ONE cp.async.bulk.tensor issued by the
-//     producer, up to kTmaRing - 2 planes ahead - and across tile boundaries - into a ring of
-//     shared-memory slots; completion is a byte count on the slot's "full" mbarrier;
-//   * a consumer warp reads the y-neighbour rows of the plane it computes from the slot (no dependence
-//     on L1 hits or on other warps: all of it was written by the TMA unit), keeps the z-neighbours in
-//     registers as before, gets x-neighbours by shuffle, and fetches the row / column just outside the
-//     tile with plain loads issued one plane ahead;
-//   * when a warp is done with a slot it arrives on the slot's "empty" mbarrier; the producer refills
-//     a slot once all eight warps have released it.  There is no CTA-wide barrier in the loop, so the
-//     warps drift apart freely within the depth of the ring.
-// The bytes in flight per SM are ring slots, not registers.
-#ifndef LZ_KBT_RING
-#define LZ_KBT_RING 6
-#endif
-#ifndef LZ_KBT_MINBLOCKS
-#define LZ_KBT_MINBLOCKS 3
-#endif
-constexpr int kTmaRing = LZ_KBT_RING;
-constexpr int kTmaTX = 64, kTmaTY = 8;
-constexpr int kTmaPlaneD = kTmaTX * kTmaTY;      // doubles per staged plane tile (4 KB)
-constexpr int kTmaThreads = kThreads + 32;       // 8 consumer warps + the producer warp
-
-template <bool HAS_B>
-__global__ void __launch_bounds__(kTmaThreads, LZ_KBT_MINBLOCKS)
-stencil_update_tma_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapb,
-                          const __grid_constant__ CUtensorMap maphi, const StencilArgs a, const int hi_kind) {
-    extern __shared__ __align__(128) unsigned char tma_smem[];
-    constexpr int R = kTmaRing;
-    double* const xs = reinterpret_cast<double*>(tma_smem);                       // [R][TY][TX]
-    double* const bs = xs + R * kTmaPlaneD;                                       // [R][TY][TX] (HAS_B)
-    unsigned long long* const full = reinterpret_cast<unsigned long long*>(bs + (HAS_B ? R * kTmaPlaneD : 0));
-    unsigned long long* const empty = full + R;
-    __shared__ double red[kWarps];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-#pragma unroll
-        for (int q = 0; q < R; ++q) { mbar_init(smem_addr(full + q), 1); mbar_init(smem_addr(empty + q), kWarps); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    uint32_t g0 = 0;                       // planes staged before this item: slot = g % R, use number = g / R
-    double acc = 0.0;
-
-    if (warp == kWarps) {
-        // ---------------- producer warp ----------------
-        if (lane == 0) {
-            for (int64_t item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-                const int tx = (int)(item % a.tiles_x);
-                const int64_t t = item / a.tiles_x;
-                const int ty = (int)(t % a.tiles_y);
-                const int cz = (int)(t / a.tiles_y);
-                const int x0 = tx * kTmaTX, y0 = ty * kTmaTY;
-                const int z0 = cz * a.zc;
-                const int z1 = min(z0 + a.zc, a.nz);
-                const int zc = z1 - z0;
-                const int top = (z1 < a.nz) ? 3 : hi_kind;  // 3: regular plane z1, 1: plane 0 (wrap), 2: ghost map, 0: none
-                const int nplanes = zc + (top ? 1 : 0);
-                for (int q = 0; q < nplanes; ++q) {
-                    const uint32_t g = g0 + (uint32_t)q;
-                    const int slot = (int)(g % R);
-                    if (g >= (uint32_t)R) mbar_wait(smem_addr(empty + slot), ((g / R) - 1u) & 1u);   // all 8 warps released it
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    const uint32_t bar = smem_addr(full + slot);
-                    const bool carries_b = HAS_B && q < zc;
-                    mbar_arrive_expect_tx(bar, (uint32_t)(kTmaPlaneD * 8) * (carries_b ? 2u : 1u));
-                    const uint32_t dx = smem_addr(xs + (size_t)slot * kTmaPlaneD);
-                    if (q < zc || top == 3) tma_load_3d(dx, &mapx, x0, y0, z0 + q, bar);
-                    else if (top == 1) tma_load_3d(dx, &mapx, x0, y0, 0, bar);
-                    else tma_load_2d(dx, &maphi, x0, y0, bar);
-                    if (carries_b) tma_load_3d(smem_addr(bs + (size_t)slot * kTmaPlaneD), &mapb, x0, y0, z0 + q, bar);
-                }
-                g0 += (uint32_t)nplanes;
-            }
-        }
-    } else {
-        // ---------------- consumer warps ----------------
-        const double s = a.scale ? __ldg(a.scale) : 1.0;
-        const double fa = (a.ca ? __ldg(a.ca) : 1.0) * (a.sa ? __ldg(a.sa) : 1.0);
-        const double fb = HAS_B ? (a.cb ? __ldg(a.cb) : 1.0) * (a.sb ? __ldg(a.sb) : 1.0) : 0.0;
-        for (int64_t item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-            const int tx = (int)(item % a.tiles_x);
-            const int64_t t = item / a.tiles_x;
-            const int ty = (int)(t % a.tiles_y);
-            const int cz = (int)(t / a.tiles_y);
-            const int x0 = tx * kTmaTX, y0 = ty * kTmaTY;
-            const int ix = x0 + 2 * lane, iy = y0 + warp;
-            const int z0 = cz * a.zc;
-            const int z1 = min(z0 + a.zc, a.nz);
-            const int zc = z1 - z0;
-            const int top = (z1 < a.nz) ? 3 : hi_kind;
-            const int nplanes = zc + (top ? 1 : 0);
-            // neighbours outside the tile: the row below warp 0 / above warp 7, the column left of lane 0 / right of lane 31
-            const bool outer = (warp == 0) || (warp == kTmaTY - 1);
-            int iyo = (warp == 0) ? iy - 1 : iy + 1;
-            double oy_m = a.oy, oy_p = a.oy, ox_l = a.ox, ox_r = a.ox;
-            if (outer) {
-                if (iyo < 0) { if (a.periodic) iyo += a.ny; else { iyo = iy; oy_m = 0.0; } }
-                if (iyo >= a.ny) { if (a.periodic) iyo -= a.ny; else { iyo = iy; oy_p = 0.0; } }
-            }
-            const bool edge = (lane == 0) || (lane == 31);
-            int ixe = (lane == 0) ? ix - 1 : ix + 2;
-            if (edge) {
-                if (ixe < 0) { if (a.periodic) ixe += a.nx; else { ixe = ix; ox_l = 0.0; } }
-                if (ixe >= a.nx) { if (a.periodic) ixe -= a.nx; else { ixe = ix; ox_r = 0.0; } }
-            }
-            const int64_t off_c = (int64_t)iy * a.nx + ix;
-            const int64_t off_o = (int64_t)iyo * a.nx + ix;
-            const int64_t off_e = (int64_t)iy * a.nx + ixe;
-            // registers: z-1 / z / z+1 of the thread's own two points; outer row and edge column of the
-            // current and of the next plane
-            const double* pc = a.x + (int64_t)z0 * a.plane;
-            double2 vm = make_double2(0.0, 0.0);
-            {
-                const double* pm = (z0 > 0) ? pc - a.plane : a.zlo;
-                if (pm) vm = ld_cached2(pm + off_c);
-            }
-            double2 ho_c = make_double2(0.0, 0.0), ho_n = ho_c;
-            double e_c = 0.0, e_n = 0.0;
-            if (outer) ho_c = ld_cached2(pc + off_o);
-            if (edge) e_c = __ldg(pc + off_e);
-            mbar_wait(smem_addr(full + g0 % R), (g0 / R) & 1u);
-            double2 vc = *reinterpret_cast<const double2*>(xs + (size_t)(g0 % R) * kTmaPlaneD + warp * kTmaTX + 2 * lane);
-
-            double* po = a.y + (int64_t)z0 * a.plane + off_c;
-#pragma unroll 1
-            for (int q = 0; q < zc; ++q) {
-                const int z = z0 + q;
-                const uint32_t gq = g0 + (uint32_t)q;
-                const int slot_c = (int)(gq % R), slot_n = (int)((gq + 1) % R);
-                if (q + 1 < zc) {              // next plane's outside neighbours: issued now, used in the next iteration
-                    if (outer) ho_n = ld_cached2(pc + a.plane + off_o);
-                    if (edge) e_n = __ldg(pc + a.plane + off_e);
-                }
-                double2 vp = make_double2(0.0, 0.0);
-                if (q + 1 < nplanes) {
-                    mbar_wait(smem_addr(full + slot_n), ((gq + 1) / R) & 1u);
-                    vp = *reinterpret_cast<const double2*>(xs + (size_t)slot_n * kTmaPlaneD + warp * kTmaTX + 2 * lane);
-                }
-                const double* xc = xs + (size_t)slot_c * kTmaPlaneD + warp * kTmaTX + 2 * lane;
-                double2 ym = ho_c, yp = ho_c;
-                if (warp > 0) ym = *reinterpret_cast<const double2*>(xc - kTmaTX);
-                if (warp < kTmaTY - 1) yp = *reinterpret_cast<const double2*>(xc + kTmaTX);
-                double2 bv = make_double2(0.0, 0.0);
-                if (HAS_B) bv = *reinterpret_cast<const double2*>(bs + (size_t)slot_c * kTmaPlaneD + warp * kTmaTX + 2 * lane);
-                double left = __shfl_up_sync(0xffffffffu, vc.y, 1);
-                double right = __shfl_down_sync(0xffffffffu, vc.x, 1);
-                if (lane == 0) left = e_c;
-                if (lane == 31) right = e_c;
-                double r0 = a.oz * vm.x, r1 = a.oz * vm.y;
-                r0 = fma(oy_m, ym.x, r0);  r1 = fma(oy_m, ym.y, r1);
-                r0 = fma(ox_l, left, r0);  r1 = fma(a.ox, vc.x, r1);
-                r0 = fma(a.c, vc.x, r0);   r1 = fma(a.c, vc.y, r1);
-                r0 = fma(a.ox, vc.y, r0);  r1 = fma(ox_r, right, r1);
-                r0 = fma(oy_p, yp.x, r0);  r1 = fma(oy_p, yp.y, r1);
-                r0 = fma(a.oz, vp.x, r0);  r1 = fma(a.oz, vp.y, r1);
-                r0 *= s; r1 *= s;
-                r0 = fma(-fa, vc.x, r0);   r1 = fma(-fa, vc.y, r1);
-                if (HAS_B) { r0 = fma(-fb, bv.x, r0); r1 = fma(-fb, bv.y, r1); }
-                // every value read from slot_c (and, on the chunk's last plane, from the top plane's slot) has
-                // been consumed by now: the warp releases the slot(s)
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(smem_addr(empty + slot_c));
-                    if (q + 1 == zc && nplanes > zc) mbar_arrive(smem_addr(empty + slot_n));
-                }
-                acc = fma(r0, r0, acc);
-                acc = fma(r1, r1, acc);
-                st_stream2(po, make_double2(r0, r1));
-                if (a.halo_lo && z == 0) *reinterpret_cast<double2*>(a.halo_lo + off_c) = make_double2(r0, r1);
-                if (a.halo_hi && z == a.nz - 1) *reinterpret_cast<double2*>(a.halo_hi + off_c) = make_double2(r0, r1);
-                vm = vc; vc = vp; ho_c = ho_n; e_c = e_n;
-                pc += a.plane; po += a.plane;
-            }
-            g0 += (uint32_t)nplanes;
-        }
-    }
-    // deterministic CTA reduction over the eight consumer warps
-    acc = warp_sum(acc);
-    if (warp < kWarps && lane == 0) red[warp] = acc;
-    __syncthreads();
-    if (tid == 0 && a.partials) {
-        double tsum = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) tsum += red[w];
-        a.partials[blockIdx.x] = tsum;
-    }
-}
-
-static int kb_use_tma() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("LZ_KB_TMA");
-        v = e ? atoi(e) : 0;
-    }
-    return v;
-}
+// KB-TMA (git history: "KB-TMA: producer warp + full/empty mbarriers"): KB with every 64 x 8 plane tile of
+// x and of v_{j-1} fetched by one cp.async.bulk.tensor.3d into a ring of shared-memory slots, y-neighbours
+// read from the slots, z-neighbours in registers, outside rows / columns by plain loads one plane ahead.
+// Correct on every test (single GPU, sharded, both boundary types) but slower than the general kernel at
+// 512^3: 0.582 ms with an elected thread and one __syncthreads per plane (ring of 6, 3 CTAs/SM), 0.675 ms
+// with a producer warp and full/empty mbarriers (deeper rings: 0.77-0.99 ms), against 0.558 ms.  Two tensor
+// copies of 4 KB per plane and CTA are too small: the K4c experience (reorth.cu) is that the cost of a bulk
+// copy is per instruction, and K4c moves 60 KB with one.  KB therefore stays with the general kernel.
 
 template <int VEC, bool HAS_Y, bool HAS_Z, int MODE>
 static const void* pick_diag(bool has_diag) {
@@ -730,39 +537,8 @@ static int launch_stencil(lz_op* op, int mode, const double* x, const double* sc
         if (whole_tiles) fn = st.diag ? (const void*)stencil_alpha_fast_kernel<true> : (const void*)stencil_alpha_fast_kernel<false>;
         else fn = st.diag ? (const void*)stencil_alpha_kernel<true> : (const void*)stencil_alpha_kernel<false>;
     }
-    // KB-TMA: tiles staged by tensor copies (whole 64 x 8 tiles, no potential array)
-    CUtensorMap mapx, mapb, maphi;
-    int hi_kind = 0;
-    size_t smem_bytes = 0;
-    bool update_tma = (mode == 2) && kb_use_tma() && aligned && has_y && has_z && (st.offx != 0.0) && !flag_dev &&
-                      !st.diag && (st.nx % kTmaTX == 0) && (st.ny % kTmaTY == 0) && st.nz >= 1;
-    if (update_tma) {
-        const uint64_t dims3[3] = {(uint64_t)st.nx, (uint64_t)st.ny, (uint64_t)st.nz};
-        const uint64_t str3[2] = {(uint64_t)st.nx * 8, (uint64_t)a.plane * 8};
-        const uint32_t box3[3] = {kTmaTX, kTmaTY, 1};
-        update_tma = encode_f64_map(&mapx, x, 3, dims3, str3, box3);
-        mapb = mapx;
-        maphi = mapx;
-        if (update_tma && a.b) update_tma = encode_f64_map(&mapb, a.b, 3, dims3, str3, box3);
-        if (st.sharded) {
-            hi_kind = a.zhi ? 2 : 0;
-            if (update_tma && a.zhi) {
-                const uint32_t box2[2] = {kTmaTX, kTmaTY};
-                update_tma = encode_f64_map(&maphi, a.zhi, 2, dims3, str3, box2);
-            }
-        } else {
-            hi_kind = a.periodic ? 1 : 0;
-        }
-    }
-    if (update_tma) {
-        fn = a.b ? (const void*)stencil_update_tma_kernel<true> : (const void*)stencil_update_tma_kernel<false>;
-        smem_bytes = (size_t)kTmaRing * kTmaPlaneD * 8 * (a.b ? 2 : 1) + 2 * kTmaRing * 8 + 128;
-        LZ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        a.tiles_x = (int)(st.nx / kTmaTX);
-        a.tiles_y = (int)(st.ny / kTmaTY);
-    }
     int per_sm = 0;
-    LZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, update_tma ? kTmaThreads : kThreads, smem_bytes));
+    LZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
     const int64_t gmax = std::min<int64_t>((int64_t)ctx->sms * per_sm, kMaxPartials);
     // choose the z-chunking: few chunks (small halo overhead 2/zc) but a CTA count that
@@ -786,13 +562,8 @@ static int launch_stencil(lz_op* op, int mode, const double* x, const double* sc
     a.chunks_z = (int)((st.nz + a.zc - 1) / a.zc);
     a.nitems = tiles * a.chunks_z;
     const int grid = (int)std::min<int64_t>(a.nitems, gmax);
-    if (update_tma) {
-        void* targs[] = {(void*)&mapx, (void*)&mapb, (void*)&maphi, (void*)&a, (void*)&hi_kind};
-        LZ_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kTmaThreads), targs, smem_bytes, ctx->stream));
-    } else {
-        void* args[] = {(void*)&a};
-        LZ_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, 0, ctx->stream));
-    }
+    void* args[] = {(void*)&a};
+    LZ_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, 0, ctx->stream));
     if (nparts) *nparts = grid;
     return LZ_OK;
 }

@@ -1,5 +1,5 @@
 // TMA (bulk tensor copy) and mbarrier primitives shared by the kernels that stage tiles in shared
-// memory (K4c in reorth.cu, KB-TMA in stencil.cu), and the host-side tensor-map encoder.
+// memory (K4c in reorth.cu), and the host-side tensor-map encoder.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
