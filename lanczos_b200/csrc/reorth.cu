@@ -1,5 +1,6 @@
 // K4a / K4b: full or selective re-orthogonalisation against the Krylov basis held in HBM as
-// a tall-skinny block GEMV pair (classical Gram-Schmidt), and K5: the Ritz-vector lift.
+// a tall-skinny block GEMV pair (classical Gram-Schmidt), K4c: the fused middle of CGS2 (tile of the
+// basis staged in shared memory by a TMA tensor copy), and K5: the Ritz-vector lift.
 //
 // Replaces Lanczos.reorthogonalize (Lanczos.py:233-251; IrrLanczos.py:448-466):
 //     ip = sum(V[j]*V, axis=1)                     -> cgs_dots    (h = V_k^T v, one sweep)

@@ -10,4 +10,4 @@ for rep in range(2):
     L.execute_Lanczos(60, v0=v0, reorth="full", cgs_passes=2, profile=True)
 r = L.result
 import os
-print("TMA" if os.environ.get("LZ_K4C_TMA") == "1" else "cp.async", f"{r.gpu_ms/60:.3f} ms/step", {k: (round(v[0], 2), v[1]) for k, v in r.kernel_ms.items() if v[1]}, flush=True)
+print("cp.async" if os.environ.get("LZ_K4C_TMA") == "0" else "TMA", f"{r.gpu_ms/60:.3f} ms/step", {k: (round(v[0], 2), v[1]) for k, v in r.kernel_ms.items() if v[1]}, flush=True)
