@@ -451,7 +451,9 @@ stencil_alpha_fast_kernel(const StencilArgs a) {
 // 512^3: 0.582 ms with an elected thread and one __syncthreads per plane (ring of 6, 3 CTAs/SM), 0.675 ms
 // with a producer warp and full/empty mbarriers (deeper rings: 0.77-0.99 ms), against 0.558 ms.  Two tensor
 // copies of 4 KB per plane and CTA are too small: the K4c experience (reorth.cu) is that the cost of a bulk
-// copy is per instruction, and K4c moves 60 KB with one.  KB therefore stays with the general kernel.
+// copy is per instruction, and K4c moves 60 KB with one.  Wider tiles confirm it - 128x4: 0.71 ms, 256x4 (16
+// consumer warps): 0.79-0.97 ms (spills at 2 CTAs/SM), 512x2 (whole 4 KB rows per copy): 0.557 ms, i.e. parity
+// with the general kernel at three times its code.  KB therefore stays with the general kernel.
 
 template <int VEC, bool HAS_Y, bool HAS_Z, int MODE>
 static const void* pick_diag(bool has_diag) {
