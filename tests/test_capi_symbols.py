@@ -78,6 +78,33 @@ def test_argument_validation_without_gpu(lib):
     assert b"null" in lib.lz_last_error()
 
 
+def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
+    """examples/c_abi_demo.c: the header compiles as C99 with -Wall -Werror, the library links from C,
+    and without a CUDA device the client stops after the boundary checks (no CPU path)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    cuda_lib = "/usr/local/cuda/lib64"
+    if not os.path.exists(os.path.join(cuda_lib, "libcudart.so")):
+        pytest.skip("libcudart.so not found (the demo allocates device memory through the CUDA runtime)")
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.join(ROOT, "lanczos_b200")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L" + libdir, "-llanczos_b200", "-L" + cuda_lib, "-lcudart",
+           "-Wl,-rpath," + libdir, "-Wl,-rpath," + cuda_lib, "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "lz_abi_version = 1" in run.stdout
+    import torch
+    if torch.cuda.is_available():
+        assert "steps_done = 12" in run.stdout
+    else:
+        assert "no CUDA device" in run.stdout
+
+
 def test_product_has_no_cpu_path():
     """Without a CUDA device the drop-in must fail loudly, never fall back."""
     import torch
