@@ -464,13 +464,23 @@ def main():
     # so the job processes world*K shard-steps; at N = 1 this is plain Lanczos steps/s.
     strong = bool(wl.get("strong"))
     value = (1 if strong else world) * K / (ms_dev / 1e3)
-    fused = {"alg_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / ms_per_step / 1e6 if reorths == 0 else None,
-             "frac_of_measured_peak": step_bytes / ms_per_step / 1e6 / peak if reorths == 0 else None,
-             "frac_of_8TBs_nominal": step_bytes / ms_per_step / 1e6 / 8000.0 if reorths == 0 else None,
-             "step_kernel": step_kernel,
-             "note": "bytes per plain step: 32*N recompute step (KA 8N + KB 24N, matrix-free operators), 48*N two-pass step "
-                     "(SURVEY 8d), + the operator's own bytes for stored operators; null when Gram-Schmidt sweeps ran",
-             "frac_of_48N_at_measured_peak": 48.0 * N / ms_per_step / 1e6 / peak if (reorths == 0 and is_stencil) else None}
+    plain = reorths == 0
+    moved_gbs = step_bytes / ms_per_step / 1e6
+    fused = {"step_kernel": step_kernel,
+             "moved_bytes_per_step": step_bytes,                       # what this implementation actually moves
+             "achieved_gbs": moved_gbs if plain else None,
+             "frac_of_measured_peak": moved_gbs / peak if plain else None,
+             "frac_of_8TBs_nominal": moved_gbs / 8000.0 if plain else None,
+             "note": "bytes per plain step: 32*N with the recompute step (KA2 8N + KB 24N: H v is re-evaluated instead of "
+                     "written and re-read), 48*N with the two-pass step (SURVEY 8d), + the operator's own bytes for stored "
+                     "operators; null when Gram-Schmidt sweeps ran"}
+    if is_stencil:
+        # BASELINE's target (>= 70 % of the HBM roofline for the fused step at 512^3) is stated for the two-pass
+        # step of SURVEY 8d, 48*N bytes: the same step time expressed in that accounting
+        survey_gbs = 48.0 * N / ms_per_step / 1e6
+        fused["survey_48N_accounting"] = {"bytes_per_step": 48.0 * N, "equivalent_gbs": survey_gbs if plain else None,
+                                          "frac_of_measured_peak": survey_gbs / peak if plain else None,
+                                          "frac_of_8TBs_nominal": survey_gbs / 8000.0 if plain else None}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
