@@ -221,6 +221,65 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------- parity gate
+def parity_check(lz, world, rank, dist):
+    """Before anything is timed: a small solve through the code path this run uses - row-sharded over the
+    `world` GPUs of the run (a 2-shard single-process team on one GPU at N = 1, so that the peer-memory
+    exchange is always exercised) - held against the oracle and against the single-GPU result, alpha/beta
+    <= 1e-12 relative (n = 40 <= 50, full re-orthogonalisation in the reference's form).  The oracle is used
+    as the checker only.  Returns the dict that goes into the JSON line; `ok` False makes bench.py exit 1."""
+    import torch
+    from lanczos_b200 import team as lzteam
+    from oracle import lanczos_oracle as orc
+    n, tol = 40, 1e-12
+    out = {"tol": tol, "n": n, "cases": []}
+
+    def rel(a, b):
+        return float(np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(b), 1e-300)))
+
+    def record(name, Hs, ref, single, sharded):
+        a1, b1 = np.diag(single.H_eff), np.diag(single.H_eff, 1)
+        a2, b2 = np.diag(sharded.H_eff), np.diag(sharded.H_eff, 1)
+        c = {"case": name, "shards": sharded.world,
+             "sharded_vs_oracle": max(rel(a2, ref["alpha"]), rel(b2, ref["beta"])),
+             "single_vs_oracle": max(rel(a1, ref["alpha"]), rel(b1, ref["beta"])),
+             "sharded_vs_single": max(rel(a2, a1), rel(b2, b1))}
+        c["ok"] = bool(max(c["sharded_vs_oracle"], c["single_vs_oracle"], c["sharded_vs_single"]) < tol)
+        out["cases"].append(c)
+
+    shards = world if world > 1 else 2
+    # structured grid, z-slabs + halo planes
+    grid = (64, 64, 16 * shards)
+    H = orc.laplacian_csr(grid, 6.0, -1.0, periodic=True)
+    ref = orc.lanczos(H, n, seed=7)
+    op = lz.StencilOperator(grid, 6.0, -1.0)
+    single = lz.Lanczos(op)
+    single.execute_Lanczos(n, seed=7, use_cuda=False, verbose=False)
+    sharded = lzteam.TeamLanczos(op, rank=rank, world=world) if world > 1 else lzteam.LocalTeamLanczos(op, shards)
+    sharded.execute_Lanczos(n, seed=7)
+    record("7-point periodic %dx%dx%d, z-slabs" % grid, H, ref, single, sharded)
+    del sharded
+    # sparse rows, ghost-index exchange
+    G = orc.delaunay_graph_laplacian(4000 * shards, seed=1)
+    refg = orc.lanczos(G, n, seed=7)
+    singleg = lz.IrrLanczos(G)
+    singleg.execute_LanczosOld(n, seed=7, verbose=False)
+    shardedg = lzteam.TeamLanczos(G, rank=rank, world=world) if world > 1 else lzteam.LocalTeamLanczos(G, shards)
+    shardedg.execute_Lanczos(n, seed=7)
+    record("Delaunay graph Laplacian %d vertices, SELL row blocks" % G.shape[0], G, refg, singleg, shardedg)
+    del shardedg
+    torch.cuda.synchronize()
+    ok = all(c["ok"] for c in out["cases"])
+    if world > 1:                       # every rank must agree that it passed
+        t = torch.tensor([0 if ok else 1], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t)
+        ok = int(t.item()) == 0
+    out["ok"] = bool(ok)
+    out["mode"] = ("one process per GPU over %d GPUs (TeamLanczos)" % world) if world > 1 else \
+                  "2 shards driven by one process on the one GPU (LocalTeamLanczos)"
+    return out
+
+
 # --------------------------------------------------------------------------- GPU arm
 def build_operator(lz, workload, world, rank):
     wl = WORKLOADS[workload]

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LZ_ABI_VERSION 1
+#define LZ_ABI_VERSION 2
 
 /* status codes */
 #define LZ_OK               0
@@ -143,7 +143,10 @@ typedef struct lz_run_opts {
                               3 recompute step (matrix-free operators: KA reduces alpha without
                               writing H v, KB applies H again inside the update: 32*M B)       */
     int32_t flags;         /* bit 0: do not fuse the middle of CGS2 (K4c: update of sweep 1 + dots of
-                              sweep 2 from one read of the basis); 0 = defaults                  */
+                              sweep 2 from one read of the basis); bit 1 (with ref_compat): the sweep
+                              takes the LZ_SWEEP_GPU form of Regular/Lanczos.py:236-238 instead of
+                              the (2 - |v|^2) form; bit 2: do not accumulate alpha inside KB (recompute
+                              step: a KA pass per step instead of the border kernel); 0 = defaults */
     double  breakdown_tol; /* stop when beta <= breakdown_tol * |alpha_0| (0: only 0/NaN) */
     double  select_tol;    /* selective: orthogonality level that triggers (0 -> sqrt(eps)) */
 } lz_run_opts;
@@ -166,6 +169,10 @@ typedef struct lz_run_info {
     int32_t step_kernel;   /* the step kernel that ran (1, 2 or 3 as in lz_run_opts)  */
     int32_t gsfused_launches; /* ... K4c fused Gram-Schmidt update + dots              */
     float   gsfused_ms;
+    int32_t border_launches;  /* ... the border kernel that completes alpha when KB accumulates it */
+    float   border_ms;
+    int32_t alpha_in_update;  /* 1: alpha of the next vector was accumulated inside KB (+ border kernel)
+                                 instead of a KA pass over the vector                   */
 } lz_run_info;
 
 /* Runs n steps from v0_dev (M doubles).  Outputs: alpha_host[n], beta_host[n-1]
@@ -184,10 +191,17 @@ int lz_lanczos_run(lz_ctx* ctx, lz_op* op, const double* v0_dev, int32_t n,
 int lz_basis_normalize(lz_ctx* ctx, double* V_dev, int64_t ldv, int32_t n, int64_t M,
                        const double* row_scale_host);
 
+/* sweep forms of the reference's reorthogonalize */
+#define LZ_SWEEP_CPU  0   /* V[j] = 2 V[j] - sum_i (V[j].V[i]) V[i], i over all rows incl. j
+                             (Lanczos.py:247-249 with use_cuda=False; IrrLanczos.py:453-460 both modes) */
+#define LZ_SWEEP_GPU  1   /* V[j] = V[j] - sum_{i != j} (V[j].V[i]) V[i]
+                             (Lanczos.py:236-238, Regular with use_cuda=True)                        */
+
 /* One Gram-Schmidt sweep of row j of V against all rows, in place: the staticmethod
- * Lanczos.reorthogonalize(V, j) (Lanczos.py:233-251, CPU form :247-249;
- * IrrLanczos.py:448-466).  V is (n x ldv) row-major on the device.  Synchronises. */
-int lz_reorthogonalize(lz_ctx* ctx, double* V_dev, int64_t ldv, int32_t n, int64_t M, int32_t j);
+ * Lanczos.reorthogonalize(V, j, use_cuda) (Lanczos.py:233-251; IrrLanczos.py:448-466) in the
+ * given form.  V is (n x ldv) row-major on the device.  Synchronises. */
+int lz_reorthogonalize(lz_ctx* ctx, double* V_dev, int64_t ldv, int32_t n, int64_t M, int32_t j,
+                       int32_t form);
 
 /* Ritz vectors: Y[c,:] = sum_j S[j,c] * row_scale[j] * V[j,:], c < k.  The lift loop of
  * get_H_eigs (Lanczos.py:154-156).  S_host is n x k column-major (column c = c-th

@@ -17,6 +17,7 @@ LZ_OK, LZ_ERR_INVALID, LZ_ERR_CUDA, LZ_ERR_NOMEM, LZ_ERR_BREAKDOWN, LZ_ERR_UNSUP
 LZ_BC_PERIODIC, LZ_BC_DIRICHLET = 0, 1
 LZ_FMT_CSR, LZ_FMT_SELL = 0, 1
 LZ_REORTH_NONE, LZ_REORTH_FULL, LZ_REORTH_SELECTIVE = 0, 1, 2
+LZ_SWEEP_CPU, LZ_SWEEP_GPU = 0, 1
 
 
 class LanczosBreakdown(ArithmeticError):
@@ -41,7 +42,8 @@ class RunInfo(C.Structure):
                 ("fused_launches", C.c_int32),
                 ("gpu_ms", C.c_float), ("apply_ms", C.c_float), ("update_ms", C.c_float),
                 ("dots_ms", C.c_float), ("gsupd_ms", C.c_float), ("fused_ms", C.c_float),
-                ("step_kernel", C.c_int32), ("gsfused_launches", C.c_int32), ("gsfused_ms", C.c_float)]
+                ("step_kernel", C.c_int32), ("gsfused_launches", C.c_int32), ("gsfused_ms", C.c_float),
+                ("border_launches", C.c_int32), ("border_ms", C.c_float), ("alpha_in_update", C.c_int32)]
 
 
 _vp, _i32, _i64, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
@@ -67,7 +69,7 @@ SIGNATURES = {
     "lz_op_destroy": (C.c_int, [_vp]),
     "lz_lanczos_run": (C.c_int, [_vp, _vp, _vp, _i32, _P(RunOpts), _vp, _vp, _vp, _i64, _vp, _P(RunInfo)]),
     "lz_basis_normalize": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp]),
-    "lz_reorthogonalize": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _i32]),
+    "lz_reorthogonalize": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _i32, _i32]),
     "lz_ritz_vectors": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _i32, _vp, _i64]),
     "lz_dot": (C.c_int, [_vp, _vp, _vp, _i64, _P(_dbl)]),
     "lz_comm_bytes": (C.c_int, [C.c_int, _i32, _i64, _i64, _P(_i64)]),

@@ -2,6 +2,7 @@
 // and the small entry points that are thin wrappers over one kernel.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -19,16 +20,24 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+bool pdl_enabled() {
+    static const bool on = []() {
+        const char* e = getenv("LZ_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 int launch_stencil_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
-                             double* partials, int* nparts, const int* flag_dev);
+                             double* partials, int* nparts, const int* flag_dev, const FinTail* fin);
 int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double* y, double* partials,
-                    int* nparts, const int* flag_dev);
+                    int* nparts, const int* flag_dev, const FinTail* fin);
 int launch_stencil27_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
-                               double* partials, int* nparts, const int* flag_dev);
+                               double* partials, int* nparts, const int* flag_dev, const FinTail* fin);
 int launch_stencil_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
-                               double* out, double* partials, int* nparts);
+                               double* out, double* partials, int* nparts, const FinTail* fin);
 int launch_stencil27_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
-                                 double* out, double* partials, int* nparts);
+                                 double* out, double* partials, int* nparts, const FinTail* fin);
 int build_csr(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const int32_t* indices,
               const double* data);
 int build_sell(lz_op* op, int64_t M, int64_t nnz, const int32_t* indptr, const int32_t* indices,
@@ -37,12 +46,12 @@ int build_from_device(lz_op* op, int64_t M, int64_t ncols, int64_t nnz, const in
                       const int32_t* indices, const double* data, int fmt, int sigma);
 
 int launch_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y, double* partials,
-                     int* nparts, int* launches, const int* flag_dev) {
+                     int* nparts, int* launches, const int* flag_dev, const FinTail* fin) {
     if (launches) *launches = 1;
     if (op->kind == LZ_OP_STENCIL && op->st.points == 27)
-        return launch_stencil27_apply_dot(op, x, scale_dev, y, partials, nparts, flag_dev);
-    if (op->kind == LZ_OP_STENCIL) return launch_stencil_apply_dot(op, x, scale_dev, y, partials, nparts, flag_dev);
-    return launch_spmv_dot(op, x, scale_dev, y, partials, nparts, flag_dev);
+        return launch_stencil27_apply_dot(op, x, scale_dev, y, partials, nparts, flag_dev, fin);
+    if (op->kind == LZ_OP_STENCIL) return launch_stencil_apply_dot(op, x, scale_dev, y, partials, nparts, flag_dev, fin);
+    return launch_spmv_dot(op, x, scale_dev, y, partials, nparts, flag_dev, fin);
 }
 
 // Matrix-free operators can re-evaluate H x inside the update instead of storing it (KA + KB).
@@ -53,14 +62,14 @@ bool recompute_step_supported(const lz_op* op) { return op->kind == LZ_OP_STENCI
 bool recompute_step_preferred(const lz_op* op) { return op->kind == LZ_OP_STENCIL && op->st.points == 7; }
 
 int launch_apply_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
-                             double* out, double* partials, int* nparts, int* launches) {
+                             double* out, double* partials, int* nparts, int* launches, const FinTail* fin) {
     if (launches) *launches = 1;
     if (op->kind != LZ_OP_STENCIL) {
         set_error("the recompute step needs a matrix-free operator");
         return LZ_ERR_UNSUPPORTED;
     }
-    if (op->st.points == 27) return launch_stencil27_update_norm(op, x, scale_dev, upd, out, partials, nparts);
-    return launch_stencil_update_norm(op, x, scale_dev, upd, out, partials, nparts);
+    if (op->st.points == 27) return launch_stencil27_update_norm(op, x, scale_dev, upd, out, partials, nparts, fin);
+    return launch_stencil_update_norm(op, x, scale_dev, upd, out, partials, nparts, fin);
 }
 
 // sum of np partials -> out[0] (one CTA, fixed order)
@@ -74,15 +83,15 @@ sum_partials_kernel(const double* __restrict__ p, int np, double* __restrict__ o
 }
 
 // coefficients of the stand-alone Gram-Schmidt sweep (Lanczos.reorthogonalize on arbitrary V):
-// coef[r] = ip_r (r != j), coef[j] = 0, cself = 2 - ip_j
+// coef[r] = ip_r (r != j), coef[j] = 0, cself = 2 - ip_j (LZ_SWEEP_CPU) or 1 (LZ_SWEEP_GPU)
 __global__ void __launch_bounds__(kThreads)
 sweep_coef_kernel(const double* __restrict__ part, int ncg, int n, int j, double* __restrict__ coef,
-                  double* __restrict__ cself) {
+                  double* __restrict__ cself, int form) {
     for (int r = threadIdx.x; r < n; r += kThreads) {
         const double* p = part + (int64_t)r * ncg;
         double a = 0.0;
         for (int g = 0; g < ncg; ++g) a += p[g];
-        if (r == j) { cself[0] = 2.0 - a; coef[r] = 0.0; }
+        if (r == j) { cself[0] = (form == LZ_SWEEP_GPU) ? 1.0 : 2.0 - a; coef[r] = 0.0; }
         else coef[r] = a;
     }
 }
@@ -123,6 +132,8 @@ int lz_ctx_create(int device, void* cuda_stream, lz_ctx** out) {
     c->sms = prop.multiProcessorCount;
     cudaError_t e = cudaMalloc((void**)&c->partials, (size_t)2 * kMaxPartials * 8);
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->scratch, 64 * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->tickets, 64 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(c->tickets, 0, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_begin);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_end);
     if (e != cudaSuccess) {
@@ -139,6 +150,7 @@ int lz_ctx_destroy(lz_ctx* c) {
     cudaSetDevice(c->device);
     if (c->partials) cudaFree(c->partials);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->tickets) cudaFree(c->tickets);
     if (c->arena) cudaFree(c->arena);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
@@ -424,8 +436,9 @@ int lz_op_export_csr(lz_op* op, int64_t* nnz_out, int32_t* indptr_host, int32_t*
     });
 }
 
-int lz_reorthogonalize(lz_ctx* ctx, double* V_dev, int64_t ldv, int32_t n, int64_t M, int32_t j) {
+int lz_reorthogonalize(lz_ctx* ctx, double* V_dev, int64_t ldv, int32_t n, int64_t M, int32_t j, int32_t form) {
     LZ_REQUIRE(ctx && V_dev, "lz_reorthogonalize: null argument");
+    LZ_REQUIRE(form == LZ_SWEEP_CPU || form == LZ_SWEEP_GPU, "lz_reorthogonalize: unknown sweep form %d", form);
     LZ_REQUIRE(n >= 1 && j >= 0 && j < n && ldv >= M && M >= 1, "lz_reorthogonalize: bad shape (n=%d, j=%d)", n, j);
     LZ_CUDA(cudaSetDevice(ctx->device));
     double* part = nullptr;
@@ -439,7 +452,7 @@ int lz_reorthogonalize(lz_ctx* ctx, double* V_dev, int64_t ldv, int32_t n, int64
     int ncg = 0;
     int st = launch_cgs_dots(ctx, V_dev, ldv, n, target, M, part, &ncg, nullptr);
     if (st == LZ_OK) {
-        sweep_coef_kernel<<<1, kThreads, 0, ctx->stream>>>(part, ncg, n, j, coef, cself);
+        sweep_coef_kernel<<<1, kThreads, 0, ctx->stream>>>(part, ncg, n, j, coef, cself, form);
         set_one_kernel<<<1, 32, 0, ctx->stream>>>(one);
         // rows before j, then rows after j (row j itself is the in-place target)
         st = launch_cgs_update(ctx, V_dev, ldv, j, target, coef, cself, target, M, nullptr);

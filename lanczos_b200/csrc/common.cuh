@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 #include "../../include/lanczos_b200.h"
 
 namespace lz {
@@ -41,8 +42,53 @@ constexpr int kThreads = 256;          // every streaming kernel uses 256-thread
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxPartials = 4096;     // upper bound on CTAs that write a partial sum
 
+// ------------------------------------------------------------------ launches
+// Programmatic dependent launch: every kernel of the loop starts with pdl_wait() (blocks until the
+// preceding kernel of the stream has completed and its writes are visible) right after
+// pdl_trigger() (lets the NEXT kernel of the stream be scheduled as soon as this one's CTAs leave
+// the SMs).  Launched with the programmatic-stream-serialization attribute the launch latency and
+// the CTA ramp of kernel k+1 overlap the tail of kernel k instead of following its drain; without
+// the attribute both instructions are no-ops.  LZ_PDL=0 in the environment turns the attribute off.
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+// untyped form (kernel chosen at run time from a table of template instances)
+inline cudaError_t launch_fn(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, void** args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelExC(&cfg, fn, args);
+}
+#endif
+
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// first statement of every loop kernel
+__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
 
 // Streaming 128-bit fp64 loads/stores.  The Krylov vectors are far larger than L2
 // (1.07 GB each at 512^3), so everything that is touched once per kernel bypasses L1

@@ -2,6 +2,7 @@
 #pragma once
 #include <vector>
 #include "common.cuh"
+#include "fin.cuh"
 
 enum lz_op_kind { LZ_OP_STENCIL = 0, LZ_OP_CSR = 1, LZ_OP_SELL = 2 };
 
@@ -11,6 +12,7 @@ struct lz_ctx {
     int sms = 148;
     double* partials = nullptr;    // 2 * kMaxPartials doubles: CTA partial sums of streaming kernels
     double* scratch = nullptr;     // 64 doubles of device scratch (lz_dot, lz_reorthogonalize, ...)
+    unsigned int* tickets = nullptr;   // last-CTA tickets of the fin tails (fin.cuh); zero between launches
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     void* arena = nullptr;         // grow-only device workspace of lz_lanczos_run
     size_t arena_bytes = 0;
@@ -62,6 +64,7 @@ struct lz_op {
     lz_csr csr;
     lz_sell sell;
     int fused_per_sm = 0;          // cached occupancy of the fused step kernel
+    int kb_zc = 0;                 // z-chunk length of the last KB launch that accumulated alpha (border kernel)
     int64_t ncols = 0;             // sparse: number of columns (> M for a row shard: M owned + ghosts)
     const double* xghost = nullptr;   // sparse row shard: where the ghost entries of x live (set per launch)
     // host copy of the CSR arrays is NOT kept; export reads them back from the device.
@@ -80,8 +83,10 @@ struct HaloPush {
 // ---- operator apply with fused dot:  y = s * (H x),  partials[cta] = sum y * (s*x) -----
 // `scale_dev` (nullable => 1) points at a device double.  `partials` has room for
 // kMaxPartials doubles; *nparts receives the number written.
+// `fin` (nullable): bookkeeping the last CTA to finish runs on the summed partials (fin.cuh).
 int launch_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
-                     double* partials, int* nparts, int* launches, const int* flag_dev = nullptr);
+                     double* partials, int* nparts, int* launches, const int* flag_dev = nullptr,
+                     const FinTail* fin = nullptr);
 
 // ---- "recompute" step of matrix-free operators (stencil.cu, stencil27.cu) -------------------
 // KA: launch_apply_dot with y == nullptr reduces alpha without writing w.
@@ -93,11 +98,19 @@ struct StencilUpdate {
     const double* cb = nullptr;
     const double* sb = nullptr;
     HaloPush halo;             // sharded structured grids: boundary planes of `out` -> the neighbours' ghost buffers
+    // alpha of the vector being produced, accumulated while it is still in registers (stencil.cu, KB + border
+    // kernel): partials of out . H out over the edges inside a CTA tile go to alpha_partials[cta] (nullable)
+    double* alpha_partials = nullptr;
 };
 bool recompute_step_supported(const lz_op* op);
 bool recompute_step_preferred(const lz_op* op);
 int launch_apply_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
-                             double* out, double* partials, int* nparts, int* launches);
+                             double* out, double* partials, int* nparts, int* launches,
+                             const FinTail* fin = nullptr);
+// alpha inside KB: supported for 7-point operators on grids made of whole 64 x 8 tiles
+bool update_alpha_supported(const lz_op* op, const double* x, const double* out);
+// the edges KB could not reach (across tile borders and z-chunks, slab top): partials[cta] of out . H out over them
+int launch_alpha_border(lz_op* op, const double* v, double* partials, int* nparts, const FinTail* fin);
 
 // ---- single-pass fused step (fused.cu) ---------------------------------------------------
 bool fused_step_supported(const lz_op* op);
@@ -107,13 +120,14 @@ int launch_fused_step(lz_op* op, const double* u, const double* rj, const double
 
 // ---- streaming vector kernels (vecops.cu) ------------------------------------------------
 // partials[cta] = sum x*y
-int launch_dot(lz_ctx* ctx, const double* x, const double* y, int64_t M, double* partials, int* nparts);
+int launch_dot(lz_ctx* ctx, const double* x, const double* y, int64_t M, double* partials, int* nparts,
+               const FinTail* fin = nullptr);
 // out = w - ca*sa*a - cb*sb*b with ca/sa/cb/sb read from device memory (nullable b),
 // partials[cta] = sum out^2.  In-place (out == w) is allowed.
 int launch_update_norm(lz_ctx* ctx, const double* w, const double* a, const double* b,
                        const double* ca_dev, const double* sa_dev, const double* cb_dev,
                        const double* sb_dev, double* out, int64_t M, double* partials, int* nparts,
-                       const HaloPush* halo = nullptr);
+                       const HaloPush* halo = nullptr, const FinTail* fin = nullptr);
 int launch_halo_push(lz_ctx* ctx, const double* x, int64_t M, const HaloPush* halo);
 int launch_ghost_push(lz_ctx* ctx, const double* x, const int32_t* send_idx, int nsend, int world,
                       const int* seg_start, double* const* dst, const int* flag_dev);

@@ -28,67 +28,16 @@
 
 namespace lz {
 
-// Fixed-order sum of n partials by one CTA: thread t adds p[t], p[t+256], ... then the
-// block tree.  Independent of everything but n => bit-reproducible run to run.
-__device__ __forceinline__ double cta_sum_partials(const double* __restrict__ p, int n, double* red) {
-    double a = 0.0;
-    for (int i = threadIdx.x; i < n; i += kThreads) a += p[i];
-    return block_sum(a, red);
-}
-
-struct RunState {          // all device pointers
-    double* alpha;         // [n]
-    double* beta;          // [n+1]  beta[j] = |r_j|  (r_j is what row j stores before any sweep)
-    double* scale;         // [n+1]  q_j = scale[j] * row_j
-    double* coef;          // [n+1]  Gram-Schmidt coefficients for K4b (already times scale[r])
-    double* omega_a;       // [n+2]  selective monitor, omega_{j,k}
-    double* omega_b;       // [n+2]
-    double* cself;         // [1]
-    double* v0scale;       // [1]    1/|v0|
-    double* alpha_pre;     // [1]    alpha of the pre-step (discarded by the reference)
-    double* anorm;         // [1]    running estimate of |H|
-    int* flags;            // [0] first breakdown step (-1: none), [1] reorth flag of the coming step,
-                           // [2] reorth count, [3] force-next flag, [4] peer timeout
-};
-
-enum { FIN_V0NORM = 0, FIN_ALPHA = 1, FIN_BETA = 2, FIN_ALPHA_S2 = 3 };
-
-// One scalar: CTA partials -> local sum -> (sharded) sum over ranks -> bookkeeping by `kind`.
+// One scalar: CTA partials -> local sum -> (sharded) sum over ranks -> bookkeeping.  The stand-alone
+// form of the fin tail (fin.cuh): the combine phase when one process drives several shards, and the
+// opt-in single-pass step.
 __global__ void __launch_bounds__(kThreads)
-fin_scalar_kernel(const double* __restrict__ partials, int np, RunState st, PeerComm pc,
-                  unsigned long long seq, int mode, int kind, double* out, int jn, double tol_rel,
-                  const double* __restrict__ magnitude, const int* __restrict__ flag) {
+fin_scalar_kernel(const double* __restrict__ partials, int np, const FinOp f, const RunState st, const PeerComm pc,
+                  unsigned long long seq, int mode, const int* __restrict__ flag) {
+    pdl_prologue();
     if (flag && *flag == 0) return;
     __shared__ double red[kWarps];
-    double s = 0.0;
-    if (mode != LZ_XCHG_COMBINE) s = cta_sum_partials(partials, np, red);
-    if (pc.world > 1) {
-        if (mode != LZ_XCHG_COMBINE) {
-            if (threadIdx.x == 0) peer_store(pc, seq, 0, s);
-            peer_publish(pc, seq);
-            if (mode == LZ_XCHG_PUSH) return;
-        }
-        peer_wait(pc, seq);
-        if (threadIdx.x == 0) s = peer_sum(pc, seq, 0);
-    }
-    if (threadIdx.x != 0) return;
-    if (kind == FIN_V0NORM) {
-        const double nrm = sqrt(s);
-        st.v0scale[0] = (nrm > 0.0) ? 1.0 / nrm : 0.0;
-        if (!(nrm > 0.0) && st.flags[0] < 0) st.flags[0] = 0;
-    } else if (kind == FIN_ALPHA) {
-        out[0] = s;
-    } else if (kind == FIN_ALPHA_S2) {        // alpha_j = q_j.H q_j from un-normalised r_j, u_j = H r_j
-        const double sc = st.scale[jn];
-        out[0] = s * sc * sc;
-    } else {
-        const double b = sqrt(s);
-        st.beta[jn] = b;
-        const double thresh = tol_rel * fabs(magnitude[0]);
-        const bool ok = isfinite(b) && (b > thresh) && (b > 0.0);
-        st.scale[jn] = (isfinite(b) && b > 0.0) ? 1.0 / b : 0.0;
-        if (!ok && st.flags[0] < 0) st.flags[0] = jn;
-    }
+    fin_scalar_body(f, st, pc, seq, mode, partials, np, red);
 }
 
 // Fin of the single-pass fused step: partials[0..g) = sum r^2, partials[g..2g) = sum r.u with
@@ -112,6 +61,7 @@ fin_fused_kernel(const double* __restrict__ partials, int g, RunState st, int jn
 
 // Non-ref start: beta[0] = |v0|, scale[0] = 1/|v0|.
 __global__ void init_first_row_kernel(RunState st) {
+    pdl_prologue();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const double s = st.v0scale[0];
         st.scale[0] = s;
@@ -127,6 +77,7 @@ __global__ void __launch_bounds__(kThreads)
 fin_ip_kernel(const double* __restrict__ part, int ncg, int j, int self_included, int ref_form,
               RunState st, PeerComm pc, unsigned long long seq, int mode,
               const int* __restrict__ flag, int count) {
+    pdl_prologue();
     if (flag && *flag == 0) return;
     const int nrows = self_included ? j + 1 : j;
     const bool sharded = pc.world > 1;
@@ -172,6 +123,7 @@ fin_ip_kernel(const double* __restrict__ part, int ncg, int j, int self_included
 // into the neighbours' ghost buffers, and waits for theirs.
 __global__ void __launch_bounds__(32)
 peer_sync_kernel(PeerComm pc, unsigned long long seq, int mode, const int* __restrict__ flag) {
+    pdl_prologue();
     if (flag && *flag == 0) return;
     if (pc.world <= 1) return;
     if (mode != LZ_XCHG_COMBINE) {
@@ -181,54 +133,12 @@ peer_sync_kernel(PeerComm pc, unsigned long long seq, int mode, const int* __res
     peer_wait(pc, seq);
 }
 
-// Selective re-orthogonalisation monitor (Simon's omega recurrence in the PROPACK form).
-// Called after step j finished (alpha[j], beta[j+1] known); estimates
-// omega_{j+1,k} ~ q_{j+1} . q_k for k <= j, and raises flags[1] for step j+1 when the
-// largest estimate exceeds `delta` (and for the step after it: vectors are re-orthogonalised
-// in pairs).  om_cur = omega_{j,.}, om_prev = omega_{j-1,.}; result overwrites om_prev.
+// the omega recurrence as a kernel of its own (single-pass fused step only; elsewhere it rides in
+// the tail of the kernel that produced beta)
 __global__ void __launch_bounds__(kThreads)
 omega_kernel(RunState st, int j, double* om_cur, double* om_prev, double delta, double eps1, double psi) {
     __shared__ double red[kWarps];
-    const double bj1 = st.beta[j + 1];
-    const double bj = (j > 0) ? st.beta[j] : 0.0;
-    const double aj = st.alpha[j];
-    // if this step's vector was itself re-orthogonalised, its omegas are at round-off level
-    if (st.flags[1]) {
-        for (int k = threadIdx.x; k < j; k += kThreads) om_cur[k] = eps1;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        double an = st.anorm[0];
-        an = fmax(an, fabs(aj) + bj + bj1);
-        st.anorm[0] = an;
-    }
-    __syncthreads();
-    const double anorm = st.anorm[0];
-    double mx = 0.0;
-    for (int k = threadIdx.x; k < j; k += kThreads) {
-        const double bk1 = st.beta[k + 1];
-        const double bk = (k > 0) ? st.beta[k] : 0.0;
-        const double ok1 = (k + 1 < j) ? om_cur[k + 1] : ((k + 1 == j) ? 1.0 : 0.0);
-        double t = bk1 * ok1 + (st.alpha[k] - aj) * om_cur[k] - bj * om_prev[k];
-        if (k > 0) t += bk * om_cur[k - 1];
-        const double d = eps1 * (fabs(aj) + bj1 + fabs(st.alpha[k]) + bk1) + eps1 * anorm;
-        t = (t + copysign(d, t)) / bj1;
-        om_prev[k] = t;                      // becomes omega_{j+1,k} after the swap on the host side
-        mx = fmax(mx, fabs(t));
-    }
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double m = 0.0;
-        for (int w = 0; w < kWarps; ++w) m = fmax(m, red[w]);
-        om_prev[j] = psi;                    // omega_{j+1,j}
-        om_prev[j + 1] = 1.0;
-        int fire = 0;
-        if (st.flags[3]) { fire = 1; st.flags[3] = 0; }          // second vector of a pair
-        else if (m > delta) { fire = 1; st.flags[3] = 1; }
-        st.flags[1] = fire;
-    }
+    omega_body(st, j, om_cur, om_prev, delta, eps1, psi, red);
 }
 
 // Carve the run's device workspace out of the context's grow-only arena (no cudaMalloc /
@@ -348,6 +258,7 @@ struct ShardRun {           // per-shard state of one run
     double* om_prev = nullptr;
     KernelTimer kt;
     int np = 0;
+    int np_kb = 0;          // CTAs of the last KB launch (its alpha partials sit in the second half of ctx->partials)
     int ncg = 0;
     double* row(int j) const { return V ? V + (int64_t)j * ldv : ring + (int64_t)(j % 3) * ld_int; }
 };
@@ -495,7 +406,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         r.kt.ctx = r.ctx;
         r.kt.on = (opts->profile != 0);
         if (r.kt.on) {   // create the pool outside the timed loop
-            while (r.ctx->event_pool.size() < (size_t)(2 * (4 + 2 * passes) * n + 8)) {
+            while (r.ctx->event_pool.size() < (size_t)(2 * (5 + 2 * passes) * n + 16)) {
                 cudaEvent_t e = nullptr;
                 LZ_CUDA(cudaEventCreate(&e));
                 r.ctx->event_pool.push_back(e);
@@ -509,8 +420,16 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     const double delta = opts->select_tol > 0.0 ? opts->select_tol : sqrt(eps);
     const double eps1 = eps * 1.5;      // noise floor of the omega recurrence
     const double psi = eps * sqrt(M_global);
-    enum { K_APPLY = 0, K_UPDATE = 1, K_DOTS = 2, K_GSUPD = 3, K_FUSED = 4, K_GSFUSED = 5, K_NKINDS = 6 };
+    enum { K_APPLY = 0, K_UPDATE = 1, K_DOTS = 2, K_GSUPD = 3, K_FUSED = 4, K_GSFUSED = 5, K_BORDER = 6, K_NKINDS = 7 };
     const bool allow_gs_fusion = passes == 2 && !(opts->flags & 1);
+    const bool gpu_sweep = (opts->flags & 2) != 0;       // Regular/Lanczos.py:236-238: self term dropped
+    const bool sel = (reorth == LZ_REORTH_SELECTIVE);
+    // alpha of the NEXT vector accumulated inside KB while that vector is in registers, plus a small border
+    // kernel for the edges that cross CTA tiles (stencil.cu): replaces KA2's full pass over the vector.  Not
+    // with full re-orthogonalisation (the sweep rewrites the vector, alpha must be taken afterwards anyway).
+    bool kb_alpha = recompute && reorth != LZ_REORTH_FULL && !(opts->flags & 4);
+    for (int s = 0; s < nl && kb_alpha; ++s)
+        kb_alpha = update_alpha_supported(R[s].op, R[s].V ? R[s].V : R[s].ring, R[s].V ? R[s].V : R[s].ring);
 
     // run `fn(shard)` on every local shard, on its device
     auto each = [&](auto&& fn) -> int {
@@ -529,10 +448,28 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         LZ_CHECK(each([&](ShardRun& r) { return launch(r, seq, (int)LZ_XCHG_PUSH); }));
         return each([&](ShardRun& r) { return launch(r, seq, (int)LZ_XCHG_COMBINE); });
     };
-    auto fin_scalar = [&](int kind, auto&& out_of, int jn, double tol, auto&& mag_of) -> int {
-        return exchange([&](ShardRun& r, unsigned long long seq, int mode) -> int {
-            fin_scalar_kernel<<<1, kThreads, 0, r.ctx->stream>>>(r.ctx->partials, r.np, r.st, r.pc, seq, mode, kind,
-                                                                 out_of(r), jn, tol, mag_of(r), nullptr);
+    // A kernel that ends in a reduction, with the scalar bookkeeping `op_of(shard)` folded into its tail
+    // (fin.cuh): produce(shard, tail) launches it.  One shard per process: the tail also does the cross-rank
+    // sum.  Several local shards: the tails push, then one combine kernel per shard.  `pred`: the kernel
+    // (and its combine) is predicated on the re-orthogonalisation flag of the step.
+    auto produce_fin = [&](auto&& op_of, auto&& produce, bool pred) -> int {
+        unsigned long long seq = 0;
+        if (team) seq = ++team->seq;
+        LZ_CHECK(each([&](ShardRun& r) {
+            FinTail t;
+            t.op = op_of(r);
+            t.ticket = r.ctx->tickets;
+            t.st = r.st;
+            t.pc = r.pc;
+            t.seq = seq;
+            t.mode = split ? (int)LZ_XCHG_PUSH : (int)LZ_XCHG_FUSED;
+            return produce(r, &t);
+        }));
+        if (!split) return LZ_OK;
+        return each([&](ShardRun& r) {
+            LZ_CUDA(launch_k(fin_scalar_kernel, dim3(1), dim3(kThreads), 0, r.ctx->stream, (const double*)r.ctx->partials,
+                             r.np, op_of(r), r.st, r.pc, seq, (int)LZ_XCHG_COMBINE,
+                             pred ? (const int*)(r.st.flags + 1) : (const int*)nullptr));
             ++launches;
             return LZ_OK;
         });
@@ -540,18 +477,61 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     auto peer_sync = [&](bool predicated) -> int {
         if (!team) return LZ_OK;
         return exchange([&](ShardRun& r, unsigned long long seq, int mode) -> int {
-            peer_sync_kernel<<<1, 32, 0, r.ctx->stream>>>(r.pc, seq, mode, predicated ? r.st.flags + 1 : nullptr);
+            LZ_CUDA(launch_k(peer_sync_kernel, dim3(1), dim3(32), 0, r.ctx->stream, r.pc, seq, mode,
+                             predicated ? (const int*)(r.st.flags + 1) : (const int*)nullptr));
             ++launches;
             return LZ_OK;
         });
     };
-    auto nul = [](ShardRun&) -> double* { return nullptr; };
+    auto op_alpha = [](double* out) { FinOp f; f.kind = FIN_ALPHA; f.out = out; return f; };
+    auto op_beta = [&](ShardRun& r, int jn, const double* mag, int omega_j) {
+        FinOp f;
+        f.kind = FIN_BETA;
+        f.jn = jn;
+        f.tol_rel = opts->breakdown_tol;
+        f.magnitude = mag;
+        if (omega_j >= 0) {
+            f.omega_j = omega_j;
+            f.om_cur = r.om_cur;
+            f.om_prev = r.om_prev;
+            f.delta = delta; f.eps1 = eps1; f.psi = psi;
+        }
+        return f;
+    };
+    // alpha of row jn from the in-tile partials KB left in the second half of the partials buffer (r.np of
+    // them) plus the border kernel's own
+    auto op_alpha_s2 = [](ShardRun& r, int jn) {
+        FinOp f;
+        f.kind = FIN_ALPHA_S2;
+        f.jn = jn;
+        f.out = r.st.alpha + jn;
+        f.extra = r.ctx->partials + kMaxPartials;
+        f.nextra = r.np_kb;
+        return f;
+    };
+    // border kernel of row jn (the vector KB just produced): the edges that cross CTA tiles, z-chunks and the
+    // slab top, whose upper ghost plane arrived with the beta exchange
+    auto alpha_border = [&](int jn) -> int {
+        return produce_fin([&](ShardRun& r) { return op_alpha_s2(r, jn); },
+                           [&](ShardRun& r, const FinTail* t) {
+                               bind_ghosts(team, r, jn & 1);
+                               r.kt.begin(K_BORDER);
+                               const int rc = launch_alpha_border(r.op, r.row(jn), r.ctx->partials, &r.np, t);
+                               r.kt.end();
+                               ++launches;
+                               return rc;
+                           }, false);
+    };
 
     LZ_CHECK(each([&](ShardRun& r) { LZ_CUDA(cudaEventRecord(r.ctx->ev_begin, r.ctx->stream)); return LZ_OK; }));
 
     // ---- start: |v0| ---------------------------------------------------------------------
-    LZ_CHECK(each([&](ShardRun& r) { ++launches; return launch_dot(r.ctx, r.v0, r.v0, r.M, r.ctx->partials, &r.np); }));
-    LZ_CHECK(fin_scalar(FIN_V0NORM, nul, 0, 0.0, nul));
+    LZ_CHECK(produce_fin([](ShardRun&) { FinOp f; f.kind = FIN_V0NORM; return f; },
+                         [&](ShardRun& r, const FinTail* t) {
+                             ++launches;
+                             return launch_dot(r.ctx, r.v0, r.v0, r.M, r.ctx->partials, &r.np, t);
+                         }, false));
+    bool alpha_known = false;            // alpha of the coming row already produced by KB + border kernel
     if (ref) {
         // pre-step (Lanczos.py:108-110): r = H q - (q.Hq) q with q = v0/|v0|; r becomes row 0.
         // Sharded: the ghost planes of v0 travel through the parity-1 buffers.
@@ -564,34 +544,41 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
             }));
             LZ_CHECK(peer_sync(false));
         }
-        LZ_CHECK(each([&](ShardRun& r) {
-            bind_ghosts(team, r, 1);
-            bind_gather(team, r, 1);
-            int l2 = 0;
-            const int rc = launch_apply_dot(r.op, r.v0, r.st.v0scale, recompute ? nullptr : r.w, r.ctx->partials,
-                                            &r.np, &l2, nullptr);
-            launches += l2;
-            return rc;
-        }));
-        LZ_CHECK(fin_scalar(FIN_ALPHA, [](ShardRun& r) { return r.st.alpha_pre; }, 0, 0.0, nul));
-        LZ_CHECK(each([&](ShardRun& r) {
-            HaloPush h = halo_for(team, r, 0);
-            if (recompute) {
-                StencilUpdate u;
-                u.ca = r.st.alpha_pre;
-                u.sa = r.st.v0scale;
-                u.halo = h;                       // KB stores the boundary planes of row 0 to the neighbours
-                int l2 = 0;
-                LZ_CHECK(launch_apply_update_norm(r.op, r.v0, r.st.v0scale, &u, r.row(0), r.ctx->partials, &r.np, &l2));
-                launches += l2;
-                return LZ_OK;
-            }
-            ++launches;
-            LZ_CHECK(launch_update_norm(r.ctx, r.w, r.v0, nullptr, r.st.alpha_pre, r.st.v0scale, nullptr, nullptr,
-                                        r.row(0), r.M, r.ctx->partials, &r.np, &h));
-            return push_ghosts(team, r, r.row(0), 0, nullptr, &launches);
-        }));
-        LZ_CHECK(fin_scalar(FIN_BETA, nul, 0, opts->breakdown_tol, [](ShardRun& r) { return r.st.alpha_pre; }));
+        LZ_CHECK(produce_fin([&](ShardRun& r) { return op_alpha(r.st.alpha_pre); },
+                             [&](ShardRun& r, const FinTail* t) {
+                                 bind_ghosts(team, r, 1);
+                                 bind_gather(team, r, 1);
+                                 int l2 = 0;
+                                 const int rc = launch_apply_dot(r.op, r.v0, r.st.v0scale, recompute ? nullptr : r.w,
+                                                                 r.ctx->partials, &r.np, &l2, nullptr, t);
+                                 launches += l2;
+                                 return rc;
+                             }, false));
+        LZ_CHECK(produce_fin([&](ShardRun& r) { return op_beta(r, 0, r.st.alpha_pre, -1); },
+                             [&](ShardRun& r, const FinTail* t) {
+                                 HaloPush h = halo_for(team, r, 0);
+                                 if (recompute) {
+                                     StencilUpdate u;
+                                     u.ca = r.st.alpha_pre;
+                                     u.sa = r.st.v0scale;
+                                     u.halo = h;        // KB stores the boundary planes of row 0 to the neighbours
+                                     if (kb_alpha) u.alpha_partials = r.ctx->partials + kMaxPartials;
+                                     int l2 = 0;
+                                     LZ_CHECK(launch_apply_update_norm(r.op, r.v0, r.st.v0scale, &u, r.row(0), r.ctx->partials,
+                                                                       &r.np, &l2, t));
+                                     r.np_kb = r.np;
+                                     launches += l2;
+                                     return LZ_OK;
+                                 }
+                                 ++launches;
+                                 LZ_CHECK(launch_update_norm(r.ctx, r.w, r.v0, nullptr, r.st.alpha_pre, r.st.v0scale, nullptr,
+                                                             nullptr, r.row(0), r.M, r.ctx->partials, &r.np, &h, t));
+                                 return push_ghosts(team, r, r.row(0), 0, nullptr, &launches);
+                             }, false));
+        if (kb_alpha) {
+            LZ_CHECK(alpha_border(0));
+            alpha_known = true;
+        }
     } else {
         LZ_CHECK(each([&](ShardRun& r) {
             LZ_CUDA(cudaMemcpyAsync(r.row(0), r.v0, (size_t)r.M * 8, cudaMemcpyDeviceToDevice, r.ctx->stream));
@@ -608,20 +595,25 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     if (fused) {
         ShardRun& r = R[0];
         cudaStream_t q = r.ctx->stream;
-        const bool sel = (reorth == LZ_REORTH_SELECTIVE);
         const int* flag = sel ? r.st.flags + 1 : nullptr;
         PeerComm solo;                       // world = 1
         double* ucur = r.w;
         double* unxt = r.w2;
         int l2 = 0;
+        auto alpha_s2 = [&](int jn, const int* fl) {
+            FinOp f;
+            f.kind = FIN_ALPHA_S2;
+            f.jn = jn;
+            f.out = r.st.alpha + jn;
+            fin_scalar_kernel<<<1, kThreads, 0, q>>>(r.ctx->partials, r.np, f, r.st, solo, 0, LZ_XCHG_FUSED, fl);
+            ++launches;
+        };
         // u_0 = H r_0 (un-normalised), alpha_0 = s_0^2 r_0.u_0
         r.kt.begin(K_APPLY);
         LZ_CHECK(launch_apply_dot(r.op, r.row(0), nullptr, ucur, r.ctx->partials, &r.np, &l2, nullptr));
         r.kt.end();
         launches += l2;
-        fin_scalar_kernel<<<1, kThreads, 0, q>>>(r.ctx->partials, r.np, r.st, solo, 0, LZ_XCHG_FUSED, FIN_ALPHA_S2,
-                                                 r.st.alpha, 0, 0.0, nullptr, nullptr);
-        ++launches;
+        alpha_s2(0, nullptr);
         for (int j = 0; j < n; ++j) {
             if (sel && j > 0) {
                 // predicated on the device flag: sweep q_j, then recompute u_j = H q_j and alpha_j
@@ -639,9 +631,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
                 }
                 LZ_CHECK(launch_apply_dot(r.op, r.row(j), nullptr, ucur, r.ctx->partials, &r.np, &l2, flag));
                 launches += l2;
-                fin_scalar_kernel<<<1, kThreads, 0, q>>>(r.ctx->partials, r.np, r.st, solo, 0, LZ_XCHG_FUSED,
-                                                         FIN_ALPHA_S2, r.st.alpha + j, j, 0.0, nullptr, flag);
-                ++launches;
+                alpha_s2(j, flag);
             }
             if (j + 1 < n) {
                 r.kt.begin(K_FUSED);
@@ -665,16 +655,15 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     for (int j = 0; !fused && j < n; ++j) {
         const int par = j & 1;
         // ---- Gram-Schmidt sweeps of q_j against the rows before it ---------------------------
-        const bool maybe_reorth = (reorth == LZ_REORTH_FULL) || (reorth == LZ_REORTH_SELECTIVE && j > 0);
-        if (maybe_reorth && (j > 0 || ref)) {
-            const bool sel = (reorth == LZ_REORTH_SELECTIVE);
+        const bool maybe_reorth = ((reorth == LZ_REORTH_FULL) || (sel && j > 0)) && (j > 0 || ref);
+        if (maybe_reorth) {
             bool pushed = false;
             // CGS2: the update of the first sweep and the dots of the second read the same j rows -
             // one fused kernel (K4c) when the staged tile fits shared memory
             bool fuse = allow_gs_fusion && j >= 1;
             for (int s = 0; s < nl && fuse; ++s) fuse = cgs_update_dots_supported(R[s].V, R[s].ldv, j, R[s].row(j));
             for (int p = 0; p < passes; ++p) {
-                const int ref_form = (ref && p == 0) ? 1 : 0;
+                const int ref_form = (ref && p == 0 && !gpu_sweep) ? 1 : 0;   // (2 - |v|^2) form incl. the self term
                 const int nrows = ref_form ? j + 1 : j;      // the reference's sum includes row j itself
                 if (nrows == 0) continue;
                 if (!(fuse && p == 1)) {
@@ -688,9 +677,10 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
                     }));
                 }
                 LZ_CHECK(exchange([&](ShardRun& r, unsigned long long seq, int mode) -> int {
-                    fin_ip_kernel<<<1, kThreads, 0, r.ctx->stream>>>(r.gs_part, r.ncg, j, ref_form, ref_form, r.st, r.pc,
-                                                                     seq, mode, sel ? r.st.flags + 1 : nullptr,
-                                                                     (p == 0 && mode != LZ_XCHG_PUSH) ? 1 : 0);
+                    LZ_CUDA(launch_k(fin_ip_kernel, dim3(1), dim3(kThreads), 0, r.ctx->stream, (const double*)r.gs_part,
+                                     r.ncg, j, ref_form, ref_form, r.st, r.pc, seq, mode,
+                                     sel ? (const int*)(r.st.flags + 1) : (const int*)nullptr,
+                                     (p == 0 && mode != LZ_XCHG_PUSH) ? 1 : 0));
                     ++launches;
                     return LZ_OK;
                 }));
@@ -721,56 +711,66 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
             if (pushed) LZ_CHECK(peer_sync(sel));
         }
         // ---- w = H q_j, alpha_j = q_j . w ------------------------------------------------------
-        LZ_CHECK(each([&](ShardRun& r) {
-            bind_ghosts(team, r, par);
-            bind_gather(team, r, par);
-            int l2 = 0;
-            r.kt.begin(K_APPLY);
-            const int rc = launch_apply_dot(r.op, r.row(j), r.st.scale + j, recompute ? nullptr : r.w, r.ctx->partials,
-                                            &r.np, &l2, nullptr);
-            r.kt.end();
-            launches += l2;
-            return rc;
-        }));
-        LZ_CHECK(fin_scalar(FIN_ALPHA, [j](ShardRun& r) { return r.st.alpha + j; }, 0, 0.0, nul));
+        // (alpha_j known from KB + border kernel of the previous step: only if a sweep just rewrote row j)
+        if (!alpha_known || maybe_reorth) {
+            const bool pred = alpha_known;
+            LZ_CHECK(produce_fin([&](ShardRun& r) { return op_alpha(r.st.alpha + j); },
+                                 [&](ShardRun& r, const FinTail* t) {
+                                     bind_ghosts(team, r, par);
+                                     bind_gather(team, r, par);
+                                     int l2 = 0;
+                                     r.kt.begin(K_APPLY);
+                                     const int rc = launch_apply_dot(r.op, r.row(j), r.st.scale + j, recompute ? nullptr : r.w,
+                                                                     r.ctx->partials, &r.np, &l2,
+                                                                     pred ? r.st.flags + 1 : nullptr, t);
+                                     r.kt.end();
+                                     launches += l2;
+                                     return rc;
+                                 }, pred));
+        } else {
+            LZ_CHECK(each([&](ShardRun& r) { bind_ghosts(team, r, par); bind_gather(team, r, par); return LZ_OK; }));
+        }
         // ---- r = w - alpha_j q_j - beta_j q_{j-1}; beta_{j+1} = |r| --------------------------
-        LZ_CHECK(each([&](ShardRun& r) {
-            double* out = (j + 1 < n) ? r.row(j + 1) : r.w;
-            HaloPush h = (j + 1 < n) ? halo_for(team, r, (j + 1) & 1) : HaloPush{};
-            if (recompute) {
-                StencilUpdate u;
-                u.b = j > 0 ? r.row(j - 1) : nullptr;
-                u.ca = r.st.alpha + j;
-                u.sa = r.st.scale + j;
-                u.cb = r.st.beta + j;
-                u.sb = j > 0 ? r.st.scale + j - 1 : nullptr;
-                u.halo = h;
-                int l2 = 0;
-                r.kt.begin(K_UPDATE);
-                const int rc2 = launch_apply_update_norm(r.op, r.row(j), r.st.scale + j, &u, out, r.ctx->partials,
-                                                         &r.np, &l2);
-                r.kt.end();
-                launches += l2;
-                return rc2;
-            }
-            r.kt.begin(K_UPDATE);
-            const int rc = launch_update_norm(r.ctx, r.w, r.row(j), j > 0 ? r.row(j - 1) : nullptr, r.st.alpha + j,
-                                              r.st.scale + j, r.st.beta + j, j > 0 ? r.st.scale + j - 1 : nullptr,
-                                              out, r.M, r.ctx->partials, &r.np, &h);
-            r.kt.end();
-            ++launches;
-            LZ_CHECK(rc);
-            if (j + 1 < n) return push_ghosts(team, r, out, (j + 1) & 1, nullptr, &launches);
-            return LZ_OK;
-        }));
-        LZ_CHECK(fin_scalar(FIN_BETA, nul, j + 1, opts->breakdown_tol, [](ShardRun& r) { return r.st.alpha; }));
-        if (reorth == LZ_REORTH_SELECTIVE && j + 1 < n) {
-            LZ_CHECK(each([&](ShardRun& r) {
-                omega_kernel<<<1, kThreads, 0, r.ctx->stream>>>(r.st, j, r.om_cur, r.om_prev, delta, eps1, psi);
-                ++launches;
-                std::swap(r.om_cur, r.om_prev);
-                return LZ_OK;
-            }));
+        const bool want_alpha = kb_alpha && (j + 1 < n);
+        LZ_CHECK(produce_fin([&](ShardRun& r) { return op_beta(r, j + 1, r.st.alpha, (sel && j + 1 < n) ? j : -1); },
+                             [&](ShardRun& r, const FinTail* t) {
+                                 double* out = (j + 1 < n) ? r.row(j + 1) : r.w;
+                                 HaloPush h = (j + 1 < n) ? halo_for(team, r, (j + 1) & 1) : HaloPush{};
+                                 if (recompute) {
+                                     StencilUpdate u;
+                                     u.b = j > 0 ? r.row(j - 1) : nullptr;
+                                     u.ca = r.st.alpha + j;
+                                     u.sa = r.st.scale + j;
+                                     u.cb = r.st.beta + j;
+                                     u.sb = j > 0 ? r.st.scale + j - 1 : nullptr;
+                                     u.halo = h;
+                                     if (want_alpha) u.alpha_partials = r.ctx->partials + kMaxPartials;
+                                     int l2 = 0;
+                                     r.kt.begin(K_UPDATE);
+                                     const int rc2 = launch_apply_update_norm(r.op, r.row(j), r.st.scale + j, &u, out,
+                                                                              r.ctx->partials, &r.np, &l2, t);
+                                     r.kt.end();
+                                     r.np_kb = r.np;
+                                     launches += l2;
+                                     return rc2;
+                                 }
+                                 r.kt.begin(K_UPDATE);
+                                 const int rc = launch_update_norm(r.ctx, r.w, r.row(j), j > 0 ? r.row(j - 1) : nullptr,
+                                                                   r.st.alpha + j, r.st.scale + j, r.st.beta + j,
+                                                                   j > 0 ? r.st.scale + j - 1 : nullptr, out, r.M,
+                                                                   r.ctx->partials, &r.np, &h, t);
+                                 r.kt.end();
+                                 ++launches;
+                                 LZ_CHECK(rc);
+                                 if (j + 1 < n) return push_ghosts(team, r, out, (j + 1) & 1, nullptr, &launches);
+                                 return LZ_OK;
+                             }, false));
+        if (sel && j + 1 < n)
+            for (int s = 0; s < nl; ++s) std::swap(R[s].om_cur, R[s].om_prev);
+        alpha_known = false;
+        if (want_alpha) {
+            LZ_CHECK(alpha_border(j + 1));
+            alpha_known = true;
         }
     }
     LZ_CHECK(each([&](ShardRun& r) {
@@ -801,8 +801,8 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     if (row_scale_host)
         for (int j = 0; j < n; ++j) row_scale_host[j] = h_scale[j];
     float ms = 0.f;
-    float kms[K_NKINDS] = {0, 0, 0, 0, 0, 0};
-    int kcnt[K_NKINDS] = {0, 0, 0, 0, 0, 0};
+    float kms[K_NKINDS] = {};
+    int kcnt[K_NKINDS] = {};
     for (int s = 0; s < nl; ++s) {
         ShardRun& r = R[s];
         if (nl > 1) LZ_CUDA(cudaSetDevice(r.ctx->device));
@@ -843,6 +843,8 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         info->fused_ms = kms[K_FUSED];   info->fused_launches = kcnt[K_FUSED];
         info->step_kernel = fused ? 2 : (recompute ? 3 : 1);
         info->gsfused_ms = kms[K_GSFUSED]; info->gsfused_launches = kcnt[K_GSFUSED];
+        info->border_ms = kms[K_BORDER]; info->border_launches = kcnt[K_BORDER];
+        info->alpha_in_update = kb_alpha ? 1 : 0;
     }
     return status;
 }

@@ -13,15 +13,23 @@
 // release semantics at system scope; a consumer spins (acquire, system scope) until all world
 // flags of its own buffer equal seq and adds the payloads in rank order - so the result is
 // bit-identical on every rank and independent of arrival order.  A rank can run at most one
-// reduction ahead of a peer (it needs the peer's next payload to go further), so 4 slots are
-// more than enough to never overwrite an unconsumed payload.
+// EXECUTED reduction ahead of a peer (it needs the peer's next payload to go further).  Sequence
+// numbers are handed out on the host for every exchange that is enqueued, including the ones whose
+// kernels are predicated off on the device (selective re-orthogonalisation: the Gram-Schmidt
+// exchanges of a step that does not fire return without publishing).  Between two executed
+// exchanges at most kMaxSkippedRun numbers are skipped, so the payload a fast rank writes while a
+// slow peer still reads exchange `a` carries a number in (a, a + kMaxSkippedRun + 1]: the ring must
+// be longer than that span for the two never to share a slot.
 #pragma once
 #include "common.cuh"
 
 namespace lz {
 
 constexpr int kMaxWorld = 16;
-constexpr int kPeerSlots = 4;
+constexpr int kMaxSkippedRun = 6;   // lanczos.cu: per step <= 2 fin_ip + peer_sync + the alpha of the re-swept row
+                                    // (all predicated on the same flag), rounded up
+constexpr int kPeerSlots = 8;
+static_assert(kPeerSlots >= kMaxSkippedRun + 2, "a skipped run of exchanges must not wrap the slot ring");
 
 struct PeerComm {
     int world = 1;

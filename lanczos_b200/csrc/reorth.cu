@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(kThreads)
 cgs_dots_kernel(const double* __restrict__ V, int64_t ldv, int nrows,
                 const double* __restrict__ target, int64_t M, int64_t chunk, int nrb, int ncg,
                 int vec_ok, double* __restrict__ part, const int* __restrict__ flag) {
+    pdl_prologue();
     if (flag && *flag == 0) return;
     __shared__ double red[kWarps];
     const int rb = blockIdx.x % nrb;
@@ -95,9 +96,8 @@ int launch_cgs_dots(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, const 
     chunk = (chunk + 2 * kThreads - 1) / (2 * kThreads) * (2 * kThreads);   // multiple of 512 columns
     ncg = (M + chunk - 1) / chunk;
     const int vec_ok = ((((uintptr_t)V | (uintptr_t)target) & 15) == 0) && ((ldv & 1) == 0);
-    cgs_dots_kernel<<<(unsigned)(nrb * ncg), kThreads, 0, ctx->stream>>>(
-        V, ldv, nrows, target, M, chunk, nrb, (int)ncg, vec_ok, part, flag_dev);
-    LZ_CUDA(cudaGetLastError());
+    LZ_CUDA(launch_k(cgs_dots_kernel, dim3((unsigned)(nrb * ncg)), dim3(kThreads), 0, ctx->stream,
+                     V, ldv, nrows, target, M, chunk, nrb, (int)ncg, vec_ok, part, flag_dev));
     if (ncg_out) *ncg_out = (int)ncg;
     return LZ_OK;
 }
@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(kThreads)
 cgs_update_kernel(const double* __restrict__ V, int64_t ldv, int nrows, const double* target,
                   const double* __restrict__ coef, const double* __restrict__ cself_p, double* out,
                   int64_t M, int vec_ok, const int* __restrict__ flag, const HaloPush halo) {
+    pdl_prologue();
     if (flag && *flag == 0) return;
     __shared__ double sc[kCoefSmem];
     const int ns = min(nrows, kCoefSmem);
@@ -183,9 +184,8 @@ int launch_cgs_update(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, cons
         vec_ok = vec_ok && (((uintptr_t)h.lo_dst | (uintptr_t)h.hi_dst) & 15) == 0 && ((h.plane & 1) == 0) &&
                  ((M & 1) == 0);
     }
-    cgs_update_kernel<<<grid, kThreads, 0, ctx->stream>>>(V, ldv, nrows, target, coef_dev, cself_dev, out,
-                                                          M, vec_ok, flag_dev, h);
-    LZ_CUDA(cudaGetLastError());
+    LZ_CUDA(launch_k(cgs_update_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, V, ldv, nrows, target,
+                     coef_dev, cself_dev, out, M, vec_ok, flag_dev, h));
     return LZ_OK;
 }
 
@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(TC)
 cgs_update_dots_kernel(const double* __restrict__ V, int64_t ldv, int k, double* target,
                        const double* __restrict__ coef, const double* __restrict__ cself_p, int64_t M,
                        int64_t ntiles, double* __restrict__ part, const int* __restrict__ flag) {
+    pdl_prologue();
     if (flag && *flag == 0) return;
     extern __shared__ __align__(128) double sm[];
     double* S = sm;                          // [k + 1][TC]: rows 0..k-1 of the basis, row k = v
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(TC)
 cgs_update_dots_tma_kernel(const __grid_constant__ CUtensorMap tmap, int k, double* target,
                            const double* __restrict__ coef, const double* __restrict__ cself_p, int64_t M,
                            int64_t ntiles, double* __restrict__ part, const int* __restrict__ flag) {
+    pdl_prologue();
     if (flag && *flag == 0) return;
     extern __shared__ __align__(128) double sm[];
     const size_t stage_d = (size_t)(k + 1) * TC;     // TC * 8 is a multiple of 128 B: every stage is 128-byte aligned
@@ -438,11 +440,11 @@ int launch_cgs_update_dots(lz_ctx* ctx, const double* V, int64_t ldv, int k, dou
     if (tma) {
         void* targs[] = {(void*)&tmap, (void*)&kk, (void*)&target, (void*)&coef_dev, (void*)&cself_dev,
                          (void*)&M, (void*)&ntiles, (void*)&part, (void*)&flag_dev};
-        LZ_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(c.tc), targs, c.smem, ctx->stream));
+        LZ_CUDA(launch_fn(fn, dim3(grid), dim3(c.tc), c.smem, ctx->stream, targs));
     } else {
         void* args[] = {(void*)&V, (void*)&ldv, (void*)&kk, (void*)&target, (void*)&coef_dev, (void*)&cself_dev,
                         (void*)&M, (void*)&ntiles, (void*)&part, (void*)&flag_dev};
-        LZ_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(c.tc), args, c.smem, ctx->stream));
+        LZ_CUDA(launch_fn(fn, dim3(grid), dim3(c.tc), c.smem, ctx->stream, args));
     }
     if (ncg_out) *ncg_out = grid;
     return LZ_OK;

@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(kThreads)
 spmv_csr_dot_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                     const double* __restrict__ data, const double* __restrict__ x,
                     const double* __restrict__ scale, double* __restrict__ y, int64_t M,
-                    double* __restrict__ partials, const double* __restrict__ xg) {
+                    double* __restrict__ partials, const double* __restrict__ xg, const FinTail fin) {
+    pdl_prologue();
     __shared__ double red[kWarps];
     constexpr int RPW = 32 / T;                       // rows per warp
     // sharded operator: columns >= M are ghost entries that live in the exchange buffer
@@ -56,6 +57,7 @@ spmv_csr_dot_kernel(const int32_t* __restrict__ indptr, const int32_t* __restric
     }
     const double tot = block_sum(acc, red);
     if (threadIdx.x == 0 && partials) partials[blockIdx.x] = tot;
+    fin_tail(fin, partials, red);
 }
 
 __device__ __forceinline__ int32_t ld_stream_i32(const int32_t* p) {
@@ -77,7 +79,8 @@ spmv_sell_dot_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __res
                      const double* __restrict__ val, const int32_t* __restrict__ row_of,
                      const double* __restrict__ x, const double* __restrict__ scale,
                      double* __restrict__ y, int64_t nchunks, double* __restrict__ partials,
-                     const double* __restrict__ xg, int32_t M, int span) {
+                     const double* __restrict__ xg, int32_t M, int span, const FinTail fin) {
+    pdl_prologue();
     __shared__ double red[kWarps];
     const double s = scale ? __ldg(scale) : 1.0;
     const int lane = threadIdx.x & 31;
@@ -122,12 +125,14 @@ spmv_sell_dot_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __res
     }
     const double tot = block_sum(acc, red);
     if (threadIdx.x == 0 && partials) partials[blockIdx.x] = tot;
+    fin_tail(fin, partials, red);
 }
 
 int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
-                    double* partials, int* nparts, const int* flag_dev) {
+                    double* partials, int* nparts, const int* flag_dev, const FinTail* fin) {
     (void)flag_dev;   // predicated applies exist only on the structured-grid fused path
     lz_ctx* ctx = op->ctx;
+    const FinTail ft = fin ? *fin : FinTail{};
     const int64_t cap = std::min<int64_t>((int64_t)ctx->sms * 8, kMaxPartials);
     if (op->kind == LZ_OP_CSR) {
         const lz_csr& c = op->csr;
@@ -135,8 +140,8 @@ int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double*
         const int64_t rows_per_cta = (int64_t)kWarps * (32 / T);
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((op->M + rows_per_cta - 1) / rows_per_cta, cap));
 #define LZ_CSR_LAUNCH(TT)                                                                          \
-    spmv_csr_dot_kernel<TT><<<grid, kThreads, 0, ctx->stream>>>(c.indptr, c.indices, c.data, x,    \
-                                                                scale_dev, y, op->M, partials, op->xghost)
+    LZ_CUDA(launch_k(spmv_csr_dot_kernel<TT>, dim3(grid), dim3(kThreads), 0, ctx->stream, c.indptr,  \
+                     c.indices, c.data, x, scale_dev, y, op->M, partials, op->xghost, ft))
         switch (T) {
             case 2: LZ_CSR_LAUNCH(2); break;
             case 4: LZ_CSR_LAUNCH(4); break;
@@ -157,10 +162,8 @@ int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double*
     span = std::max(span, kWarps);
     const int64_t nspans = (sl.nchunks + span - 1) / span;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nspans, std::min<int64_t>((int64_t)ctx->sms * 16, kMaxPartials)));
-    spmv_sell_dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(sl.chunk_off, sl.col, sl.val, sl.row_of, x,
-                                                             scale_dev, y, sl.nchunks, partials, op->xghost,
-                                                             (int32_t)op->M, span);
-    LZ_CUDA(cudaGetLastError());
+    LZ_CUDA(launch_k(spmv_sell_dot_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, sl.chunk_off, sl.col,
+                     sl.val, sl.row_of, x, scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, span, ft));
     if (nparts) *nparts = grid;
     return LZ_OK;
 }
@@ -178,6 +181,7 @@ struct GhostPushArgs {
 
 __global__ void __launch_bounds__(kThreads)
 ghost_push_kernel(const double* __restrict__ x, const GhostPushArgs g, const int* __restrict__ flag) {
+    pdl_prologue();
     if (flag && *flag == 0) return;
     const int tid = blockIdx.x * kThreads + threadIdx.x;
     const int nthr = gridDim.x * kThreads;
@@ -199,8 +203,7 @@ int launch_ghost_push(lz_ctx* ctx, const double* x, const int32_t* send_idx, int
     for (int q = world + 1; q < 17; ++q) g.seg_start[q] = nsend;
     for (int q = 0; q < 16; ++q) g.dst[q] = q < world ? dst[q] : nullptr;
     const int grid = std::max(1, std::min((nsend + kThreads - 1) / kThreads, ctx->sms * 4));
-    ghost_push_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, g, flag_dev);
-    LZ_CUDA(cudaGetLastError());
+    LZ_CUDA(launch_k(ghost_push_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, g, flag_dev));
     return LZ_OK;
 }
 

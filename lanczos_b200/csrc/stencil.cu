@@ -20,6 +20,7 @@
 // the new z+1 values and two for the y-1 / y+1 rows (L1 hits except on the two tile-edge
 // rows); x neighbours travel by warp shuffle, only the two edge lanes load them.  HBM
 // traffic is the compulsory 8 B read + 8 B write per point (+ 2/zc for the chunk halo).
+#include <stdlib.h>
 #include "internal.h"
 
 namespace lz {
@@ -44,8 +45,10 @@ struct StencilArgs {
     double* halo_hi;      // plane nz-1 to the upper neighbour's (NVLink peer stores, as K3 does)
     const int* skip;      // device flag, nullptr or *skip != 0: run
     double* partials;
+    double* alpha_partials;   // KB with ALPHA: partial of out . H out over the edges inside the CTA's tiles
     int tiles_x, tiles_y, chunks_z, zc;
     int64_t nitems;
+    FinTail fin;          // what the last CTA does with the summed partials (fin.cuh)
 };
 
 template <int VEC>
@@ -82,11 +85,25 @@ __device__ __forceinline__ void zero_vec(double (&v)[VEC]) {
 #ifndef LZ_KB_MINBLOCKS
 #define LZ_KB_MINBLOCKS 4
 #endif
-template <int VEC, bool HAS_Y, bool HAS_Z, bool HAS_DIAG, int MODE>
+// ALPHA (MODE 2, grids made of whole 64 x 8 tiles): alpha of the vector being produced,
+//     out . H out = sum_i (c + d_i) out_i^2 + 2 sum_edges o out_i out_j,
+// is accumulated while `out` is in registers, for every edge whose two ends this CTA produces: the edge
+// inside a thread's pair and to the next lane (shuffle), to the row of the next warp (one shared-memory
+// row exchange per plane), to the previous plane of the z-chunk (two registers).  The edges that leave the
+// tile (lane 31 -> next tile, warp 7 -> next tile, last plane of a chunk -> next chunk / wrap / ghost plane)
+// are left to stencil_alpha_border_kernel: ~3.5 B per point instead of KA2's 8.
+template <int VEC, bool HAS_Y, bool HAS_Z, bool HAS_DIAG, int MODE, bool ALPHA = false>
 __global__ void __launch_bounds__(kThreads, MODE == 2 ? LZ_KB_MINBLOCKS : (MODE == 1 ? LZ_KA_MINBLOCKS : LZ_K1_MINBLOCKS))
 stencil_apply_dot_kernel(const StencilArgs a) {
+    pdl_prologue();
     if (a.skip && *a.skip == 0) return;
     __shared__ double red[kWarps];
+    __shared__ double2 xrow[ALPHA ? 2 : 1][ALPHA ? kWarps : 1][ALPHA ? 32 : 1];   // rows of `out`, double-buffered
+    double acc2 = 0.0;
+    double po[VEC];                      // `out` of the previous plane of this chunk
+    zero_vec<VEC>(po);
+    int it = 0;                          // running plane count of this CTA: parity of the exchange buffer
+    const double ox2 = 2.0 * a.ox, oy2 = 2.0 * a.oy, oz2 = 2.0 * a.oz;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double s = a.scale ? __ldg(a.scale) : 1.0;
     const double fa = MODE == 2 ? (a.ca ? __ldg(a.ca) : 1.0) * (a.sa ? __ldg(a.sa) : 1.0) : 0.0;
@@ -194,6 +211,29 @@ stencil_apply_dot_kernel(const StencilArgs a) {
                     if constexpr (VEC == 2) st_stream2(py, make_double2(out[0], out[1]));
                     else st_stream1(py, out[0]);
                 }
+                if constexpr (ALPHA && VEC == 2) {
+                    // every thread of the CTA is active here (whole tiles): barriers are uniform
+                    acc2 = fma((a.c + dg[0]) * out[0], out[0], acc2);
+                    acc2 = fma((a.c + dg[1]) * out[1], out[1], acc2);
+                    acc2 = fma(ox2 * out[0], out[1], acc2);
+                    const double nxt = __shfl_down_sync(0xffffffffu, out[0], 1);
+                    if (lane < 31) acc2 = fma(ox2 * out[1], nxt, acc2);
+                    if (z > z0) {
+                        acc2 = fma(oz2 * po[0], out[0], acc2);
+                        acc2 = fma(oz2 * po[1], out[1], acc2);
+                    }
+                    po[0] = out[0];
+                    po[1] = out[1];
+                    const int buf = it & 1;
+                    ++it;
+                    xrow[buf][warp][lane] = make_double2(out[0], out[1]);
+                    __syncthreads();
+                    if (warp < kWarps - 1) {
+                        const double2 up = xrow[buf][warp + 1][lane];
+                        acc2 = fma(oy2 * out[0], up.x, acc2);
+                        acc2 = fma(oy2 * out[1], up.y, acc2);
+                    }
+                }
                 if (MODE == 2) {
                     if (a.halo_lo && z == 0) {
                         if constexpr (VEC == 2) *reinterpret_cast<double2*>(a.halo_lo + off_c) = make_double2(out[0], out[1]);
@@ -210,8 +250,85 @@ stencil_apply_dot_kernel(const StencilArgs a) {
             pc += a.plane;
         }
     }
+    if constexpr (ALPHA) {
+        const double t2 = block_sum(acc2, red);
+        if (threadIdx.x == 0) a.alpha_partials[blockIdx.x] = t2;
+    }
     const double tot = block_sum(acc_alpha, red);
     if (threadIdx.x == 0 && a.partials) a.partials[blockIdx.x] = tot;
+    fin_tail(a.fin, a.partials, red);
+}
+
+// The edges of out . H out that stencil_apply_dot_kernel<ALPHA> could not reach (see there), for a vector v
+// on a grid of whole 64 x 8 tiles walked in z-chunks of zc planes:
+//   Y: rows 8t+7 -> 8t+8 (wrap: periodic only)        nz * tiles_y * nx products, two full rows per pair
+//   Z: plane (chunk end - 1) -> next plane (or the plane above the slab: wrap / ghost / none)
+//   X: columns 64t+63 -> 64t+64 (wrap: periodic only)  nz * ny * tiles_x products
+// One flat index space, grid-stride, double2 loads for Y and Z; partials[cta] = 2 * sum o v_i v_j.
+struct BorderArgs {
+    int nx, ny, nz, periodic;
+    int tiles_x, tiles_y, zc, chunks_z;
+    int64_t plane;
+    double ox2, oy2, oz2;
+    const double* v;
+    const double* zhi;    // plane above the slab (nullptr: none)
+    double* partials;
+    FinTail fin;
+};
+
+__global__ void __launch_bounds__(kThreads)
+stencil_alpha_border_kernel(const BorderArgs a) {
+    pdl_prologue();
+    __shared__ double red[kWarps];
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * kThreads;
+    const int hx = a.nx >> 1;                                    // double2 per row
+    const int ty_pairs = (a.periodic || a.tiles_y == 0) ? a.tiles_y : a.tiles_y - 1;   // Dirichlet: no wrap pair
+    const int tx_pairs = a.periodic ? a.tiles_x : a.tiles_x - 1;
+    const int64_t WY = (int64_t)a.nz * ty_pairs * hx;
+    const int zpairs = (a.zhi != nullptr) ? a.chunks_z : a.chunks_z - 1;
+    const int64_t WZ = (int64_t)zpairs * (a.plane >> 1);
+    const int64_t WX = (int64_t)a.nz * a.ny * tx_pairs;
+    double accy = 0.0, accz = 0.0, accx = 0.0;
+#pragma unroll 2
+    for (int64_t i = tid; i < WY; i += nthr) {
+        const int x2 = (int)(i % hx);
+        const int64_t t = i / hx;
+        const int ty = (int)(t % ty_pairs);
+        const int z = (int)(t / ty_pairs);
+        const int ya = ty * kWarps + kWarps - 1;
+        const int yb = (ya + 1 == a.ny) ? 0 : ya + 1;
+        const double* pz = a.v + (int64_t)z * a.plane + 2 * x2;
+        const double2 p = ld_stream2(pz + (int64_t)ya * a.nx);
+        const double2 q = ld_stream2(pz + (int64_t)yb * a.nx);
+        accy = fma(p.x, q.x, accy);
+        accy = fma(p.y, q.y, accy);
+    }
+#pragma unroll 2
+    for (int64_t i = tid; i < WZ; i += nthr) {
+        const int64_t hp = a.plane >> 1;
+        const int64_t e2 = i % hp;
+        const int cz = (int)(i / hp);
+        const int za = min((cz + 1) * a.zc, a.nz) - 1;
+        const double* pa = a.v + (int64_t)za * a.plane + 2 * e2;
+        const double* pb = (za + 1 < a.nz) ? pa + a.plane : a.zhi + 2 * e2;
+        const double2 p = ld_stream2(pa);
+        const double2 q = ld_stream2(pb);
+        accz = fma(p.x, q.x, accz);
+        accz = fma(p.y, q.y, accz);
+    }
+#pragma unroll 2
+    for (int64_t i = tid; i < WX; i += nthr) {
+        const int tx = (int)(i % tx_pairs);
+        const int64_t row = i / tx_pairs;                        // y + ny * z
+        const int xa = tx * 64 + 63;
+        const int xb = (xa + 1 == a.nx) ? 0 : xa + 1;
+        const double* pr = a.v + row * a.nx;
+        accx = fma(ld_stream1(pr + xa), ld_stream1(pr + xb), accx);
+    }
+    const double tot = block_sum(fma(a.oy2, accy, fma(a.oz2, accz, a.ox2 * accx)), red);
+    if (threadIdx.x == 0) a.partials[blockIdx.x] = tot;
+    fin_tail(a.fin, a.partials, red);
 }
 
 // KA2: alpha_j alone for a full 3-D 7-point operator, from the symmetric form
@@ -231,6 +348,7 @@ stencil_apply_dot_kernel(const StencilArgs a) {
 template <bool HAS_DIAG>
 __global__ void __launch_bounds__(kThreads, LZ_KA2_MINBLOCKS)
 stencil_alpha_kernel(const StencilArgs a) {
+    pdl_prologue();
     if (a.skip && *a.skip == 0) return;
     __shared__ double red[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -315,6 +433,7 @@ stencil_alpha_kernel(const StencilArgs a) {
     }
     const double tot = block_sum(acc * (s * s), red);
     if (threadIdx.x == 0 && a.partials) a.partials[blockIdx.x] = tot;
+    fin_tail(a.fin, a.partials, red);
 }
 
 // KA2, lean form for grids made of whole tiles (nx % 64 == 0, ny % 16 == 0, plane < 4 GB): every
@@ -336,6 +455,7 @@ template <bool HAS_DIAG>
 __global__ void __launch_bounds__(kThreads, LZ_KA2F_MINBLOCKS)
 stencil_alpha_fast_kernel(const StencilArgs a) {
     constexpr int WX = LZ_KA2_WX;
+    pdl_prologue();
     if (a.skip && *a.skip == 0) return;
     __shared__ double red[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -433,6 +553,7 @@ stencil_alpha_fast_kernel(const StencilArgs a) {
     }
     const double tot = block_sum(acc * (s * s), red);
     if (threadIdx.x == 0 && a.partials) a.partials[blockIdx.x] = tot;
+    fin_tail(a.fin, a.partials, red);
 }
 
 // KB with its two HBM streams (own values of the plane above, v_{j-1}) fetched 2-4 planes ahead by
@@ -475,20 +596,22 @@ static const void* pick_kernel(bool has_y, bool has_z, bool has_diag, int mode) 
 }
 
 static int launch_stencil(lz_op* op, int mode, const double* x, const double* scale_dev, double* y,
-                          const StencilUpdate* upd, double* partials, int* nparts, const int* flag_dev);
+                          const StencilUpdate* upd, double* partials, int* nparts, const int* flag_dev,
+                          const FinTail* fin);
 
 int launch_stencil_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
-                             double* partials, int* nparts, const int* flag_dev) {
-    return launch_stencil(op, y ? 0 : 1, x, scale_dev, y, nullptr, partials, nparts, flag_dev);
+                             double* partials, int* nparts, const int* flag_dev, const FinTail* fin) {
+    return launch_stencil(op, y ? 0 : 1, x, scale_dev, y, nullptr, partials, nparts, flag_dev, fin);
 }
 
 int launch_stencil_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
-                               double* out, double* partials, int* nparts) {
-    return launch_stencil(op, 2, x, scale_dev, out, upd, partials, nparts, nullptr);
+                               double* out, double* partials, int* nparts, const FinTail* fin) {
+    return launch_stencil(op, 2, x, scale_dev, out, upd, partials, nparts, nullptr, fin);
 }
 
 static int launch_stencil(lz_op* op, int mode, const double* x, const double* scale_dev, double* y,
-                          const StencilUpdate* upd, double* partials, int* nparts, const int* flag_dev) {
+                          const StencilUpdate* upd, double* partials, int* nparts, const int* flag_dev,
+                          const FinTail* fin) {
     const lz_stencil& st = op->st;
     lz_ctx* ctx = op->ctx;
     StencilArgs a;
@@ -503,6 +626,8 @@ static int launch_stencil(lz_op* op, int mode, const double* x, const double* sc
     a.cb = upd ? upd->cb : nullptr; a.sb = upd ? upd->sb : nullptr;
     a.halo_lo = upd ? upd->halo.lo_dst : nullptr;
     a.halo_hi = upd ? upd->halo.hi_dst : nullptr;
+    if (fin) a.fin = *fin;
+    a.alpha_partials = (upd && mode == 2) ? upd->alpha_partials : nullptr;
     const bool has_y = (st.offy != 0.0);
     const bool has_z = (st.offz != 0.0);
     if (st.sharded) {
@@ -539,6 +664,14 @@ static int launch_stencil(lz_op* op, int mode, const double* x, const double* sc
         if (whole_tiles) fn = st.diag ? (const void*)stencil_alpha_fast_kernel<true> : (const void*)stencil_alpha_fast_kernel<false>;
         else fn = st.diag ? (const void*)stencil_alpha_kernel<true> : (const void*)stencil_alpha_kernel<false>;
     }
+    if (a.alpha_partials) {
+        if (!(vec == 2 && update_alpha_supported(op, x, y))) {
+            set_error("alpha inside KB needs a 7-point operator on whole 64 x 8 tiles and 16-byte aligned vectors");
+            return LZ_ERR_UNSUPPORTED;
+        }
+        fn = st.diag ? (const void*)stencil_apply_dot_kernel<2, true, true, true, 2, true>
+                     : (const void*)stencil_apply_dot_kernel<2, true, true, false, 2, true>;
+    }
     int per_sm = 0;
     LZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
@@ -563,9 +696,45 @@ static int launch_stencil(lz_op* op, int mode, const double* x, const double* sc
     a.zc = (int)((st.nz + best_chunks - 1) / best_chunks);
     a.chunks_z = (int)((st.nz + a.zc - 1) / a.zc);
     a.nitems = tiles * a.chunks_z;
+    if (a.alpha_partials) op->kb_zc = a.zc;          // the border kernel walks the same chunks
     const int grid = (int)std::min<int64_t>(a.nitems, gmax);
     void* args[] = {(void*)&a};
-    LZ_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, 0, ctx->stream));
+    LZ_CUDA(launch_fn(fn, dim3(grid), dim3(kThreads), 0, ctx->stream, args));
+    if (nparts) *nparts = grid;
+    return LZ_OK;
+}
+
+bool update_alpha_supported(const lz_op* op, const double* x, const double* out) {
+    static const bool off = []() { const char* e = getenv("LZ_KB_ALPHA"); return e && e[0] == '0'; }();
+    if (off || op->kind != LZ_OP_STENCIL || op->st.points != 7) return false;
+    const lz_stencil& st = op->st;
+    return st.offx != 0.0 && st.offy != 0.0 && st.offz != 0.0 && st.nx % 64 == 0 && st.ny % kWarps == 0 &&
+           st.nx * st.ny * 8 < ((int64_t)1 << 32) &&
+           ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(st.diag)) & 15) == 0;
+}
+
+int launch_alpha_border(lz_op* op, const double* v, double* partials, int* nparts, const FinTail* fin) {
+    const lz_stencil& st = op->st;
+    lz_ctx* ctx = op->ctx;
+    LZ_REQUIRE(op->kb_zc > 0, "launch_alpha_border: no KB launch with alpha partials preceded");
+    BorderArgs a;
+    a.nx = (int)st.nx; a.ny = (int)st.ny; a.nz = (int)st.nz;
+    a.periodic = (st.bc == LZ_BC_PERIODIC);
+    a.tiles_x = (int)(st.nx / 64);
+    a.tiles_y = (int)(st.ny / kWarps);
+    a.zc = op->kb_zc;
+    a.chunks_z = (int)((st.nz + a.zc - 1) / a.zc);
+    a.plane = st.nx * st.ny;
+    a.ox2 = 2.0 * st.offx; a.oy2 = 2.0 * st.offy; a.oz2 = 2.0 * st.offz;
+    a.v = v;
+    a.zhi = st.sharded ? st.ghost_hi : (a.periodic ? v : nullptr);
+    a.partials = partials;
+    if (fin) a.fin = *fin;
+    const int64_t work = (int64_t)a.nz * a.tiles_y * (a.nx / 2) + (int64_t)a.chunks_z * (a.plane / 2) +
+                         (int64_t)a.nz * a.ny * a.tiles_x;
+    const int64_t want = (work + (int64_t)kThreads * 4 - 1) / ((int64_t)kThreads * 4);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min<int64_t>((int64_t)ctx->sms * 8, kMaxPartials)));
+    LZ_CUDA(launch_k(stencil_alpha_border_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, a));
     if (nparts) *nparts = grid;
     return LZ_OK;
 }

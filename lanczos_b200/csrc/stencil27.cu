@@ -40,6 +40,7 @@ struct Stencil27Args {
     double* partials;
     int tiles_x, tiles_y, chunks_z, zc;
     int64_t nitems;
+    FinTail fin;          // what the last CTA does with the summed partials (fin.cuh)
 };
 
 template <int VEC>
@@ -60,6 +61,7 @@ __device__ __forceinline__ void load_row(const double* p, double (&v)[VEC]) {
 template <int VEC, bool HAS_DIAG, int MODE>
 __global__ void __launch_bounds__(kThreads, MODE == 2 ? 4 : 5)
 stencil27_apply_dot_kernel(const Stencil27Args a) {
+    pdl_prologue();
     if (a.skip && *a.skip == 0) return;
     __shared__ double red[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -192,6 +194,7 @@ stencil27_apply_dot_kernel(const Stencil27Args a) {
     }
     const double tot = block_sum(acc_alpha, red);
     if (threadIdx.x == 0 && a.partials) a.partials[blockIdx.x] = tot;
+    fin_tail(a.fin, a.partials, red);
 }
 
 template <int VEC, int MODE>
@@ -201,20 +204,22 @@ static const void* pick27(bool has_diag) {
 }
 
 static int launch_stencil27(lz_op* op, int mode, const double* x, const double* scale_dev, double* y,
-                            const StencilUpdate* upd, double* partials, int* nparts, const int* flag_dev);
+                            const StencilUpdate* upd, double* partials, int* nparts, const int* flag_dev,
+                            const FinTail* fin);
 
 int launch_stencil27_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
-                               double* partials, int* nparts, const int* flag_dev) {
-    return launch_stencil27(op, y ? 0 : 1, x, scale_dev, y, nullptr, partials, nparts, flag_dev);
+                               double* partials, int* nparts, const int* flag_dev, const FinTail* fin) {
+    return launch_stencil27(op, y ? 0 : 1, x, scale_dev, y, nullptr, partials, nparts, flag_dev, fin);
 }
 
 int launch_stencil27_update_norm(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd,
-                                 double* out, double* partials, int* nparts) {
-    return launch_stencil27(op, 2, x, scale_dev, out, upd, partials, nparts, nullptr);
+                                 double* out, double* partials, int* nparts, const FinTail* fin) {
+    return launch_stencil27(op, 2, x, scale_dev, out, upd, partials, nparts, nullptr, fin);
 }
 
 static int launch_stencil27(lz_op* op, int mode, const double* x, const double* scale_dev, double* y,
-                            const StencilUpdate* upd, double* partials, int* nparts, const int* flag_dev) {
+                            const StencilUpdate* upd, double* partials, int* nparts, const int* flag_dev,
+                            const FinTail* fin) {
     const lz_stencil& st = op->st;
     lz_ctx* ctx = op->ctx;
     Stencil27Args a;
@@ -229,6 +234,7 @@ static int launch_stencil27(lz_op* op, int mode, const double* x, const double* 
     a.cb = upd ? upd->cb : nullptr; a.sb = upd ? upd->sb : nullptr;
     a.halo_lo = upd ? upd->halo.lo_dst : nullptr;
     a.halo_hi = upd ? upd->halo.hi_dst : nullptr;
+    if (fin) a.fin = *fin;
     if (st.sharded) { a.zlo = st.ghost_lo; a.zhi = st.ghost_hi; }
     else if (a.periodic) { a.zlo = x + (st.nz - 1) * a.plane; a.zhi = x; }
     else { a.zlo = nullptr; a.zhi = nullptr; }
@@ -269,7 +275,7 @@ static int launch_stencil27(lz_op* op, int mode, const double* x, const double* 
     a.nitems = tiles * a.chunks_z;
     const int grid = (int)std::min<int64_t>(a.nitems, gmax);
     void* args[] = {(void*)&a};
-    LZ_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, 0, ctx->stream));
+    LZ_CUDA(launch_fn(fn, dim3(grid), dim3(kThreads), 0, ctx->stream, args));
     if (nparts) *nparts = grid;
     return LZ_OK;
 }

@@ -18,7 +18,8 @@ static int stream_grid(lz_ctx* ctx, int64_t M, int per_thread) {
 
 __global__ void __launch_bounds__(kThreads)
 dot_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t M, int vec_ok,
-           double* __restrict__ partials) {
+           double* __restrict__ partials, const FinTail fin) {
+    pdl_prologue();
     __shared__ double red[kWarps];
     double acc0 = 0.0, acc1 = 0.0;
     const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -36,13 +37,15 @@ dot_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t M
     }
     const double tot = block_sum(acc0 + acc1, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+    fin_tail(fin, partials, red);
 }
 
-int launch_dot(lz_ctx* ctx, const double* x, const double* y, int64_t M, double* partials, int* nparts) {
+int launch_dot(lz_ctx* ctx, const double* x, const double* y, int64_t M, double* partials, int* nparts,
+               const FinTail* fin) {
     const int grid = stream_grid(ctx, M, 4);
     const int vec_ok = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
-    dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, y, M, vec_ok, partials);
-    LZ_CUDA(cudaGetLastError());
+    LZ_CUDA(launch_k(dot_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, y, M, vec_ok, partials,
+                     fin ? *fin : FinTail{}));
     if (nparts) *nparts = grid;
     return LZ_OK;
 }
@@ -72,7 +75,8 @@ update_norm_kernel(const double* w, const double* __restrict__ a, const double* 
                    const double* __restrict__ ca, const double* __restrict__ sa,
                    const double* __restrict__ cb, const double* __restrict__ sb,
                    double* out, int64_t M, int vec_ok, double* __restrict__ partials,
-                   const HaloPush halo) {
+                   const HaloPush halo, const FinTail fin) {
+    pdl_prologue();
     __shared__ double red[kWarps];
     const double fa = (ca ? __ldg(ca) : 1.0) * (sa ? __ldg(sa) : 1.0);
     const double fb = HAS_B ? (cb ? __ldg(cb) : 1.0) * (sb ? __ldg(sb) : 1.0) : 0.0;
@@ -133,13 +137,15 @@ update_norm_kernel(const double* w, const double* __restrict__ a, const double* 
     }
     const double tot = block_sum(acc0 + acc1, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+    fin_tail(fin, partials, red);
 }
 
 int launch_update_norm(lz_ctx* ctx, const double* w, const double* a, const double* b,
                        const double* ca_dev, const double* sa_dev, const double* cb_dev,
                        const double* sb_dev, double* out, int64_t M, double* partials, int* nparts,
-                       const HaloPush* halo) {
+                       const HaloPush* halo, const FinTail* fin) {
     const int grid = stream_grid(ctx, M, 4);
+    const FinTail ft = fin ? *fin : FinTail{};
     HaloPush h{};
     const bool push = halo && (halo->lo_dst || halo->hi_dst);
     if (push) h = *halo;
@@ -147,8 +153,9 @@ int launch_update_norm(lz_ctx* ctx, const double* w, const double* a, const doub
     if (push) vec_ok = vec_ok && (((uintptr_t)h.lo_dst | (uintptr_t)h.hi_dst) & 15) == 0 &&
                        ((h.plane & 1) == 0) && ((M & 1) == 0);
 #define LZ_UPD(HB, HL, bb, cbb, sbb)                                                               \
-    update_norm_kernel<HB, HL><<<grid, kThreads, 0, ctx->stream>>>(w, a, bb, ca_dev, sa_dev, cbb, sbb, \
-                                                                   out, M, vec_ok, partials, h)
+    LZ_CUDA(launch_k(update_norm_kernel<HB, HL>, dim3(grid), dim3(kThreads), 0, ctx->stream, w, a,       \
+                     (const double*)bb, ca_dev, sa_dev, (const double*)cbb, (const double*)sbb, out, M,  \
+                     vec_ok, partials, h, ft))
     if (b) { if (push) LZ_UPD(true, true, b, cb_dev, sb_dev); else LZ_UPD(true, false, b, cb_dev, sb_dev); }
     else { if (push) LZ_UPD(false, true, nullptr, nullptr, nullptr); else LZ_UPD(false, false, nullptr, nullptr, nullptr); }
 #undef LZ_UPD
@@ -160,6 +167,7 @@ int launch_update_norm(lz_ctx* ctx, const double* w, const double* a, const doub
 // plain halo publication of an existing vector (start vector / first row)
 __global__ void __launch_bounds__(kThreads)
 halo_push_kernel(const double* __restrict__ x, int64_t M, const HaloPush h) {
+    pdl_prologue();
     const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * kThreads;
     for (int64_t e = tid; e < h.plane; e += nthr) {
@@ -171,8 +179,7 @@ halo_push_kernel(const double* __restrict__ x, int64_t M, const HaloPush h) {
 int launch_halo_push(lz_ctx* ctx, const double* x, int64_t M, const HaloPush* halo) {
     if (!halo || !(halo->lo_dst || halo->hi_dst)) return LZ_OK;
     const int grid = stream_grid(ctx, halo->plane, 1);
-    halo_push_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, M, *halo);
-    LZ_CUDA(cudaGetLastError());
+    LZ_CUDA(launch_k(halo_push_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, M, *halo));
     return LZ_OK;
 }
 

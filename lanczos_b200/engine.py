@@ -30,6 +30,12 @@ def _torch():
     return torch
 
 
+def run_flags(cgs_fused: bool = True, sweep_form: int = 0, kb_alpha: bool = True) -> int:
+    """lz_run_opts.flags: bit 0 = CGS2 without K4c, bit 1 = the Regular GPU sweep form (LZ_SWEEP_GPU),
+    bit 2 = recompute step with a KA pass per step instead of alpha accumulated inside KB."""
+    return (0 if cgs_fused else 1) | (2 if sweep_form == _capi.LZ_SWEEP_GPU else 0) | (0 if kb_alpha else 4)
+
+
 def padded_ld(M: int) -> int:
     """Row stride of the basis: rows start on 512-byte boundaries."""
     return (int(M) + 63) // 64 * 64
@@ -341,7 +347,9 @@ class LanczosResult:
                           "dots": (float(info.dots_ms), info.dots_launches),
                           "gs_update": (float(info.gsupd_ms), info.gsupd_launches),
                           "fused": (float(info.fused_ms), info.fused_launches),
-                          "gs_fused": (float(info.gsfused_ms), info.gsfused_launches)}
+                          "gs_fused": (float(info.gsfused_ms), info.gsfused_launches),
+                          "border": (float(info.border_ms), info.border_launches)}
+        self.alpha_in_update = bool(info.alpha_in_update)
 
     def tridiagonal(self) -> np.ndarray:
         """Dense H_eff like Lanczos.py:121-130."""
@@ -387,7 +395,7 @@ class LanczosResult:
 
 def run_lanczos(op: DeviceOperator, v0, n: int, *, reorth="full", cgs_passes=1, ref_compat=True,
                 keep_basis=True, breakdown_tol=0.0, select_tol=0.0, V_dev=None,
-                profile=False, step_kernel="auto", cgs_fused=True) -> LanczosResult:
+                profile=False, step_kernel="auto", cgs_fused=True, sweep_form=0, kb_alpha=True) -> LanczosResult:
     """Enqueue and run the n-step loop (lz_lanczos_run).  `v0` is a host array (copied through
     pinned memory) or a CUDA tensor of M doubles."""
     torch = _torch()
@@ -417,7 +425,7 @@ def run_lanczos(op: DeviceOperator, v0, n: int, *, reorth="full", cgs_passes=1, 
         beta = np.zeros(max(n - 1, 0))
         scale = np.ones(n)
         opts = RunOpts(mode, int(cgs_passes), 1 if ref_compat else 0, 1 if profile else 0,
-                       STEP_KERNEL[step_kernel], 0 if cgs_fused else 1, float(breakdown_tol), float(select_tol))
+                       STEP_KERNEL[step_kernel], run_flags(cgs_fused, sweep_form, kb_alpha), float(breakdown_tol), float(select_tol))
         info = RunInfo()
         status = ctx.lib.lz_lanczos_run(
             ctx.handle, op.handle, C.c_void_p(v0_dev.data_ptr()), n, C.byref(opts),
@@ -431,15 +439,16 @@ def run_lanczos(op: DeviceOperator, v0, n: int, *, reorth="full", cgs_passes=1, 
     return LanczosResult(ctx, n, M, alpha, beta, V_dev, ld, scale, info)
 
 
-def reorthogonalize_rows(V, j: int):
+def reorthogonalize_rows(V, j: int, form: int = 0):
     """Lanczos.reorthogonalize(V, j) for a basis held as rows: V is a CUDA tensor (n, ld>=M)
-    [in place] or a host (n, M) array [updated in place through the device]."""
+    [in place] or a host (n, M) array [updated in place through the device].  `form`:
+    LZ_SWEEP_CPU (2 V[j] - sum, Lanczos.py:247-249) or LZ_SWEEP_GPU (self term dropped, :236-238)."""
     torch = _torch()
     if isinstance(V, torch.Tensor):
         ctx = Context.default(V.device.index)
         n, M = V.shape
         ld = V.stride(0)
-        _capi.check(ctx.lib.lz_reorthogonalize(ctx.handle, C.c_void_p(V.data_ptr()), ld, n, M, int(j)))
+        _capi.check(ctx.lib.lz_reorthogonalize(ctx.handle, C.c_void_p(V.data_ptr()), ld, n, M, int(j), int(form)))
         return V
     A = np.asarray(V)
     ctx = Context.default()
@@ -447,6 +456,6 @@ def reorthogonalize_rows(V, j: int):
     ld = padded_ld(M)
     Vd = torch.zeros((n, ld), dtype=torch.float64, device=ctx.torch_device)
     Vd[:, :M] = torch.from_numpy(np.ascontiguousarray(A, dtype=np.float64)).to(ctx.torch_device)
-    _capi.check(ctx.lib.lz_reorthogonalize(ctx.handle, C.c_void_p(Vd.data_ptr()), ld, n, M, int(j)))
+    _capi.check(ctx.lib.lz_reorthogonalize(ctx.handle, C.c_void_p(Vd.data_ptr()), ld, n, M, int(j), int(form)))
     V[j] = Vd[j, :M].cpu().numpy()
     return V

@@ -11,6 +11,8 @@ class Lanczos(LanczosBase):
     call execute_Lanczos(n), read H_eff / V / H_eigvals / H_eigvecs.  `H` is a scipy.sparse
     matrix (what Hamiltonian.py builds) or a matrix-free lanczos_b200.StencilOperator."""
 
+    _GPU_SWEEP_FORM = 1          # Lanczos.py:236-238: with use_cuda=True the sweep drops the self term
+
     def execute_Lanczos(self, n, seed=99, use_cuda=True, v0=None, **options):
         """Lanczos.py:75-141.  Positional/keyword arguments as in the reference; `options` are the
         keyword-only extras of LanczosBase._execute, which default to the reference's behaviour

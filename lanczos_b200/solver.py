@@ -19,6 +19,11 @@ _NOT_RUN = "Lanczos Algorithm has not been called."      # Lanczos.py:31
 
 
 class LanczosBase:
+    # The reference has two forms of its Gram-Schmidt sweep (see lz_reorthogonalize): Regular with
+    # use_cuda=True drops the self term (Lanczos.py:236-238), everything else uses 2 V[j] - sum
+    # (Lanczos.py:247-249, IrrLanczos.py:453-460).  Subclasses say which one `use_cuda=True` means.
+    _GPU_SWEEP_FORM = 0
+
     # ---- construction (Lanczos.py:19-26) --------------------------------------------------
     def __init__(self, H):
         self.H = H
@@ -90,7 +95,7 @@ class LanczosBase:
     # ---- the loop ---------------------------------------------------------------------------
     def _execute(self, n, seed, use_cuda, v0, *, reorth="full", cgs_passes=1, ref_compat=True,
                  fmt="auto", sigma=0, device=None, keep_basis=True, breakdown_tol=0.0,
-                 select_tol=0.0, profile=False, step_kernel="auto", cgs_fused=True, verbose=True):
+                 select_tol=0.0, profile=False, step_kernel="auto", cgs_fused=True, kb_alpha=True, verbose=True):
         """Keyword-only extras (all default to the reference's behaviour):
         reorth 'full' | 'selective' | 'none'; cgs_passes 1 | 2; ref_compat (the v0-discarding
         pre-step and the (2-|v|^2) sweep form of the reference); fmt 'auto' | 'csr' | 'sell' and
@@ -130,7 +135,8 @@ class LanczosBase:
         self._result = engine.run_lanczos(op, start, n, reorth=reorth, cgs_passes=cgs_passes,
                                           ref_compat=ref_compat, keep_basis=keep_basis,
                                           breakdown_tol=breakdown_tol, select_tol=select_tol,
-                                          profile=profile, step_kernel=step_kernel, cgs_fused=cgs_fused)
+                                          profile=profile, step_kernel=step_kernel, cgs_fused=cgs_fused,
+                                          sweep_form=self._GPU_SWEEP_FORM if use_cuda else 0, kb_alpha=kb_alpha)
         self._H_eff = self._result.tridiagonal()
         self._V_host = None
         self._Y_dev = None
@@ -224,12 +230,13 @@ class LanczosBase:
         return pairs, overlap
 
     # ---- static helpers kept from the reference (Lanczos.py:233-337) ---------------------------
-    @staticmethod
-    def reorthogonalize(V, j, use_cuda=True):
-        """One Gram-Schmidt sweep of row j of V against all rows, in place (CPU form of the
-        reference, Lanczos.py:247-249: V[j] = 2 V[j] - sum_i (V[j].V[i]) V[i]).  V: (n, M) host
-        array or CUDA tensor with rows = Lanczos vectors."""
-        return engine.reorthogonalize_rows(V, j)
+    @classmethod
+    def reorthogonalize(cls, V, j, use_cuda=True):
+        """One Gram-Schmidt sweep of row j of V against all rows, in place, in the form the
+        reference class uses for this `use_cuda` (Lanczos.py:236-238 / :247-249;
+        IrrLanczos.py:453-460).  V: (n, M) host array or CUDA tensor with rows = Lanczos vectors.
+        Always computed on the GPU (there is no CPU path)."""
+        return engine.reorthogonalize_rows(V, j, form=cls._GPU_SWEEP_FORM if use_cuda else 0)
 
     @staticmethod
     def get_matched_eigs(v, vL, l, lL):

@@ -52,7 +52,47 @@ def gram_schmidt_row(V, j):
     V[j] = 2 * V[j] - np.sum(ip[:, None] * V, axis=0)
 
 
-def tridiagonalize(H, n, seed=99, v0=None, reorth=True):
+def gram_schmidt_row_blocked(V, j, nrows=None, threads=None):
+    """gram_schmidt_row for bases of GB size (full-size config-2 parity test): the same arithmetic,
+    bit for bit, without the two (n, M) temporaries of the reference's expressions.
+      * ip[r] = np.sum(V[j]*V[r]) row by row - the reduction NumPy runs per row of `np.sum(V[j]*V, axis=1)`
+        (pairwise summation along the contiguous axis);
+      * the axis-0 sum `np.sum(ip[:,None]*V, axis=0)` adds the rows in order, element by element:
+        acc = ip[0]*V[0]; acc += ip[1]*V[1]; ...   (done per column slab, slabs in parallel);
+      * rows >= nrows are known to be zero (rows the loop has not reached): they add +0.0 to every sum.
+    tests/test_oracle.py holds it to gram_schmidt_row bit-for-bit."""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    n, M = V.shape
+    nrows = n if nrows is None else nrows
+    threads = threads or min(16, os.cpu_count() or 1)
+    vj = V[j].copy()
+    with ThreadPoolExecutor(threads) as ex:
+        ip = np.array(list(ex.map(lambda r: np.sum(vj * V[r]), range(nrows))))
+        slab = -(-M // (threads * 4))
+
+        def upd(c0):
+            c1 = min(M, c0 + slab)
+            acc = ip[0] * V[0, c0:c1]
+            for r in range(1, nrows):
+                acc += ip[r] * V[r, c0:c1]
+            return c0, c1, acc
+        out = np.empty(M)
+        for c0, c1, acc in ex.map(upd, range(0, M, slab)):
+            out[c0:c1] = acc
+    V[j] = 2 * vj - out
+
+
+def gram_schmidt_row_gpu_form(V, j):
+    """The sweep as Regular/Lanczos.py:236-238 states it for use_cuda=True (CuPy arrays there;
+    the same operations on NumPy arrays here): the self inner product is zeroed,
+        ip = sum(V[j]*V, axis=1); ip[j] = 0;  V[j] = V[j] - sum(ip[:,None]*V, axis=0)"""
+    ip = np.sum(V[j] * V, axis=1)
+    ip[j] = 0
+    V[j] = V[j] - np.sum(ip[:, None] * V, axis=0)
+
+
+def tridiagonalize(H, n, seed=99, v0=None, reorth=True, sweep="cpu", blocked=False):
     """The n-step symmetric Lanczos loop exactly as the reference runs it
     (Lanczos.py:104-119 == IrrLanczos.py:221-238), quirks included:
       * the user's start vector only seeds the pre-step; row 0 of the basis is
@@ -60,6 +100,8 @@ def tridiagonalize(H, n, seed=99, v0=None, reorth=True):
       * beta[j-1] at j=0 lands in beta[-1] and is overwritten by the last step;
       * V[j-1] at j=0 is the (still zero) last row;
       * n == 1 raises IndexError (beta is empty), n > M raises ValueError.
+    `sweep`: "cpu" = the 2 V[j] - sum form (Lanczos.py:247-249, IrrLanczos.py both branches),
+    "gpu" = the form Regular/Lanczos.py:236-238 states for use_cuda=True (self term dropped).
     Returns (alpha (n,), beta (n-1,), V (n, M) row-major)."""
     M = np.shape(H)[0]
     if n > M:
@@ -75,8 +117,10 @@ def tridiagonalize(H, n, seed=99, v0=None, reorth=True):
     for j in range(n):
         beta[j - 1] = np.linalg.norm(r)
         V[j] = r / beta[j - 1]
-        if reorth:
-            gram_schmidt_row(V, j)
+        if reorth and blocked and sweep == "cpu":
+            gram_schmidt_row_blocked(V, j, nrows=j + 1)      # same bits, no (n, M) temporaries
+        elif reorth:
+            (gram_schmidt_row_gpu_form if sweep == "gpu" else gram_schmidt_row)(V, j)
         r = H * V[j]
         alpha[j] = np.dot(V[j], r)
         r = r - V[j] * alpha[j] - V[j - 1] * beta[j - 1]
@@ -106,9 +150,9 @@ def ritz_pairs(T, V_cols):
     return theta, S, Y
 
 
-def lanczos(H, n, seed=99, v0=None, reorth=True, vectors=False):
+def lanczos(H, n, seed=99, v0=None, reorth=True, vectors=False, sweep="cpu", blocked=False):
     """Convenience wrapper: returns dict(alpha, beta, T, V (M,n), theta[, Y])."""
-    alpha, beta, V = tridiagonalize(H, n, seed=seed, v0=v0, reorth=reorth)
+    alpha, beta, V = tridiagonalize(H, n, seed=seed, v0=v0, reorth=reorth, sweep=sweep, blocked=blocked)
     T = assemble_tridiagonal(alpha, beta)
     out = {"alpha": alpha, "beta": beta, "T": T, "V": V.T}
     if vectors:

@@ -62,7 +62,7 @@ def test_struct_layouts_match_header_and_integration_stub():
 
 def test_abi_version_and_error_string(lib):
     lib.lz_abi_version.restype = ctypes.c_int
-    assert lib.lz_abi_version() == 1
+    assert lib.lz_abi_version() == 2
     lib.lz_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.lz_last_error(), bytes)
 
@@ -97,7 +97,7 @@ def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
     assert res.returncode == 0, res.stderr
     run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert run.returncode == 0, run.stdout + run.stderr
-    assert "lz_abi_version = 1" in run.stdout
+    assert "lz_abi_version = 2" in run.stdout
     import torch
     if torch.cuda.is_available():
         assert "steps_done = 12" in run.stdout

@@ -213,6 +213,62 @@ def test_irregular_delaunay(lz, golden):
     np.testing.assert_allclose(L.H_eigvals, golden["del_theta"], rtol=TOL_RITZ, atol=1e-12)
 
 
+def test_sweep_form_follows_use_cuda(lz):
+    """Regular.execute_Lanczos(use_cuda=True) sweeps in the form of Lanczos.py:236-238 (self term
+    dropped), use_cuda=False and IrrLanczos in the 2 V[j] - sum form (:247-249): each against the
+    oracle in the same form; the two forms agree to rounding."""
+    grid, n = (12, 10, 9), 30
+    H = orc.laplacian_csr(grid, 6.5, -1.0, periodic=True)
+    op = lz.StencilOperator(grid, 6.5, -1.0)
+    gpu_form = orc.lanczos(H, n, seed=4, sweep="gpu")
+    cpu_form = orc.lanczos(H, n, seed=4)
+    L = lz.Lanczos(op)
+    L.execute_Lanczos(n, seed=4)                               # use_cuda=True
+    assert rel(np.diag(L.H_eff), gpu_form["alpha"]) < TOL_AB
+    assert rel(np.diag(L.H_eff, 1), gpu_form["beta"]) < TOL_AB
+    with pytest.warns(RuntimeWarning):
+        L.execute_Lanczos(n, seed=4, use_cuda=False)
+    assert rel(np.diag(L.H_eff), cpu_form["alpha"]) < TOL_AB
+    assert rel(np.diag(L.H_eff, 1), cpu_form["beta"]) < TOL_AB
+    Li = lz.IrrLanczos(H)
+    Li.execute_LanczosOld(n, seed=4)
+    assert rel(np.diag(Li.H_eff), cpu_form["alpha"]) < TOL_AB
+    assert rel(gpu_form["alpha"], cpu_form["alpha"]) < 1e-13
+
+
+def test_config2_full_size_vs_oracle(lz):
+    """BASELINE config 2 at its stated size: graph Laplacian of a 1 M-vertex 2-D Delaunay mesh, CSR in,
+    m = 200, full re-orthogonalisation in the reference's form (IrrLanczos.py:193-260), against the
+    oracle on the host (1.6 GB basis).  alpha/beta of the first 50 steps <= 1e-12 relative (the
+    north-star bound is stated for m <= 50), every step <= 1e-9, converged Ritz values <= 1e-10."""
+    npts, m = 1_000_000, 200
+    H = orc.delaunay_graph_laplacian(npts, seed=0)
+    assert H.shape[0] == npts and H.indices.dtype == np.int32
+    ref = orc.lanczos(H, m, seed=99, blocked=True)            # bit-identical form without (n, M) temporaries
+    th, S = np.linalg.eigh(ref["T"])                           # Lanczos.py:151
+    L = lz.IrrLanczos(H)
+    L.execute_LanczosOld(m, seed=99)
+    a, b = np.diag(L.H_eff), np.diag(L.H_eff, 1)
+    assert rel(a[:50], ref["alpha"][:50]) < TOL_AB
+    assert rel(b[:50], ref["beta"][:50]) < TOL_AB
+    assert rel(a, ref["alpha"]) < 1e-9
+    assert rel(b, ref["beta"]) < 1e-9
+    # converged Ritz pairs of the oracle: residual |H y - theta y| <= 1e-8 |H|
+    theta = np.linalg.eigvalsh(L.H_eff)
+    resid = np.abs(ref["beta"][-1] * S[-1, :])                 # |beta_m s_mi|: the Lanczos residual estimate
+    conv = resid < 1e-8 * np.abs(th).max()
+    assert conv.sum() >= 1, "no converged Ritz value at m = 200"
+    np.testing.assert_allclose(theta[conv], th[conv], rtol=TOL_RITZ, atol=1e-10 * np.abs(th).max())
+    # the extreme Ritz value, converged or not, also agrees (it is a function of alpha/beta alone)
+    assert abs(theta[-1] - th[-1]) <= 1e-10 * abs(th[-1])
+    # and the lifted Ritz vector of the best converged pair matches the oracle's up to sign
+    i = int(np.argmin(np.where(conv, resid, np.inf)))
+    _, Yg = L.ritz_vectors(m)
+    yg = Yg[i].cpu().numpy()
+    yo = np.dot(ref["V"], S[:, i])                             # Lanczos.py:155-156, one column
+    assert min(np.linalg.norm(yg - yo), np.linalg.norm(yg + yo)) < 1e-7
+
+
 def test_irregular_rgg_vs_oracle(lz):
     H = orc.rgg_graph_laplacian(20000, mean_degree=13.0, seed=4)
     ref = orc.lanczos(H, 40, seed=11)
@@ -255,14 +311,23 @@ def test_static_reorthogonalize(lz):
         Vo = V.copy()
         orc.gram_schmidt_row(Vo, j)
         Vg = V.copy()
-        lz.Lanczos.reorthogonalize(Vg, j)
+        lz.Lanczos.reorthogonalize(Vg, j, use_cuda=False)       # Lanczos.py:247-249
         assert np.max(np.abs(Vg - Vo)) < 1e-15
+        Vi = V.copy()
+        lz.IrrLanczos.reorthogonalize(Vi, j)                    # IrrLanczos.py:453-455: same form on both branches
+        assert np.array_equal(Vi, Vg)
+        # Regular with use_cuda=True (the default) drops the self term (Lanczos.py:236-238)
+        Vo2 = V.copy()
+        orc.gram_schmidt_row_gpu_form(Vo2, j)
+        Vg2 = V.copy()
+        lz.Lanczos.reorthogonalize(Vg2, j)
+        assert np.max(np.abs(Vg2 - Vo2)) < 1e-15
     # rows after j that are not zero take part as well (the reference sums over all rows)
     V2 = rs.uniform(-1, 1, (6, 515)) / np.sqrt(515)
     Vo = V2.copy()
     orc.gram_schmidt_row(Vo, 2)
     Vg = V2.copy()
-    lz.Lanczos.reorthogonalize(Vg, 2)
+    lz.Lanczos.reorthogonalize(Vg, 2, use_cuda=False)
     assert np.max(np.abs(Vg - Vo)) < 1e-15
 
 
