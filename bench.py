@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -125,19 +125,19 @@ class ClockSampler:
 
 
 def ncu_traffic(kernel_name):
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel_name` from the
-    committed `ncu --set full` summaries (profiles/r1c_ncu_traffic.json, then r1b_, then r1_ncu_traffic.json;
-    captured at the 512^3 config / the 50M-vertex graph)."""
-    for name in ("r1c_ncu_traffic.json", "r1b_ncu_traffic.json", "r1_ncu_traffic.json"):
+    """(DRAM bytes per launch, source file) of `kernel_name`: dram__bytes_read.sum + dram__bytes_write.sum from the
+    committed `ncu --set full` summaries under profiles/ (newest round first; captured at the 512^3 config / the
+    50M-vertex graph).  Static evidence, not measured in this run - the source file is named in the JSON line."""
+    for name in ("r2_ncu_traffic.json", "r1c_ncu_traffic.json", "r1b_ncu_traffic.json", "r1_ncu_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 t = json.load(f)
             for k, v in t.items():
                 if k.startswith(kernel_name):
-                    return v["dram_bytes_per_launch"]
+                    return v["dram_bytes_per_launch"], "profiles/" + name
         except Exception:
             pass
-    return None
+    return None, None
 
 
 def measured_peaks():
@@ -150,54 +150,107 @@ def measured_peaks():
 
 
 # --------------------------------------------------------------------------- CPU baseline
-def cpu_reference_leg(workload: str, budget_s: float = 20.0):
-    """The reference's CPU algorithm (oracle port: same NumPy/SciPy ops as Lanczos.py:100-119 and
-    :247-249) on a bounded sample of the workload, all host threads NumPy/OpenBLAS will use."""
+def _quiet_call(fn, *a, **k):
+    """The reference prints banners and draws tqdm bars (Lanczos.py:79,111): keep stdout/stderr clean."""
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        return fn(*a, **k)
+
+
+def _reference_runner(irregular: bool):
+    """(run(H, n, v0, sweeps) -> seconds, kind).  `kind` "reference": the unmodified reference classes
+    vendored by oracle/build_ref.py into oracle/_ref (Lanczos.execute_Lanczos / IrrLanczos.execute_LanczosOld,
+    use_cuda=False); "port": the oracle's restatement of the same NumPy/SciPy operations when oracle/_ref is
+    absent.  sweeps=False times the same loop with the reference's `reorthogonalize` call made a no-op - the
+    like-for-like of a GPU run in which no Gram-Schmidt sweep fired (the reference has no such mode)."""
+    from oracle import build_ref
+    from oracle import lanczos_oracle as orc
+    mods = build_ref.load()
+    if mods is None:
+        def run_port(H, n, v0, sweeps=True):
+            return orc.timed_steps(H, n, v0, reorth=sweeps)
+        return run_port, "port"
+    cls = mods[1].IrrLanczos if irregular else mods[0].Lanczos
+
+    def run_ref(H, n, v0, sweeps=True):
+        saved = cls.__dict__["reorthogonalize"]
+        if not sweeps:
+            cls.reorthogonalize = staticmethod(lambda V, j, use_cuda=True: None)
+        try:
+            L = cls(H)
+            t0 = time.perf_counter()
+            _quiet_call(L.execute_LanczosOld if irregular else L.execute_Lanczos, n, use_cuda=False, v0=v0)
+            return time.perf_counter() - t0
+        finally:
+            cls.reorthogonalize = saved
+    return run_ref, "reference"
+
+
+def cpu_reference_leg(workload: str, budget_s: float = 25.0):
+    """The reference's CPU path on a bounded sample of the workload, with all the host threads NumPy/OpenBLAS
+    will use (SciPy's SpMV and NumPy's elementwise kernels are single-threaded).  Two numbers:
+      reference_form  the reference as it is - one full Gram-Schmidt sweep against all n rows every step;
+      no_sweep        the same loop without the sweep, at the largest size that builds in seconds (256^3).
+    `value` is the one that matches what the GPU arm does on this workload: no_sweep for the selective /
+    none configurations (in the timed region no sweep fires), reference_form for the full-reorth ones.
+    Both are extrapolated linearly in the number of unknowns to the workload's size (stated in `sample`)."""
     from oracle import lanczos_oracle as orc
     wl = WORKLOADS[workload]
     cores = os.cpu_count() or 1
+    irregular = "grid" not in wl
+    run, kind = _reference_runner(irregular)
+    out = dict(unit=UNIT, cores=cores, kind=kind, numpy=np.__version__)
     if "grid" in wl and len(wl["grid"]) == 3:
         full_M = int(np.prod(wl["grid"]))
-        side, n = 96, 16
-        H = orc.laplacian_csr((side, side, side), 6.0, -1.0, periodic=True)
+        side, n = 96, 32
+        H = orc.laplacian_csr((side,) * 3, 6.0, -1.0, periodic=True)
         v0 = np.random.RandomState(99).uniform(-1, 1, side ** 3)
-        t = orc.timed_steps(H, n, v0, reorth=True)
-        # more steps if the box is fast, to land near the budget
-        if t < budget_s / 4:
-            n = 32
-            t = orc.timed_steps(H, n, v0, reorth=True)
-        sample_rate = n / t
-        value = sample_rate * (side ** 3) / full_M           # linear extrapolation in M
-        t2 = orc.timed_steps(H, n, v0, reorth=False)
-        step_only = (n / t2) * (side ** 3) / full_M
-        sample = (f"{side}^3 periodic 7-pt Laplacian, n={n}, full reorth as the reference always does "
-                  f"({sample_rate:.2f} steps/s measured), extrapolated linearly in M to {full_M} unknowns; "
-                  f"its reorth cost also grows with n (all n rows every step), so n={wl['steps']} would be slower still; "
-                  f"step-only (no reorth) extrapolated: {step_only:.3f} steps/s")
-        return dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample,
-                    step_only_value=step_only, numpy=np.__version__)
+        t = run(H, n, v0, True)
+        form_rate = n / t
+        form_value = form_rate * (side ** 3) / full_M
+        side2, n2 = 256, 12
+        H2 = orc.laplacian_csr((side2,) * 3, 6.0, -1.0, periodic=True)
+        v2 = np.random.RandomState(99).uniform(-1, 1, side2 ** 3)
+        t2 = run(H2, n2, v2, False)
+        ns_rate = n2 / t2
+        ns_value = ns_rate * (side2 ** 3) / full_M
+        like = wl["reorth"] != "full"
+        out.update(value=ns_value if like else form_value, reference_form_value=form_value, no_sweep_value=ns_value,
+                   step_only_value=ns_value,
+                   sample=(f"reference_form: {side}^3 periodic 7-pt Laplacian (CSR), n={n}, the reference's full sweep every step: "
+                           f"{form_rate:.2f} steps/s measured, x{side ** 3 / full_M:.2e} (linear in M) -> {form_value:.4f} steps/s at "
+                           f"{full_M} unknowns (its sweep cost also grows with n); no_sweep: {side2}^3, n={n2}, sweep disabled: "
+                           f"{ns_rate:.2f} steps/s measured, x{side2 ** 3 / full_M:.3f} -> {ns_value:.3f} steps/s; "
+                           f"value = {'no_sweep' if like else 'reference_form'}"))
+        return out
     if workload == "c4":
         npts, n = 200_000, 32
         H = orc.rgg_graph_laplacian(npts, mean_degree=13.0, seed=0)
         v0 = np.random.RandomState(99).uniform(-1, 1, npts)
-        t = orc.timed_steps(H, n, v0, reorth=True)
+        t = run(H, n, v0, True)
+        t2 = run(H, n, v0, False)
         full = 50_000_000
-        return dict(value=(n / t) * npts / full, unit=UNIT, cores=cores, kind="port",
-                    sample=f"3D random geometric graph, {npts} vertices, mean degree 13, n={n}, full reorth as the "
-                           f"reference always does ({n/t:.2f} steps/s), extrapolated linearly in M to {full}")
+        out.update(value=(n / t2) * npts / full, reference_form_value=(n / t) * npts / full, no_sweep_value=(n / t2) * npts / full,
+                   sample=f"3D random geometric graph, {npts} vertices, mean degree 13, n={n}: reference_form {n / t:.2f} steps/s, "
+                          f"no_sweep {n / t2:.2f} steps/s measured, both x{npts / full:.1e} (linear in M) to {full} vertices; value = no_sweep")
+        return out
     if workload == "c2":
         npts, n = 100_000, 40
         H = orc.delaunay_graph_laplacian(npts, seed=0)
         v0 = np.random.RandomState(99).uniform(-1, 1, npts)
-        t = orc.timed_steps(H, n, v0, reorth=True)
+        t = run(H, n, v0, True)
         value = (n / t) * npts / wl["npts"]
-        return dict(value=value, unit=UNIT, cores=cores, kind="port",
-                    sample=f"Delaunay {npts} vertices, n={n}, full reorth ({n/t:.2f} steps/s), extrapolated linearly in M to {wl['npts']}")
+        out.update(value=value, reference_form_value=value,
+                   sample=f"Delaunay {npts} vertices, n={n}, full sweep every step ({n / t:.2f} steps/s measured), "
+                          f"x{npts / wl['npts']:.2f} (linear in M) to {wl['npts']} vertices")
+        return out
     grid, n = wl["grid"], wl["steps"]
     H = orc.laplacian_csr(grid, 4.0, -1.0, periodic=False)
     v0 = np.random.RandomState(99).uniform(-1, 1, int(np.prod(grid)))
-    t = orc.timed_steps(H, n, v0, reorth=True)
-    return dict(value=n / t, unit=UNIT, cores=cores, kind="port", sample=f"the full config: {grid}, n={n}, full reorth")
+    t = run(H, n, v0, True)
+    out.update(value=n / t, reference_form_value=n / t, sample=f"the full config: {grid}, n={n}, full sweep every step, not extrapolated")
+    return out
 
 
 def run_reference_arm(args):
@@ -205,17 +258,14 @@ def run_reference_arm(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    vals = []
-    base = None
-    for _ in range(max(1, min(args.steps, 1))):      # one bounded sample per run (each is ~10-30 s)
-        base = cpu_reference_leg(args.workload)
-        vals.append(base["value"])
-    v = float(np.median(vals))
-    base["value"] = v
+    base = cpu_reference_leg(args.workload)
+    v = float(base["value"])
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v if v > 0 else None,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": f"{args.workload}: {wl['desc']}"},
+            "higher_is_better": True, "scaling": "strong" if wl.get("strong") else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": f"{args.workload}: {wl['desc']}",
+                                            "note": "one bounded sample per run (see cpu_baseline.sample); --steps/--warmup do not "
+                                                    "change it: the reference at the full size would take hours"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -302,6 +352,32 @@ def build_operator(lz, workload, world, rank):
     return H, (wl["npts"],)
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this process (and the pinned host buffers it first-touches afterwards) to the CPUs of the NUMA node
+    the GPU hangs off: with 4-8 ranks staging 1 GB start vectors at once, remote-node pinned memory is what
+    makes the end-to-end number fall off.  Best effort; returns a description for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "single NUMA node"
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return "node %d has no allowed CPUs" % node
+        os.sched_setaffinity(0, allowed)
+        return "bound to NUMA node %d (%d CPUs)" % (node, len(allowed))
+    except Exception as e:
+        return "not bound (%s)" % type(e).__name__
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -310,7 +386,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-cgs-fusion", action="store_true", help="CGS2 as four separate sweeps (comparison runs)")
+    ap.add_argument("--no-kb-alpha", action="store_true", help="recompute step with a KA pass per step (comparison runs)")
+    ap.add_argument("--min-region-s", type=float, default=1.5,
+                    help="the K-step solve is repeated until the timed region is at least this long")
     ap.add_argument("--step-kernel", default="auto", choices=["auto", "two_pass", "recompute", "fused"],
                     help="auto = the library default (recompute for matrix-free operators)")
     args = ap.parse_args()
@@ -328,6 +408,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU path)")
     torch.cuda.set_device(local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         # NCCL prints its version banner on stdout when the communicator comes up; stdout carries
@@ -343,13 +424,24 @@ def main():
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
+    numa = bind_to_gpu_numa_node(local)
     import lanczos_b200 as lz
+
+    # ---- parity gate: nothing is timed unless the code path of this run agrees with the oracle ----------------
+    parity = None
+    if not args.no_parity_check:
+        parity = parity_check(lz, world, rank, dist)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "parity_check": parity,
+                                  "error": "parity check failed: nothing was timed"}), flush=True)
+            raise SystemExit(1)
 
     K, W = int(args.steps), max(3, int(args.warmup))
     H, grid = build_operator(lz, args.workload, world, rank)
     M_total = int(np.prod(grid))
     opts = dict(reorth=wl["reorth"], cgs_passes=wl["cgs_passes"], ref_compat=True, step_kernel=args.step_kernel,
-                cgs_fused=not args.no_cgs_fusion)
+                cgs_fused=not args.no_cgs_fusion, kb_alpha=not args.no_kb_alpha)
 
     if world > 1:
         from lanczos_b200 import team as lzteam
@@ -394,67 +486,100 @@ def main():
 
     # ---- warm-up: W untimed steps (also sizes the workspace arena and the allocator cache) ----
     solve(max(W, 2), v0_dev)
-    if len(chunks) == 1:
-        solve(chunks[0], v0_dev)           # allocator + arena warm at the timed size
+    res = None
+    for c in chunks:
+        res = solve(c, v0_dev)             # allocator + arena warm at the timed size
+    est_ms = max(1e-3, sum(1 for _ in chunks) * 0 + res.gpu_ms * K / chunks[-1])
+    del res
+    if world > 1:
+        t = torch.tensor([est_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        est_ms = float(t.item())
+    # the K-step solve is repeated R times so that the timed region lasts >= min_region_s: long enough for
+    # >= 10 clock samples and for the board to reach its sustained power state
+    R = int(min(2000, max(1, np.ceil(args.min_region_s * 1e3 / est_ms))))
     barrier()
 
-    # ---- timed region A: device-resident input, exactly K steps -------------------------------
+    # ---- timed region A: device-resident input, R x exactly K steps ----------------------------
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.25)
+    time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.perf_counter()
     ev0.record()
     launches = 0
     reorths = 0
-    for c in chunks:
-        res = solve(c, v0_dev)
-        launches += res.launches
-        reorths += res.reorth_count
-        del res                       # the result owns the ~100 GB basis; the next solve reuses it
+    solve_ms = []
+    alpha_in_update = False
+    for _ in range(R):
+        ms = 0.0
+        for c in chunks:
+            res = solve(c, v0_dev)
+            launches += res.launches
+            reorths += res.reorth_count
+            ms += res.gpu_ms
+            alpha_in_update = getattr(res, "alpha_in_update", False)
+            del res                       # the result owns the basis (~100 GB at K = 100); the next solve reuses it
+        solve_ms.append(ms)
     ev1.record()
     barrier()
     t_wall1 = time.perf_counter()
     ms_dev = ev0.elapsed_time(ev1)
+    burst_ms = min(solve_ms)
     if world > 1:
-        t = torch.tensor([ms_dev], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms_dev, burst_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev = float(t.item())
+        ms_dev, burst_ms = float(t[0].item()), float(t[1].item())
+    time.sleep(0.1)
+    sampler.stop()
+    clocks = sampler.summary(t_wall0, t_wall1)
 
-    # ---- region A2: the same K steps again with a CUDA-event pair around every bandwidth kernel
-    # (per-kernel roofline).  Kept out of region A because the event records break up
-    # back-to-back launches and cost several percent of step time.
-    kern = {"apply": [0.0, 0], "update": [0.0, 0], "dots": [0.0, 0], "gs_update": [0.0, 0], "fused": [0.0, 0],
-            "gs_fused": [0.0, 0]}
+    # ---- region A2: the same K steps a few more times with a CUDA-event pair around every bandwidth kernel
+    # (per-kernel roofline).  Kept out of region A because the event records break up back-to-back launches.
+    kern = {}
     step_kernel = "two_pass"
-    for c in chunks:
-        res = solve(c, v0_dev, profile=True)
-        step_kernel = res.step_kernel
-        for k, (ms, cnt) in res.kernel_ms.items():
-            acc = kern.setdefault(k, [0.0, 0])
-            acc[0] += ms
-            acc[1] += cnt
-        del res
+    for _ in range(max(1, min(R, 3))):
+        for c in chunks:
+            res = solve(c, v0_dev, profile=True)
+            step_kernel = res.step_kernel
+            for k, (ms, cnt) in res.kernel_ms.items():
+                acc = kern.setdefault(k, [0.0, 0])
+                acc[0] += ms
+                acc[1] += cnt
+            del res
+    for k in ("apply", "update", "dots", "gs_update", "fused", "gs_fused", "border"):
+        kern.setdefault(k, [0.0, 0])
+    prof_solves = max(1, min(R, 3))
     barrier()
     theta = solver.ritz_values(10)
 
     # ---- timed region B: end to end through the drop-in class, host buffers --------------------
+    # every solve copies its start vector from pinned host memory and returns alpha/beta to the host
     barrier()
     e0 = time.perf_counter()
     for c in chunks:
         solve(c, v0_host)
-        T = solver.H_eff                   # host ndarray (alpha/beta came back D2H inside the call)
-        _ = solver.ritz_values(10)
+    torch.cuda.synchronize()
+    e_one = time.perf_counter() - e0
+    if world > 1:
+        t = torch.tensor([e_one], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_one = float(t.item())
+    Re = int(min(500, max(2, np.ceil(min(args.min_region_s, 1.0) / max(e_one, 1e-4)))))
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(Re):
+        for c in chunks:
+            solve(c, v0_host)
+            T = solver.H_eff                   # host ndarray (alpha/beta came back D2H inside the call)
+            _ = solver.ritz_values(10)
     torch.cuda.synchronize()
     e_wall = time.perf_counter() - e0
     if world > 1:
         t = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_wall = float(t.item())
-    time.sleep(0.15)
-    sampler.stop()
-    clocks = sampler.summary(t_wall0, t_wall1)
 
     # ---- roofline of the dominant kernel --------------------------------------------------------
     peak, peak_src = measured_peaks()
@@ -470,8 +595,11 @@ def main():
     per_kernel = {}
     # K3 reads w, v_j, v_{j-1}, writes r; KB (recompute) reads v_j, v_{j-1}, writes r and applies H again
     update_bytes = 24.0 * N if recompute else 32.0 * N
-    alg = {"apply": apply_bytes, "update": update_bytes}
-    for k in ("apply", "update"):
+    # border kernel (alpha inside KB): 2 of every 8 rows (y tile borders), the two sectors around every 64th
+    # column (x tile borders, 64 B per 512 B of row) and two planes per z-chunk - counted as 3.5 B per unknown
+    border_bytes = 3.5 * N
+    alg = {"apply": apply_bytes, "update": update_bytes, "border": border_bytes}
+    for k in ("apply", "update", "border"):
         ms, cnt = kern[k]
         if cnt:
             per_kernel[k] = {"launches": cnt, "avg_ms": ms / cnt, "alg_bytes": alg[k],
@@ -496,43 +624,55 @@ def main():
         for k, tot_b in (("dots", dots_b), ("gs_update", upd_b), ("gs_fused", fus_b)):
             ms, cnt = kern[k]
             if cnt:
-                per_kernel[k] = {"launches": cnt, "avg_ms": ms / cnt, "alg_bytes": tot_b / cnt,
-                                 "achieved_gbs": tot_b / ms / 1e6}
-    gs_ms = kern["dots"][0] + kern["gs_update"][0] + kern["gs_fused"][0]
+                per_kernel[k] = {"launches": cnt, "avg_ms": ms / cnt, "alg_bytes": tot_b * prof_solves / cnt,
+                                 "achieved_gbs": tot_b * prof_solves / ms / 1e6}
+    gs_ms = (kern["dots"][0] + kern["gs_update"][0] + kern["gs_fused"][0]) / prof_solves
     dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"] * per_kernel[k]["launches"]) if per_kernel else None
     names = {"apply": "stencil_alpha_kernel (KA2)" if recompute else ("stencil_apply_dot_kernel" if is_stencil else "spmv_sell_dot_kernel"),
-             "update": "stencil_apply_dot_kernel<MODE=2> (KB)" if recompute else "update_norm_kernel",
+             "update": ("stencil_apply_dot_kernel<MODE=2, ALPHA> (KB + alpha of the next vector)" if alpha_in_update else
+                        "stencil_apply_dot_kernel<MODE=2> (KB)") if recompute else "update_norm_kernel",
+             "border": "stencil_alpha_border_kernel",
              "dots": "cgs_dots_kernel", "gs_update": "cgs_update_kernel", "gs_fused": "cgs_update_dots_kernel"}
     ncu_names = {"apply": "stencil_alpha_fast_kernel<0>" if recompute else names["apply"],
-                 "update": "stencil_apply_dot_kernel<2, 1, 1, 0, 2>" if recompute else names["update"],
+                 "update": ("stencil_apply_dot_kernel<2, 1, 1, 0, 2, 1>" if alpha_in_update else
+                            "stencil_apply_dot_kernel<2, 1, 1, 0, 2, 0>") if recompute else names["update"],
+                 "border": names["border"],
                  "dots": names["dots"], "gs_update": names["gs_update"], "gs_fused": names["gs_fused"]}
     roofline = None
     if dom:
         pk = per_kernel[dom]
-        traffic = ncu_traffic(ncu_names[dom]) if ((args.workload in ("c3", "c3full") and M_local == 512 ** 3) or
-                                                  (args.workload == "c4" and world == 1)) else None
+        traffic, traffic_src = (None, None)
+        if (args.workload in ("c3", "c3full") and M_local == 512 ** 3) or (args.workload == "c4" and world == 1):
+            traffic, traffic_src = ncu_traffic(ncu_names[dom])
         roofline = {"kernel": names[dom], "bound": "hbm", "achieved": pk["achieved_gbs"], "peak": peak,
                     "unit": "GB/s", "frac": pk["achieved_gbs"] / peak, "traffic": traffic,
+                    "traffic_source": traffic_src,
                     "peak_source": peak_src, "alg_bytes_per_launch": pk["alg_bytes"],
                     "avg_launch_ms": pk["avg_ms"], "launches": pk["launches"],
-                    "timing": "CUDA-event pair around every launch of a second K-step solve on the launching stream",
+                    "timing": "CUDA-event pair around every launch of %d further K-step solves on the launching stream" % prof_solves,
                     "frac_of_8TBs_nominal": pk["achieved_gbs"] / 8000.0}
-    step_bytes = apply_bytes + update_bytes
-    ms_per_step = ms_dev / K
+    ms_per_step = ms_dev / (R * K)
     # whole-job aggregate: every rank advances its own 512^3-unknown shard K steps (weak scaling),
     # so the job processes world*K shard-steps; at N = 1 this is plain Lanczos steps/s.
     strong = bool(wl.get("strong"))
-    value = (1 if strong else world) * K / (ms_dev / 1e3)
+    scale_n = 1 if strong else world
+    value = scale_n * R * K / (ms_dev / 1e3)
     plain = reorths == 0
+    if recompute and alpha_in_update:
+        step_bytes = update_bytes + border_bytes
+        step_note = ("bytes per plain step: 24*N (KB: H v re-evaluated inside the three-term update, alpha of the new vector "
+                     "accumulated while it is in registers) + ~3.5*N (border kernel: the edges that cross CTA tiles)")
+    else:
+        step_bytes = apply_bytes + update_bytes
+        step_note = ("bytes per plain step: 32*N with the recompute step (KA2 8N + KB 24N: H v is re-evaluated instead of "
+                     "written and re-read), 48*N with the two-pass step (SURVEY 8d), + the operator's own bytes for stored operators")
     moved_gbs = step_bytes / ms_per_step / 1e6
-    fused = {"step_kernel": step_kernel,
+    fused = {"step_kernel": step_kernel, "alpha_in_update": bool(alpha_in_update),
              "moved_bytes_per_step": step_bytes,                       # what this implementation actually moves
              "achieved_gbs": moved_gbs if plain else None,
              "frac_of_measured_peak": moved_gbs / peak if plain else None,
              "frac_of_8TBs_nominal": moved_gbs / 8000.0 if plain else None,
-             "note": "bytes per plain step: 32*N with the recompute step (KA2 8N + KB 24N: H v is re-evaluated instead of "
-                     "written and re-read), 48*N with the two-pass step (SURVEY 8d), + the operator's own bytes for stored "
-                     "operators; null when Gram-Schmidt sweeps ran"}
+             "note": step_note + "; null when Gram-Schmidt sweeps ran"}
     if is_stencil:
         # BASELINE's target (>= 70 % of the HBM roofline for the fused step at 512^3) is stated for the two-pass
         # step of SURVEY 8d, 48*N bytes: the same step time expressed in that accounting
@@ -541,28 +681,41 @@ def main():
                                           "frac_of_measured_peak": survey_gbs / peak if plain else None,
                                           "frac_of_8TBs_nominal": survey_gbs / 8000.0 if plain else None}
 
+    n_solves_e = Re * len(chunks)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']}", "grid": list(grid), "unknowns": M_total,
-                   "unknowns_per_gpu": M_local, "lanczos_m": chunks, "reorth": wl["reorth"],
-                   "cgs_passes": wl["cgs_passes"], "l2": "inputs larger than L2 (each vector %.2f GB)" % (8 * M_local / 1e9),
+                   "unknowns_per_gpu": M_local, "lanczos_m": chunks, "chunked": len(chunks) > 1, "reorth": wl["reorth"],
+                   "cgs_passes": wl["cgs_passes"], "l2": "inputs larger than L2 (each vector %.2f GB)" % (8 * M_local / 1e9)
+                   if 8 * M_local > 126e6 else "vectors of %.1f MB fit L2: this configuration is launch/latency-bound" % (8 * M_local / 1e6),
                    "sharding": ("z-slabs, one process per GPU" if is_stencil else "contiguous row blocks (z-slabs of cells), ghost-index exchange over peer memory, one process per GPU") if world > 1 else "single GPU",
                    "aggregate": ("strong scaling: value = K / time of the one global solve" if strong else
                                  "value = n_gpus * K / time: each GPU advances its 512^3 shard K steps; "
                                  "the global (n_gpus x larger) solve advances K steps"),
-                   "global_steps_per_sec": K / (ms_dev / 1e3)},
-        "e2e": {"value": (1 if strong else world) * K / e_wall, "unit": UNIT, "h2d_bytes_per_step": 8.0 * M_local * len(chunks) / K,
+                   "repeats": R,
+                   "timed_region": "the K-step solve (pre-step, K steps, alpha/beta back to the host) repeated %d times "
+                                   "back to back = %.2f s; value and ms_per_step are the sustained figures over the whole "
+                                   "region, burst = the fastest single solve" % (R, ms_dev / 1e3),
+                   "global_steps_per_sec": R * K / (ms_dev / 1e3), "host": numa},
+        "timed_region_s": ms_dev / 1e3,
+        "burst": {"value": scale_n * K / (burst_ms / 1e3), "ms_per_step": burst_ms / K,
+                  "note": "fastest single K-step solve of the region (device time of the loop alone)"},
+        "e2e": {"value": scale_n * Re * K / e_wall, "unit": UNIT, "h2d_bytes_per_step": 8.0 * M_local * len(chunks) / K,
                 "d2h_bytes_per_step": (sum(3 * (8 * (c + 2) + 512) + 32 for c in chunks)) / K,
-                "wall_s": e_wall},
+                "wall_s": e_wall, "solves": n_solves_e,
+                "note": "every solve: start vector H2D from pinned host memory (%.2f GB), K steps, alpha/beta D2H, "
+                        "H_eff and the lowest Ritz values on the host" % (8.0 * M_local / 1e9)},
         "gpu_launches": launches,
+        "gpu_launches_per_solve": launches / max(1, R * len(chunks)),
         "clocks": clocks,
         "roofline": roofline,
         "kernels": per_kernel,
         "gram_schmidt_ms": gs_ms,
         "reorth_steps": reorths,
         "fused_step": fused,
+        "parity_check": parity,
         "ritz_lowest": [float(x) for x in theta[:4]],
     }
     if world > 1:

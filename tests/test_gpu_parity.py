@@ -236,6 +236,7 @@ def test_sweep_form_follows_use_cuda(lz):
     assert rel(gpu_form["alpha"], cpu_form["alpha"]) < 1e-13
 
 
+@pytest.mark.slow
 def test_config2_full_size_vs_oracle(lz):
     """BASELINE config 2 at its stated size: graph Laplacian of a 1 M-vertex 2-D Delaunay mesh, CSR in,
     m = 200, full re-orthogonalisation in the reference's form (IrrLanczos.py:193-260), against the
@@ -567,6 +568,44 @@ def test_recompute_step_matches_two_pass_and_oracle(lz, grid, bc, reorth):
         ref = orc.lanczos(H, n, seed=13)
         assert rel(ar, ref["alpha"]) < 1e-12 and rel(br, ref["beta"]) < 1e-12
         assert np.max(np.abs(Vr - ref["V"])) < 1e-12
+
+
+ALPHA_CASES = [((64, 16, 12), "periodic", False), ((128, 32, 5), "dirichlet", False), ((64, 8, 1), "periodic", False),
+               ((64, 8, 2), "periodic", True), ((192, 24, 40), "periodic", True), ((64, 64, 33), "dirichlet", True),
+               ((256, 64, 70), "periodic", False)]
+
+
+@pytest.mark.parametrize("grid,bc,pot", ALPHA_CASES)
+def test_alpha_accumulated_inside_update(lz, grid, bc, pot):
+    """Recompute step on whole 64 x 8 tiles: alpha_{j+1} comes from KB (edges inside a CTA tile) + the
+    border kernel (edges across tiles, z-chunks and the periodic wrap) instead of a KA pass; against
+    the KA form and against the oracle."""
+    M = int(np.prod(grid))
+    diag = np.cos(np.arange(M) * 0.37) * 0.3 if pot else None
+    off = [-1.0, -0.7, -1.2]
+    op = lz.StencilOperator(grid, 6.5, off, bc=bc, diag=diag)
+    H = orc.laplacian_csr(grid, 6.5, off, periodic=(bc == "periodic"), diag=diag)
+    n = 14
+    ref = orc.lanczos(H, n, seed=5, reorth=False)
+    res = {}
+    for flag in (True, False):
+        L = lz.Lanczos(op)
+        L.execute_Lanczos(n, seed=5, reorth="none", kb_alpha=flag, profile=True)
+        assert L.result.step_kernel == "recompute" and L.result.alpha_in_update == flag
+        assert (L.result.kernel_ms["border"][1] > 0) == flag
+        res[flag] = (np.diag(L.H_eff).copy(), np.diag(L.H_eff, 1).copy())
+    k = 8                                                       # without sweeps round-off differences grow
+    assert rel(res[True][0][:k], res[False][0][:k]) < 1e-12 and rel(res[True][1][:k], res[False][1][:k]) < 1e-12
+    assert rel(res[True][0][:k], ref["alpha"][:k]) < 1e-12 and rel(res[True][1][:k], ref["beta"][:k]) < 1e-12
+    # without a basis (three-row ring), and with selective sweeps that fire (alpha re-taken after the sweep)
+    R = lz.Lanczos(op)
+    R.execute_Lanczos(n, seed=5, reorth="none", keep_basis=False)
+    assert R.result.alpha_in_update and rel(np.diag(R.H_eff)[:k], res[True][0][:k]) < 1e-12
+    full = orc.lanczos(H, 30, seed=5)
+    S = lz.Lanczos(op)
+    S.execute_Lanczos(30, seed=5, reorth="selective", cgs_passes=2, select_tol=1e-15)      # fires at once: ~ full CGS2
+    assert S.result.alpha_in_update and S.result.reorth_count >= 25
+    assert rel(np.diag(S.H_eff), full["alpha"]) < 1e-11 and rel(np.diag(S.H_eff, 1), full["beta"]) < 1e-11
 
 
 def test_recompute_step_with_potential_27pt_and_ring(lz):

@@ -35,6 +35,9 @@ CASES = [
     ((40, 36), "dirichlet", 3, "selective", 2),
     ((15, 6, 8), "periodic", 2, "full", 1),           # odd nx: scalar path, odd plane
     ((257,), "dirichlet", 4, "full", 1),              # 1-D segments
+    ((64, 16, 12), "periodic", 3, "selective", 2),    # whole tiles: alpha inside KB + border kernel, slab-top edge from the ghost plane
+    ((64, 8, 8), "dirichlet", 2, "none", 1),
+    ((128, 8, 6), "periodic", 6, "none", 1),          # one plane per shard
 ]
 
 

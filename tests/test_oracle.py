@@ -171,3 +171,57 @@ def test_deuteron27_matches_reference(golden):
     res = orc.lanczos(H, 60, seed=78)
     np.testing.assert_allclose(res["alpha"], golden["deut27_alpha"], rtol=1e-12)
     np.testing.assert_allclose(res["beta"], golden["deut27_beta"], rtol=1e-12)
+
+
+def test_blocked_sweep_is_bit_identical():
+    """gram_schmidt_row_blocked (used by the full-size config-2 GPU parity test) against the plain
+    restatement of Lanczos.py:247-249, bit for bit, zero tail rows included."""
+    rs = np.random.RandomState(1)
+    for n, M, j, nrows in [(7, 1000, 3, 7), (9, 100003, 4, 5), (5, 70000, 0, 1), (6, 33, 5, 6), (4, 129, 1, 2)]:
+        V = rs.uniform(-1, 1, (n, M)) / np.sqrt(M)
+        V[nrows:] = 0.0
+        A, B = V.copy(), V.copy()
+        orc.gram_schmidt_row(A, j)
+        orc.gram_schmidt_row_blocked(B, j, nrows=nrows, threads=3)
+        assert np.array_equal(A, B)
+    H = orc.delaunay_graph_laplacian(2000, seed=0)
+    a, b = orc.lanczos(H, 30, seed=99), orc.lanczos(H, 30, seed=99, blocked=True)
+    assert np.array_equal(a["alpha"], b["alpha"]) and np.array_equal(a["beta"], b["beta"]) and np.array_equal(a["V"], b["V"])
+
+
+def test_gpu_form_sweep_matches_the_reference_expression():
+    """Regular/Lanczos.py:236-238 (use_cuda=True branch, CuPy there): the same expressions on NumPy arrays."""
+    rs = np.random.RandomState(2)
+    V = rs.uniform(-1, 1, (6, 500)) / np.sqrt(500)
+    j = 2
+    W = V.copy()
+    ip = np.sum(W[j] * W, axis=1)
+    ip[j] = 0
+    W[j] = W[j] - np.sum(ip[:, None] * W, axis=0)
+    U = V.copy()
+    orc.gram_schmidt_row_gpu_form(U, j)
+    assert np.array_equal(U, W)
+    # the two forms agree to rounding on a normalised row
+    V[j] /= np.linalg.norm(V[j])
+    A, B = V.copy(), V.copy()
+    orc.gram_schmidt_row(A, j)
+    orc.gram_schmidt_row_gpu_form(B, j)
+    assert np.max(np.abs(A - B)) < 1e-15
+
+
+def test_vendored_reference_matches_golden():
+    """oracle/_ref (bench.py's reference arm) is the unmodified reference: it reproduces the golden alpha/beta."""
+    from oracle import build_ref
+    mods = build_ref.load()
+    if mods is None:
+        pytest.skip("oracle/_ref not built (no /root/reference in reach)")
+    import contextlib
+    import io
+    man = build_ref.manifest()
+    assert set(man["files"]) == {"Lanczos.py", "IrrLanczos.py", "Hamiltonian.py"}
+    H = orc.laplacian_csr((200, 200), 4.0, -1.0, periodic=False)
+    L = mods[0].Lanczos(H)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        L.execute_Lanczos(20, seed=99, use_cuda=False)
+    ref = orc.lanczos(H, 20, seed=99)
+    assert np.array_equal(np.diag(L.H_eff), ref["alpha"]) and np.array_equal(np.diag(L.H_eff, 1), ref["beta"])
