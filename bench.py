@@ -388,8 +388,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-cgs-fusion", action="store_true", help="CGS2 as four separate sweeps (comparison runs)")
-    ap.add_argument("--no-kb-alpha", action="store_true", help="recompute step with a KA pass per step (comparison runs)")
-    ap.add_argument("--min-region-s", type=float, default=1.5,
+    ap.add_argument("--kb-alpha", action="store_true",
+                    help="recompute step with alpha accumulated inside KB + border kernel instead of a KA pass (comparison runs)")
+    ap.add_argument("--min-region-s", type=float, default=1.2,
                     help="the K-step solve is repeated until the timed region is at least this long")
     ap.add_argument("--step-kernel", default="auto", choices=["auto", "two_pass", "recompute", "fused"],
                     help="auto = the library default (recompute for matrix-free operators)")
@@ -441,7 +442,7 @@ def main():
     H, grid = build_operator(lz, args.workload, world, rank)
     M_total = int(np.prod(grid))
     opts = dict(reorth=wl["reorth"], cgs_passes=wl["cgs_passes"], ref_compat=True, step_kernel=args.step_kernel,
-                cgs_fused=not args.no_cgs_fusion, kb_alpha=not args.no_kb_alpha)
+                cgs_fused=not args.no_cgs_fusion, kb_alpha=args.kb_alpha)
 
     if world > 1:
         from lanczos_b200 import team as lzteam

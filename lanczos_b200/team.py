@@ -422,7 +422,7 @@ class _TeamBase:
 
     def execute_Lanczos(self, n, seed=99, use_cuda=True, v0=None, *, reorth="full", cgs_passes=1,
                         ref_compat=True, keep_basis=True, breakdown_tol=0.0, select_tol=0.0,
-                        profile=False, step_kernel="auto", cgs_fused=True, sweep_form=0, kb_alpha=True, **_ignored):
+                        profile=False, step_kernel="auto", cgs_fused=True, sweep_form=0, kb_alpha=False, **_ignored):
         torch = engine._torch()
         n = int(n)
         if n > self.M:

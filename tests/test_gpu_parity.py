@@ -599,11 +599,11 @@ def test_alpha_accumulated_inside_update(lz, grid, bc, pot):
     assert rel(res[True][0][:k], ref["alpha"][:k]) < 1e-12 and rel(res[True][1][:k], ref["beta"][:k]) < 1e-12
     # without a basis (three-row ring), and with selective sweeps that fire (alpha re-taken after the sweep)
     R = lz.Lanczos(op)
-    R.execute_Lanczos(n, seed=5, reorth="none", keep_basis=False)
+    R.execute_Lanczos(n, seed=5, reorth="none", keep_basis=False, kb_alpha=True)
     assert R.result.alpha_in_update and rel(np.diag(R.H_eff)[:k], res[True][0][:k]) < 1e-12
     full = orc.lanczos(H, 30, seed=5)
     S = lz.Lanczos(op)
-    S.execute_Lanczos(30, seed=5, reorth="selective", cgs_passes=2, select_tol=1e-15)      # fires at once: ~ full CGS2
+    S.execute_Lanczos(30, seed=5, reorth="selective", cgs_passes=2, select_tol=1e-15, kb_alpha=True)      # fires at once: ~ full CGS2
     assert S.result.alpha_in_update and S.result.reorth_count >= 25
     assert rel(np.diag(S.H_eff), full["alpha"]) < 1e-11 and rel(np.diag(S.H_eff, 1), full["beta"]) < 1e-11
 

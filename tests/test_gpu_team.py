@@ -48,9 +48,11 @@ def test_local_team_matches_single_gpu(lz, grid, bc, world, reorth, passes):
     op = lz.StencilOperator(grid, 2.0 * dim + 0.25, [-1.0, -0.8, -1.1][:dim], bc=bc)
     n = 24
     one = lz.Lanczos(op)
+    kba = (grid[0] % 64 == 0)        # whole-tile cases: alpha inside KB + border kernel (slab-top edge from the ghost plane)
     one.execute_Lanczos(n, seed=7, reorth=reorth, cgs_passes=passes)
     team = LocalTeamLanczos(op, world)
-    team.execute_Lanczos(n, seed=7, reorth=reorth, cgs_passes=passes)
+    team.execute_Lanczos(n, seed=7, reorth=reorth, cgs_passes=passes, kb_alpha=kba)
+    assert team.result.alpha_in_update == (kba and reorth != "full")
     a1, b1 = np.diag(one.H_eff), np.diag(one.H_eff, 1)
     a2, b2 = np.diag(team.H_eff), np.diag(team.H_eff, 1)
     tol = 1e-12 if reorth != "none" else 1e-9

@@ -54,8 +54,8 @@ def case_recompute():
     ref = orc.lanczos(H, n, seed=3)
     op = lz.StencilOperator(grid, 6.0, -1.0)
     L = lz.Lanczos(op)
-    for kw in (dict(reorth="full", use_cuda=False), dict(reorth="selective", cgs_passes=2, select_tol=1e-13),
-               dict(reorth="full", cgs_passes=2), dict(reorth="none", keep_basis=False)):
+    for kw in (dict(reorth="full", use_cuda=False), dict(reorth="selective", cgs_passes=2, select_tol=1e-13, kb_alpha=True),
+               dict(reorth="full", cgs_passes=2), dict(reorth="none", keep_basis=False, kb_alpha=True)):
         import warnings
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
