@@ -112,6 +112,36 @@ int lz_op_csr_create_dev(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, con
                          const int32_t* indices_dev, const double* data_dev, int fmt, int sigma,
                          lz_op** out);
 
+/* Diagonal potential evaluated on the device: out_dev[i + nx*(j + ny*k)] = f(x[i], y[j], z[k]) for
+ * a postfix program f over the coordinates and constants (op codes below; CONST carries the index
+ * of its constant in bits 8..).  Replaces the three nested Python loops of
+ * Hamiltonian.create_sparse_V (Hamiltonian.py:35-46); the result is what lz_op_stencil*_create
+ * take as diag_dev.  Arithmetic ops round once each (no fma contraction), like NumPy's ufuncs.
+ * shape[3]; x/y/z_host: the coordinate axes (Hamiltonian.py:15-17).  Synchronises. */
+#define LZ_POT_X       0
+#define LZ_POT_Y       1
+#define LZ_POT_Z       2
+#define LZ_POT_CONST   3
+#define LZ_POT_ADD     4    /* binary: ADD SUB MUL DIV POW MIN MAX */
+#define LZ_POT_SUB     5
+#define LZ_POT_MUL     6
+#define LZ_POT_DIV     7
+#define LZ_POT_POW     8
+#define LZ_POT_MIN     9
+#define LZ_POT_MAX     10
+#define LZ_POT_NEG     11   /* unary: NEG SQRT EXP LOG ABS SIN COS TANH SQUARE */
+#define LZ_POT_SQRT    12
+#define LZ_POT_EXP     13
+#define LZ_POT_LOG     14
+#define LZ_POT_ABS     15
+#define LZ_POT_SIN     16
+#define LZ_POT_COS     17
+#define LZ_POT_TANH    18
+#define LZ_POT_SQUARE  19
+int lz_potential_eval(lz_ctx* ctx, const int64_t* shape, const double* x_host, const double* y_host,
+                      const double* z_host, int32_t nops, const int32_t* ops_host, int32_t nconsts,
+                      const double* consts_host, double* out_dev);
+
 int lz_op_rows(const lz_op* op, int64_t* M);
 int lz_op_nnz(const lz_op* op, int64_t* nnz_true, int64_t* nnz_stored);
 
@@ -249,6 +279,13 @@ int lz_team_lanczos_run(lz_team* team, lz_op* const* ops, const double* const* v
                         const lz_run_opts* opts, double* alpha_host, double* beta_host,
                         double* const* V_dev, const int64_t* ldv, double* row_scale_host,
                         lz_run_info* info);
+/* y = H x over the shards of a team (x_dev / y_dev: one local block per local shard) plus the two
+ * global sums of the residual diagnostics (print_good_eigs, Lanczos.py:171-176):
+ * dots_host[0] = x . H x, dots_host[1] = H x . H x, identical on every rank.  Synchronises. */
+int lz_team_apply_dots(lz_team* team, lz_op* const* ops, const double* const* x_dev,
+                       double* const* y_dev, double* dots_host);
+/* A team whose run failed part-way (LZ_ERR_CUDA / LZ_ERR_PEER) refuses further runs: destroy it and
+ * create a new one on every rank. */
 int lz_team_destroy(lz_team* team);
 
 /* Deterministic device reductions used by the diagnostics (test_is_normalized,

@@ -7,9 +7,10 @@ Only the hot path lives here: hand-written sm_100a CUDA (csrc/) behind a C ABI
 """
 from ._capi import LanczosBreakdown
 from .engine import Context, DeviceOperator, StencilOperator, reference_T27_weights, run_lanczos
+from .hamiltonian import Hamiltonian, MatrixFreeMatrix
 from .irregular import IrrLanczos
 from .regular import Lanczos
 
-__all__ = ["Lanczos", "IrrLanczos", "StencilOperator", "DeviceOperator", "Context", "reference_T27_weights",
-           "run_lanczos", "LanczosBreakdown"]
+__all__ = ["Lanczos", "IrrLanczos", "Hamiltonian", "MatrixFreeMatrix", "StencilOperator", "DeviceOperator", "Context",
+           "reference_T27_weights", "run_lanczos", "LanczosBreakdown"]
 __version__ = "0.1.0"

@@ -62,6 +62,7 @@ SIGNATURES = {
     "lz_op_csr_create": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, C.c_int, C.c_int, _P(_vp)]),
     "lz_op_csr_shard_create": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, C.c_int, C.c_int, _P(_vp)]),
     "lz_op_csr_create_dev": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, C.c_int, C.c_int, _P(_vp)]),
+    "lz_potential_eval": (C.c_int, [_vp, _P(_i64), _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "lz_op_rows": (C.c_int, [_vp, _P(_i64)]),
     "lz_op_nnz": (C.c_int, [_vp, _P(_i64), _P(_i64)]),
     "lz_op_apply": (C.c_int, [_vp, _vp, _vp]),
@@ -81,6 +82,7 @@ SIGNATURES = {
     "lz_team_attach": (C.c_int, [_vp, C.c_int, _P(_vp), C.c_int, C.c_int]),
     "lz_team_set_ghosts": (C.c_int, [_vp, C.c_int, _i32, _vp, _vp, _vp]),
     "lz_team_lanczos_run": (C.c_int, [_vp, _P(_vp), _P(_vp), _i32, _P(RunOpts), _vp, _vp, _P(_vp), _P(_i64), _vp, _P(RunInfo)]),
+    "lz_team_apply_dots": (C.c_int, [_vp, _P(_vp), _P(_vp), _P(_vp), _vp]),
     "lz_team_destroy": (C.c_int, [_vp]),
 }
 

@@ -235,6 +235,7 @@ struct lz_team {
     CommLayout layout{};
     std::vector<lz_shard> shards;
     unsigned long long seq = 0;          // sequence number of the last cross-rank exchange
+    bool poisoned = false;               // a run failed part-way: the ranks' sequence numbers may differ for good
 };
 
 namespace {
@@ -1027,8 +1028,102 @@ extern "C" int lz_team_lanczos_run(lz_team* team, lz_op* const* ops, const doubl
     LZ_REQUIRE(team && ops && v0_dev && opts, "lz_team_lanczos_run: null argument");
     for (int s = 0; s < team->nlocal; ++s)
         LZ_REQUIRE(team->shards[s].comm[team->shards[s].rank], "lz_team_lanczos_run: shard %d is not attached", s);
-    return run_loop(team, team->nlocal, ops, v0_dev, n, opts, alpha_host, beta_host, V_dev, ldv,
-                    row_scale_host, info);
+    if (team->poisoned) {
+        set_error("lz_team_lanczos_run: an earlier run on this team failed part-way; its exchange sequence may "
+                  "differ between the ranks - destroy the team and create a new one on every rank");
+        return LZ_ERR_PEER;
+    }
+    const int rc = run_loop(team, team->nlocal, ops, v0_dev, n, opts, alpha_host, beta_host, V_dev, ldv,
+                            row_scale_host, info);
+    // a breakdown is detected identically on every rank; anything else may have left the ranks out of step
+    if (rc != LZ_OK && rc != LZ_ERR_BREAKDOWN && rc != LZ_ERR_INVALID) team->poisoned = true;
+    return rc;
+}
+
+// y = H x over the shards of a team, with the two global sums the residual diagnostics need.
+// The same exchange as one loop step: halo planes / ghost entries of x pushed to the neighbours,
+// a flag round, the operator kernel, and the rank-ordered sums of the CTA partials.
+extern "C" int lz_team_apply_dots(lz_team* team, lz_op* const* ops, const double* const* x_dev,
+                                  double* const* y_dev, double* dots_host) {
+    LZ_REQUIRE(team && ops && x_dev && y_dev && dots_host, "lz_team_apply_dots: null argument");
+    const int nl = team->nlocal;
+    const bool split = nl > 1;
+    std::vector<ShardRun> R(nl);
+    for (int s = 0; s < nl; ++s) {
+        ShardRun& r = R[s];
+        r.op = ops[s];
+        LZ_REQUIRE(r.op && x_dev[s] && y_dev[s], "lz_team_apply_dots: null operator or vector of shard %d", s);
+        r.ctx = r.op->ctx;
+        r.sh = &team->shards[s];
+        LZ_REQUIRE(r.sh->ctx == r.ctx, "lz_team_apply_dots: operator %d is not on its shard's context", s);
+        LZ_REQUIRE(r.sh->comm[r.sh->rank], "lz_team_apply_dots: shard %d is not attached", s);
+        r.M = r.op->M;
+        r.pc = r.sh->pc;
+        LZ_CUDA(cudaSetDevice(r.ctx->device));
+        LZ_CUDA(cudaMemsetAsync(r.ctx->scratch, 0, 64 * 8, r.ctx->stream));
+        r.pc.err = reinterpret_cast<int*>(r.ctx->scratch + 8);
+        r.st.flags = reinterpret_cast<int*>(r.ctx->scratch + 16);      // fin_apply(FIN_ALPHA) touches no flag
+    }
+    int launches = 0;
+    auto each = [&](auto&& fn) -> int {
+        for (int s = 0; s < nl; ++s) {
+            if (nl > 1) LZ_CUDA(cudaSetDevice(R[s].ctx->device));
+            LZ_CHECK(fn(R[s], s));
+        }
+        return LZ_OK;
+    };
+    auto exchange = [&](auto&& launch) -> int {
+        const unsigned long long seq = ++team->seq;
+        if (!split) return each([&](ShardRun& r, int) { return launch(r, seq, (int)LZ_XCHG_FUSED); });
+        LZ_CHECK(each([&](ShardRun& r, int) { return launch(r, seq, (int)LZ_XCHG_PUSH); }));
+        return each([&](ShardRun& r, int) { return launch(r, seq, (int)LZ_XCHG_COMBINE); });
+    };
+    auto sum_to = [&](int slot) -> int {
+        return exchange([&](ShardRun& r, unsigned long long seq, int mode) -> int {
+            FinOp f;
+            f.kind = FIN_ALPHA;
+            f.out = r.ctx->scratch + slot;
+            LZ_CUDA(launch_k(fin_scalar_kernel, dim3(1), dim3(kThreads), 0, r.ctx->stream, (const double*)r.ctx->partials,
+                             r.np, f, r.st, r.pc, seq, mode, (const int*)nullptr));
+            return LZ_OK;
+        });
+    };
+    LZ_CHECK(each([&](ShardRun& r, int s) {
+        HaloPush h = halo_for(team, r, 0);
+        LZ_CHECK(launch_halo_push(r.ctx, x_dev[s], r.M, &h));
+        return push_ghosts(team, r, x_dev[s], 0, nullptr, &launches);
+    }));
+    LZ_CHECK(exchange([&](ShardRun& r, unsigned long long seq, int mode) -> int {
+        LZ_CUDA(launch_k(peer_sync_kernel, dim3(1), dim3(32), 0, r.ctx->stream, r.pc, seq, mode, (const int*)nullptr));
+        return LZ_OK;
+    }));
+    LZ_CHECK(each([&](ShardRun& r, int s) {
+        bind_ghosts(team, r, 0);
+        bind_gather(team, r, 0);
+        int l2 = 0;
+        return launch_apply_dot(r.op, x_dev[s], nullptr, y_dev[s], r.ctx->partials, &r.np, &l2, nullptr, nullptr);
+    }));
+    LZ_CHECK(sum_to(0));                                               // x . H x
+    LZ_CHECK(each([&](ShardRun& r, int s) { return launch_dot(r.ctx, y_dev[s], y_dev[s], r.M, r.ctx->partials, &r.np); }));
+    LZ_CHECK(sum_to(1));                                               // H x . H x
+    std::vector<int> err(nl, 0);
+    for (int s = 0; s < nl; ++s) {
+        ShardRun& r = R[s];
+        if (nl > 1) LZ_CUDA(cudaSetDevice(r.ctx->device));
+        if (s == 0) LZ_CUDA(cudaMemcpyAsync(dots_host, r.ctx->scratch, 16, cudaMemcpyDeviceToHost, r.ctx->stream));
+        LZ_CUDA(cudaMemcpyAsync(&err[s], r.pc.err, sizeof(int), cudaMemcpyDeviceToHost, r.ctx->stream));
+    }
+    for (int s = 0; s < nl; ++s) {
+        if (nl > 1) LZ_CUDA(cudaSetDevice(R[s].ctx->device));
+        LZ_CUDA(cudaStreamSynchronize(R[s].ctx->stream));
+    }
+    for (int s = 0; s < nl; ++s)
+        if (err[s]) {
+            set_error("multi-GPU exchange timed out on rank %d (a peer did not arrive)", team->shards[s].rank);
+            team->poisoned = true;
+            return LZ_ERR_PEER;
+        }
+    return LZ_OK;
 }
 
 extern "C" int lz_team_destroy(lz_team* team) {

@@ -141,10 +141,29 @@ def save_checkpoint(path: str, solver, with_basis: bool = True) -> str:
     T = solver.H_eff
     out = {"alpha": np.diag(T).copy(), "beta": np.diag(T, 1).copy(), "n": np.int64(T.shape[0]),
            "M": np.int64(solver.M), "format": np.int64(1)}
+    base = path[:-4] if path.endswith(".npz") else path
+    team = getattr(solver, "_team", None)
+    if team is not None:
+        # row-sharded run: the basis is written shard by shard (no process ever holds all of it);
+        # the header file carries the partition so that a restore can check it
+        out["shard_starts"] = np.asarray([team.plan.rows(r)[0] for r in range(team.world)] + [team.M], dtype=np.int64)
+        if with_basis:
+            for s, r in zip(team.shards, team.results):
+                r0, r1 = team.plan.rows(s.rank)
+                np.savez(shard_path(base, s.rank), V_rows=r.basis_rows_host(), rows=np.asarray([r0, r1], dtype=np.int64),
+                         format=np.int64(1))
+            out["sharded_basis"] = np.int64(1)
+        if team.shards[0].rank == 0:
+            np.savez(base, **out)
+        return base + ".npz"
     if with_basis:
         out["V_rows"] = solver.result.basis_rows_host()          # (n, M), rows = Lanczos vectors
-    np.savez(path, **out)
-    return path if path.endswith(".npz") else path + ".npz"
+    np.savez(base, **out)
+    return base + ".npz"
+
+
+def shard_path(base: str, rank: int) -> str:
+    return "%s.shard%d.npz" % (base, rank)
 
 
 def load_checkpoint(path: str) -> dict:
@@ -155,10 +174,12 @@ def load_checkpoint(path: str) -> dict:
     return d
 
 
-def restore_checkpoint(solver, path: str):
+def restore_checkpoint(solver, path: str, devices=None, fmt="auto", sigma=0):
     """Put a saved run back into `solver` (a Lanczos / IrrLanczos instance for the same operator):
     H_eff on the host, the basis - when it was saved - back in HBM, so that get_H_eigs, H_eigvecs and
-    print_good_eigs work without running the loop again."""
+    print_good_eigs work without running the loop again.  A checkpoint of a row-sharded run is
+    restored shard by shard onto `devices` (same meaning as in execute_Lanczos; the partition must
+    be the one the checkpoint was written with)."""
     import torch
     from . import engine
     from ._capi import RunInfo
@@ -166,6 +187,50 @@ def restore_checkpoint(solver, path: str):
     n, M = int(d["n"]), int(d["M"])
     if M != solver.M:
         raise ValueError(f"checkpoint is for M = {M}, the operator has M = {solver.M}")
+    if "shard_starts" in d and devices is not None:
+        team = solver._team_for(devices, fmt, sigma)
+        if team is None:
+            raise ValueError("restore_checkpoint: `devices` does not describe a row-sharded run")
+        starts = [team.plan.rows(r)[0] for r in range(team.world)] + [team.M]
+        if list(d["shard_starts"]) != starts:
+            raise ValueError("the checkpoint was written with another partition of the rows")
+        team._ensure_team(n)
+        base = path[:-4] if path.endswith(".npz") else path
+        results = []
+        for s in team.shards:
+            Ml = team.plan.local_rows(s.rank)
+            ld = engine.padded_ld(Ml)
+            V_dev = None
+            if int(d.get("sharded_basis", 0)):
+                with np.load(shard_path(base, s.rank)) as z:
+                    rows, Vr = z["rows"], z["V_rows"]
+                if tuple(rows) != tuple(team.plan.rows(s.rank)):
+                    raise ValueError(f"shard file of rank {s.rank} covers other rows")
+                with torch.cuda.device(s.ctx.device):
+                    V_dev = torch.zeros((n, ld), dtype=torch.float64, device=s.ctx.torch_device)
+                    V_dev[:, :Ml] = torch.from_numpy(np.ascontiguousarray(Vr)).to(s.ctx.torch_device)
+            info = RunInfo()
+            info.steps_done = n
+            results.append(engine.LanczosResult(s.ctx, n, Ml, d["alpha"].copy(), d["beta"].copy(), V_dev, ld, np.ones(n), info))
+        team.n = n
+        team._results = results
+        team._H_eff = results[0].tridiagonal()
+        team.Lanczos_has_been_executed = True
+        solver.n = n
+        solver._team = team
+        solver._result = results[0]
+        solver._H_eff = team._H_eff
+        solver._V_host = None
+        solver._Y_dev = None
+        solver.H_eigs_have_been_found = False
+        solver.Lanczos_has_been_executed = True
+        return solver
+    if "shard_starts" in d and int(d.get("sharded_basis", 0)):
+        # sharded checkpoint onto one GPU: stitch the shard files together
+        base = path[:-4] if path.endswith(".npz") else path
+        world = len(d["shard_starts"]) - 1
+        d = dict(d)
+        d["V_rows"] = np.concatenate([np.load(shard_path(base, r))["V_rows"] for r in range(world)], axis=1)
     ctx = engine.Context.default()
     ld = engine.padded_ld(M)
     V_dev = None
@@ -179,6 +244,8 @@ def restore_checkpoint(solver, path: str):
     solver._result = res
     solver._H_eff = res.tridiagonal()
     solver._V_host = None
+    solver._team = None
+    solver._Y_dev = None
     solver.H_eigs_have_been_found = False
     solver.Lanczos_has_been_executed = True
     return solver

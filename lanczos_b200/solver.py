@@ -33,6 +33,7 @@ class LanczosBase:
         self.H_exact_eigs_have_been_found = False
         self._result = None
         self._V_host = None
+        self._team = None            # row-sharded run (devices=...): lanczos_b200.team object
 
     # ---- lazy properties (Lanczos.py:28-66) -----------------------------------------------
     @property
@@ -48,7 +49,7 @@ class LanczosBase:
         if not self.Lanczos_has_been_executed:
             raise ValueError(_NOT_RUN)
         if self._V_host is None:
-            self._V_host = self._result.basis_rows_host()
+            self._V_host = (self._team if self._team is not None else self._result).basis_rows_host()
         return self._V_host.T
 
     @property
@@ -95,14 +96,20 @@ class LanczosBase:
     # ---- the loop ---------------------------------------------------------------------------
     def _execute(self, n, seed, use_cuda, v0, *, reorth="full", cgs_passes=1, ref_compat=True,
                  fmt="auto", sigma=0, device=None, keep_basis=True, breakdown_tol=0.0,
-                 select_tol=0.0, profile=False, step_kernel="auto", cgs_fused=True, kb_alpha=False, verbose=True):
+                 select_tol=0.0, profile=False, step_kernel="auto", cgs_fused=True, kb_alpha=False, verbose=True,
+                 devices=None):
         """Keyword-only extras (all default to the reference's behaviour):
         reorth 'full' | 'selective' | 'none'; cgs_passes 1 | 2; ref_compat (the v0-discarding
         pre-step and the (2-|v|^2) sweep form of the reference); fmt 'auto' | 'csr' | 'sell' and
         sigma for sparse operators; device index; keep_basis; breakdown_tol; select_tol;
         profile (per-kernel CUDA-event timing); step_kernel 'auto' | 'two_pass' | 'fused' | 'recompute';
         cgs_fused (CGS2: one read of the basis for the update of sweep 1 and the dots of sweep 2);
-        verbose (the reference's '+++' banners)."""
+        verbose (the reference's '+++' banners);
+        devices: row-sharded run over several GPUs behind the same API - a list of device indices
+        (this process drives one shard per device) or "auto" (one process per GPU under torchrun: the
+        initialised torch.distributed group is the team).  Every result (H_eff, V, H_eigvals,
+        H_eigvecs, print_good_eigs) is then assembled from the shards; alpha/beta are bit-identical
+        on every rank."""
         if n > self.M:
             raise ValueError("n cannot be larger than M!")                  # Lanczos.py:76-77
         if ref_compat and n < 2:
@@ -114,6 +121,29 @@ class LanczosBase:
         if verbose:
             print("+++ Executing Lanczos algorithm")
         self.n = n
+        team = self._team_for(devices, fmt, sigma)
+        if team is not None:
+            np.random.seed(seed)
+            self._result = None
+            self._V_host = None
+            self._team = None
+            self.Lanczos_has_been_executed = False
+            team.execute_Lanczos(n, seed, True, v0, reorth=reorth, cgs_passes=cgs_passes, ref_compat=ref_compat,
+                                 keep_basis=keep_basis, breakdown_tol=breakdown_tol, select_tol=select_tol,
+                                 profile=profile, step_kernel=step_kernel, cgs_fused=cgs_fused, kb_alpha=kb_alpha,
+                                 sweep_form=self._GPU_SWEEP_FORM if use_cuda else 0)
+            self._team = team
+            self._result = team.result
+            self._H_eff = team.H_eff
+            self._Y_dev = None
+            self.H_eigs_have_been_found = False
+            if verbose:
+                print("+++ Lanczos executed successfully.")
+            self.Lanczos_has_been_executed = True
+            return
+        self._team = None
+        if devices is not None and devices != "auto" and len(list(devices)) == 1:
+            device = int(list(devices)[0])
         ctx = Context.default(device)
         # the device copy of the operator (CSR upload / SELL conversion) is made once per instance
         key = (id(ctx), fmt, sigma)
@@ -145,15 +175,43 @@ class LanczosBase:
             print("+++ Lanczos executed successfully.")
         self.Lanczos_has_been_executed = True
 
+    def _team_for(self, devices, fmt, sigma):
+        """The row-sharded driver for `devices` (None: single-GPU run), built once per instance."""
+        if devices is None:
+            return None
+        from . import team as lzteam
+        if isinstance(devices, str):
+            if devices != "auto":
+                raise ValueError("devices: a list of device indices or 'auto'")
+            import torch.distributed as dist
+            if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+                return None
+            key, make = ("dist", fmt, sigma), (lambda: lzteam.TeamLanczos(self.H, fmt=fmt, sigma=sigma))
+        else:
+            devs = [int(d) for d in devices]
+            if len(devs) <= 1:
+                return None
+            key = (tuple(devs), fmt, sigma)
+            make = (lambda: lzteam.LocalTeamLanczos(self.H, len(devs), devices=devs, fmt=fmt, sigma=sigma))
+        cache = self.__dict__.setdefault("_team_cache", {})
+        if key not in cache:
+            cache[key] = make()
+        return cache[key]
+
     # ---- Ritz pairs (Lanczos.py:145-163) ------------------------------------------------------
     def _ritz(self, check_vectors):
         if not self.Lanczos_has_been_executed:
             raise ValueError(_NOT_RUN)
         print("+++ Converting eigenvectors from H_eff to H basis.")
         theta, S = np.linalg.eigh(self.H_eff)                   # small n x n problem: host LAPACK
-        Y = self._result.ritz_vectors_dev(S)                    # K5 on the device
-        self._Y_dev = Y                                         # kept for the residual diagnostics
-        Yh = np.ascontiguousarray(Y[:, :self.M].cpu().numpy().T)   # (M, n) like the reference
+        if self._team is not None:
+            Y = self._team.ritz_vectors_dev(S)                  # K5 on every shard: each lifts its own rows
+            self._Y_dev = Y
+            Yh = np.ascontiguousarray(self._team.rows_host(Y).T)
+        else:
+            Y = self._result.ritz_vectors_dev(S)                # K5 on the device
+            self._Y_dev = Y                                     # kept for the residual diagnostics
+            Yh = np.ascontiguousarray(Y[:, :self.M].cpu().numpy().T)   # (M, n) like the reference
         if check_vectors:
             self.test_is_normalized(Yh, tol=0.001)
             self.test_is_orthogonal(Yh, tol=0.01)
@@ -169,9 +227,13 @@ class LanczosBase:
 
     def ritz_vectors(self, k, which="lowest"):
         """(theta[:k], Y) with Y a CUDA tensor (k, M): only the wanted Ritz vectors are lifted,
-        (n + k) * 8 * M bytes of traffic instead of the reference's full (M, n) product."""
+        (n + k) * 8 * M bytes of traffic instead of the reference's full (M, n) product.  After a
+        row-sharded run Y is a list with one (k, M_local) tensor per local shard."""
         theta, S = np.linalg.eigh(self.H_eff)
         sel = np.arange(k) if which == "lowest" else np.arange(len(theta) - k, len(theta))
+        if self._team is not None:
+            Ys = self._team.ritz_vectors_dev(S[:, sel])
+            return theta[sel], [Y[:, :self._team.plan.local_rows(s.rank)] for s, Y in zip(self._team.shards, Ys)]
         Y = self._result.ritz_vectors_dev(S[:, sel])
         return theta[sel], Y[:, :self.M]
 
@@ -184,6 +246,11 @@ class LanczosBase:
         from . import _capi
         torch = engine._torch()
         eigvecs = self.H_eigvecs                                  # runs get_H_eigs when needed
+        if self._team is not None:
+            Ys = getattr(self, "_Y_dev", None)
+            if not isinstance(Ys, list):
+                Ys = self._team.ritz_vectors_dev(np.linalg.eigh(self.H_eff)[1])
+            return self._team.residual_cosines(Ys)
         ctx = Context.default()
         op = getattr(self, "_device_op", None)
         if op is None or op.ctx is not ctx:

@@ -458,6 +458,15 @@ class _TeamBase:
             beta.ctypes.data_as(C.c_void_p), Vp, ldp, scale.ctypes.data_as(C.c_void_p), C.byref(info))
         if status == _capi.LZ_ERR_BREAKDOWN:
             raise LanczosBreakdown(self.lib.lz_last_error().decode(), steps_done=info.steps_done)
+        if status in (_capi.LZ_ERR_CUDA, _capi.LZ_ERR_PEER):
+            # the ranks may be out of step for good (the library refuses further runs on this team):
+            # every rank sees an error - its own or a peer timeout - and builds a fresh team on the next call
+            msg = self.lib.lz_last_error().decode()
+            try:
+                self._destroy_team()
+            except Exception:
+                pass
+            raise RuntimeError(f"lanczos_b200 error {status}: {msg} (the team was discarded; the next run creates a new one)")
         _capi.check(status)
         self.n = n
         self._results = [engine.LanczosResult(s.ctx, n, self.plan.local_rows(s.rank), alpha, beta, V, ld,
@@ -497,6 +506,55 @@ class _TeamBase:
     def M_local(self):
         return self.plan.local_rows(self.shards[0].rank)
 
+    # ---- what the drop-in classes need after the loop (Lanczos.py:132-185), shard by shard ------------------
+    def ritz_vectors_dev(self, S):
+        """Per local shard: Y (k, ld) CUDA tensor, Y[c] = this shard's rows of V @ S[:, c] (K5 on every shard;
+        the lift needs no exchange: each rank lifts its own rows, Lanczos.py:154-156)."""
+        return [r.ritz_vectors_dev(S) for r in self.results]
+
+    def _gather_blocks(self, blocks):
+        """Per-local-shard host arrays (k, M_local) -> the global (k, M) array on every process."""
+        return np.concatenate(blocks, axis=1)
+
+    def rows_host(self, tensors):
+        """(k, M) host array from per-shard CUDA tensors (k, ld >= M_local)."""
+        blocks = [t[:, :self.plan.local_rows(s.rank)].cpu().numpy() for s, t in zip(self.shards, tensors)]
+        return self._gather_blocks(blocks)
+
+    def basis_rows_host(self):
+        """(n, M) host array of the normalised basis, assembled from the shards."""
+        return self._gather_blocks([r.basis_rows_host() for r in self.results])
+
+    def apply_dots(self, xs, ys=None):
+        """y = H x over the shards (xs / ys: one CUDA tensor of M_local doubles per local shard; ys allocated
+        when None).  Returns (x.Hx, Hx.Hx, ys), the sums taken over all ranks in rank order."""
+        torch = engine._torch()
+        self._ensure_team(max(self.max_steps, 2))
+        nl = len(self.shards)
+        if ys is None:
+            ys = [torch.empty_like(x) for x in xs]
+        for s in self.shards:
+            torch.cuda.synchronize(s.ctx.device)
+        dots = np.zeros(2)
+        ops = (C.c_void_p * nl)(*[s.op_handle for s in self.shards])
+        xp = (C.c_void_p * nl)(*[x.data_ptr() for x in xs])
+        yp = (C.c_void_p * nl)(*[y.data_ptr() for y in ys])
+        self._pre_run_barrier()
+        _capi.check(self.lib.lz_team_apply_dots(self.team, ops, xp, yp, dots.ctypes.data_as(C.c_void_p)))
+        return float(dots[0]), float(dots[1]), ys
+
+    def residual_cosines(self, Ys):
+        """cos^2 of the angle between H y and y for every row of the sharded Ritz-vector blocks `Ys`
+        (Lanczos.py:171-176) - the operator kernel with its halo / ghost exchange, sums over the peer ring."""
+        k = Ys[0].shape[0]
+        out = np.zeros(k)
+        ys = None
+        for i in range(k):
+            xs = [Y[i, :self.plan.local_rows(s.rank)] for s, Y in zip(self.shards, Ys)]
+            xhx, hxhx, ys = self.apply_dots(xs, ys)
+            out[i] = xhx ** 2 / hxhx if hxhx > 0.0 else 0.0
+        return out
+
     def nnz_local(self):
         """(true, stored) entries of the first local shard of a sparse operator."""
         t, s = C.c_int64(), C.c_int64()
@@ -533,12 +591,6 @@ class LocalTeamLanczos(_TeamBase):
             if s.comm_ptr:
                 self.lib.lz_comm_free(s.ctx.handle, s.comm_ptr)
                 s.comm_ptr = None
-
-    def basis_rows_host(self):
-        """(n, M) host array assembled from the shards (tests)."""
-        parts = [r.basis_rows_host() for r in self.results]
-        return np.concatenate(parts, axis=1)
-
 
 class TeamLanczos(_TeamBase):
     """One process per GPU (torchrun): this process drives the shard of its rank; exchange
@@ -578,6 +630,13 @@ class TeamLanczos(_TeamBase):
 
     def _pre_run_barrier(self):
         self.dist.barrier()
+
+    def _gather_blocks(self, blocks):
+        """The local (k, M_local) block of every rank -> the global (k, M) array on every rank (host side,
+        through the process group: this is output plumbing, used when the caller asks for host arrays)."""
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, blocks[0])
+        return np.concatenate(parts, axis=1)
 
     def _gather_ghost_lists(self, mine: dict) -> dict:
         parts = [None] * self.dist.get_world_size()

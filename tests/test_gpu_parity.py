@@ -770,3 +770,75 @@ def test_deuteron27_driver_operator(lz, golden):
     L2 = lz.Lanczos(Hs)
     L2.execute_Lanczos(60, seed=78)
     assert rel(np.diag(L2.H_eff)[:50], golden["deut27_alpha"][:50]) < TOL_AB
+
+
+GUARD = 4096           # doubles on either side of every buffer the library writes
+
+
+@pytest.mark.parametrize("case", ["stencil_full_cgs2", "stencil_selective_kb_alpha", "sparse_sell", "team", "lift"])
+def test_writes_stay_inside_the_callers_buffers(lz, case):
+    """compute-sanitizer is closed on the GPU pool (it refuses to start), so out-of-bounds writes are
+    hunted with guard bands instead: every buffer the C ABI writes (basis rows incl. the TMA-staged K4c
+    tiles and the in-place sweeps, Ritz vectors, apply outputs) sits between bands of a sentinel that
+    must survive, and the results must still match the oracle.  Sizes are odd on purpose (ragged last
+    tiles / chunks / planes)."""
+    import ctypes as C
+    import torch
+    from lanczos_b200 import _capi, engine
+    sentinel = -7.0e300
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def guarded(rows, ld):
+        buf = torch.full((rows * ld + 2 * GUARD,), sentinel, dtype=torch.float64, device=dev)
+        return buf, buf[GUARD:GUARD + rows * ld].view(rows, ld)
+
+    def intact(buf, rows, ld):
+        torch.cuda.synchronize()
+        return bool((buf[:GUARD] == sentinel).all()) and bool((buf[GUARD + rows * ld:] == sentinel).all())
+
+    if case in ("stencil_full_cgs2", "stencil_selective_kb_alpha", "lift"):
+        grid = (64, 24, 7) if case != "stencil_full_cgs2" else (66, 9, 5)
+        H = orc.laplacian_csr(grid, 6.0, -1.0, periodic=True)
+        op = lz.StencilOperator(grid, 6.0, -1.0)
+        ctx = engine.Context.default()
+        dop = op.device_handle(ctx)
+        M, n = op.M, 20
+        ld = engine.padded_ld(M)
+        buf, V = guarded(n, ld)
+        kw = dict(reorth="full", cgs_passes=2) if case != "stencil_selective_kb_alpha" else \
+            dict(reorth="selective", cgs_passes=2, select_tol=1e-14, kb_alpha=True)
+        v0 = orc.start_vector(M, seed=3)
+        res = engine.run_lanczos(dop, v0, n, V_dev=V, **kw)
+        assert intact(buf, n, ld)
+        ref = orc.lanczos(H, n, seed=3)
+        assert rel(res.alpha[:10], ref["alpha"][:10]) < 1e-10
+        if case == "lift":
+            theta, S = np.linalg.eigh(res.tridiagonal())
+            ybuf, Y = guarded(n, ld)
+            _capi.check(ctx.lib.lz_ritz_vectors(ctx.handle, C.c_void_p(V.data_ptr()), ld, n, M,
+                                                res.row_scale.ctypes.data_as(C.c_void_p),
+                                                np.asfortranarray(S).ctypes.data_as(C.c_void_p), n,
+                                                C.c_void_p(Y.data_ptr()), ld))
+            assert intact(ybuf, n, ld) and intact(buf, n, ld)
+            abuf, y = guarded(1, ld)
+            _capi.check(ctx.lib.lz_op_apply(dop.handle, C.c_void_p(Y[0].data_ptr()), C.c_void_p(y.data_ptr())))
+            assert intact(abuf, 1, ld)
+            assert bool((y[0, M:] == sentinel).all())           # the pad of the row is not written either
+    elif case == "sparse_sell":
+        G = orc.delaunay_graph_laplacian(5003, seed=1)
+        ctx = engine.Context.default()
+        dop = engine.as_device_operator(G, ctx)
+        M, n = G.shape[0], 24
+        ld = engine.padded_ld(M)
+        buf, V = guarded(n, ld)
+        res = engine.run_lanczos(dop, orc.start_vector(M, seed=3), n, V_dev=V, reorth="full", cgs_passes=2)
+        assert intact(buf, n, ld)
+        assert rel(res.alpha[:10], orc.lanczos(G, n, seed=3)["alpha"][:10]) < 1e-10
+    else:
+        from lanczos_b200.team import LocalTeamLanczos
+        grid = (64, 8, 9)
+        op = lz.StencilOperator(grid, 6.0, -1.0)
+        t = LocalTeamLanczos(op, 3)
+        t.execute_Lanczos(16, seed=3, reorth="selective", cgs_passes=2, select_tol=1e-14, kb_alpha=True)
+        ref = orc.lanczos(orc.laplacian_csr(grid, 6.0, -1.0, periodic=True), 16, seed=3)
+        assert rel(np.diag(t.H_eff)[:10], ref["alpha"][:10]) < 1e-10

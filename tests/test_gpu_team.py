@@ -212,3 +212,108 @@ def test_local_team_stencil27(lz):
     team.execute_Lanczos(20, seed=5)
     assert rel(np.diag(team.H_eff), ref["alpha"]) < 1e-12
     assert rel(np.diag(team.H_eff, 1), ref["beta"]) < 1e-12
+
+
+def _same_up_to_sign(A, B, tol):
+    """columns of A and B agree up to a sign each"""
+    for i in range(A.shape[1]):
+        d = min(np.linalg.norm(A[:, i] - B[:, i]), np.linalg.norm(A[:, i] + B[:, i]))
+        assert d < tol, (i, d)
+
+
+def test_dropin_classes_row_sharded(lz, tmp_path, capsys):
+    """Multi-GPU behind the reference API: Lanczos(H).execute_Lanczos(n, devices=[...]) and everything the
+    reference class offers afterwards - H_eff, V, get_H_eigs / H_eigvecs (each shard lifts its rows),
+    print_good_eigs (sharded operator apply, sums over the peer ring), ritz_vectors(k), checkpoint -
+    against the single-GPU run of the same class (Lanczos.py:132-185)."""
+    import torch
+    from lanczos_b200 import io as lzio
+    d = torch.cuda.current_device()
+    ndev = torch.cuda.device_count()
+    devices = [i % ndev for i in range(3)] if ndev >= 2 else [d, d, d]
+    H, c, o, pot = orc.deuteron_hamiltonian(12)
+    op = lz.StencilOperator((12, 12, 12), c, o, diag=pot)
+    n = 60
+    one = lz.Lanczos(op)
+    one.execute_Lanczos(n, seed=78)
+    sh = lz.Lanczos(op)
+    sh.execute_Lanczos(n, seed=78, devices=devices)
+    assert rel(np.diag(sh.H_eff), np.diag(one.H_eff)) < 1e-12 and rel(np.diag(sh.H_eff, 1), np.diag(one.H_eff, 1)) < 1e-12
+    assert sh.V.shape == (12 ** 3, n) and np.max(np.abs(sh.V - one.V)) < 1e-11
+    one.get_H_eigs()
+    sh.get_H_eigs()                                   # includes the reference's normalisation / orthogonality asserts
+    np.testing.assert_allclose(sh.H_eigvals, one.H_eigvals, rtol=1e-10, atol=1e-12)
+    assert sh.H_eigvecs.shape == (12 ** 3, n)
+    _same_up_to_sign(sh.H_eigvecs[:, :5], one.H_eigvecs[:, :5], 1e-8)
+    ip1 = one.print_good_eigs(print_nr=5)
+    ip2 = sh.print_good_eigs(print_nr=5)
+    assert np.max(np.abs(ip1 - ip2)) < 1e-9
+    assert "EIGENVALUE AND EIGVENVECTOR COMPARISON" in capsys.readouterr().out
+    th1, Y1 = one.ritz_vectors(3)
+    th2, Y2 = sh.ritz_vectors(3)
+    assert isinstance(Y2, list) and len(Y2) == 3
+    Y2h = np.concatenate([y.cpu().numpy() for y in Y2], axis=1)
+    _same_up_to_sign(Y2h.T, Y1.cpu().numpy().T, 1e-8)
+    # sharded checkpoint: one file per shard, restored onto the same partition and onto one GPU
+    path = lzio.save_checkpoint(str(tmp_path / "run.npz"), sh)
+    for r in range(3):
+        assert os.path.exists(lzio.shard_path(str(tmp_path / "run"), r))
+    back = lz.Lanczos(op)
+    lzio.restore_checkpoint(back, path, devices=devices)
+    back.get_H_eigs()
+    np.testing.assert_allclose(back.H_eigvals, one.H_eigvals, rtol=1e-10, atol=1e-12)
+    _same_up_to_sign(back.H_eigvecs[:, :3], one.H_eigvecs[:, :3], 1e-8)
+    flat = lz.Lanczos(op)
+    lzio.restore_checkpoint(flat, path)
+    assert np.max(np.abs(flat.V - one.V)) < 1e-11
+    # irregular class, sparse row blocks
+    G = orc.delaunay_graph_laplacian(5000, seed=2)
+    a = lz.IrrLanczos(G)
+    a.execute_LanczosOld(30, seed=5)
+    b = lz.IrrLanczos(G)
+    b.execute_LanczosOld(30, seed=5, devices=devices[:2])
+    assert rel(np.diag(b.H_eff), np.diag(a.H_eff)) < 1e-12
+    a.get_H_eigs()
+    b.get_H_eigs()
+    _same_up_to_sign(b.H_eigvecs[:, -3:], a.H_eigvecs[:, -3:], 1e-8)
+    assert np.max(np.abs(a.print_good_eigs(print_nr=3) - b.print_good_eigs(print_nr=3))) < 1e-9
+
+
+def _rank_dropin(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import lanczos_b200 as lz
+        op = lz.StencilOperator((64, 32, 48), 6.0, -1.0)
+        L = lz.Lanczos(op)
+        L.execute_Lanczos(30, seed=7, devices="auto", verbose=False)
+        L.get_H_eigs()
+        ip = L.print_good_eigs(print_nr=2)
+        if rank == 0:
+            np.savez(out, T=L.H_eff, theta=L.H_eigvals, Y=L.H_eigvecs[:, :3], ip=ip, V=L.V[:, :4])
+        del L
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dropin_one_process_per_gpu(lz, tmp_path):
+    """devices="auto" under a process group: the torchrun form of the same drop-in call."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    out = str(tmp_path / "dropin.npz")
+    mp.spawn(_rank_dropin, args=(world, _free_port(), out), nprocs=world, join=True)
+    z = np.load(out)
+    one = lz.Lanczos(lz.StencilOperator((64, 32, 48), 6.0, -1.0))
+    one.execute_Lanczos(30, seed=7)
+    one.get_H_eigs()
+    assert rel(np.diag(z["T"]), np.diag(one.H_eff)) < 1e-12
+    np.testing.assert_allclose(z["theta"], one.H_eigvals, rtol=1e-10, atol=1e-12)
+    assert np.max(np.abs(z["V"] - one.V[:, :4])) < 1e-11
+    assert np.max(np.abs(z["ip"] - one.print_good_eigs(print_nr=2))) < 1e-9
