@@ -176,7 +176,8 @@ typedef struct lz_run_opts {
                               sweep 2 from one read of the basis); bit 1 (with ref_compat): the sweep
                               takes the LZ_SWEEP_GPU form of Regular/Lanczos.py:236-238 instead of
                               the (2 - |v|^2) form; bit 2: do not accumulate alpha inside KB (recompute
-                              step: a KA pass per step instead of the border kernel); 0 = defaults */
+                              step: a KA pass per step instead of the border kernel); bit 3: sparse row shards without
+                              the interior/boundary overlap on a second stream; 0 = defaults */
     double  breakdown_tol; /* stop when beta <= breakdown_tol * |alpha_0| (0: only 0/NaN) */
     double  select_tol;    /* selective: orthogonality level that triggers (0 -> sqrt(eps)) */
 } lz_run_opts;
@@ -203,6 +204,8 @@ typedef struct lz_run_info {
     float   border_ms;
     int32_t alpha_in_update;  /* 1: alpha of the next vector was accumulated inside KB (+ border kernel)
                                  instead of a KA pass over the vector                   */
+    int32_t overlap;          /* 1: sparse row shards - the interior rows of the next apply ran while the ghost
+                                 entries and the beta sum travelled on a second stream  */
 } lz_run_info;
 
 /* Runs n steps from v0_dev (M doubles).  Outputs: alpha_host[n], beta_host[n-1]

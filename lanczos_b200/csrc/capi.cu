@@ -148,6 +148,9 @@ int lz_ctx_create(int device, void* cuda_stream, lz_ctx** out) {
 int lz_ctx_destroy(lz_ctx* c) {
     if (!c) return LZ_OK;
     cudaSetDevice(c->device);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->partials) cudaFree(c->partials);
     if (c->scratch) cudaFree(c->scratch);
     if (c->tickets) cudaFree(c->tickets);
@@ -231,9 +234,11 @@ int lz_op_csr_create_dev(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, con
     LZ_CUDA(cudaSetDevice(ctx->device));
     lz_op* op = new lz_op();
     op->ctx = ctx;
-    const int st = build_from_device(op, M, ncols, nnz, indptr_dev, indices_dev, data_dev, fmt, sigma);
+    int st = build_from_device(op, M, ncols, nnz, indptr_dev, indices_dev, data_dev, fmt, sigma);
     if (st != LZ_OK) { lz_op_destroy(op); return st; }
     op->ncols = ncols;
+    st = sell_classify_spans(op);
+    if (st != LZ_OK) { lz_op_destroy(op); return st; }
     *out = op;
     return LZ_OK;
 }
@@ -257,6 +262,8 @@ static int csr_create_impl(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, c
                                  : build_sell(op, M, nnz, indptr, indices, data, sigma);
     if (st != LZ_OK) { lz_op_destroy(op); return st; }
     op->ncols = ncols;
+    st = sell_classify_spans(op);              // row shards: interior / boundary spans for the overlapped apply
+    if (st != LZ_OK) { lz_op_destroy(op); return st; }
     *out = op;
     return LZ_OK;
 }
@@ -303,6 +310,8 @@ int lz_op_destroy(lz_op* op) {
     if (op->sell.col) cudaFree(op->sell.col);
     if (op->sell.val) cudaFree(op->sell.val);
     if (op->sell.row_of) cudaFree(op->sell.row_of);
+    if (op->sell.spans_int) cudaFree(op->sell.spans_int);
+    if (op->sell.spans_bnd) cudaFree(op->sell.spans_bnd);
     delete op;
     return LZ_OK;
 }

@@ -14,6 +14,10 @@ struct lz_ctx {
     double* scratch = nullptr;     // 64 doubles of device scratch (lz_dot, lz_reorthogonalize, ...)
     unsigned int* tickets = nullptr;   // last-CTA tickets of the fin tails (fin.cuh); zero between launches
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // second stream: the interior part of a row shard's SpMV runs here while the ghost entries and the beta
+    // sum travel over NVLink on `stream` (created on first use; lower priority than nothing - see lanczos.cu)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void* arena = nullptr;         // grow-only device workspace of lz_lanczos_run
     size_t arena_bytes = 0;
     std::vector<cudaEvent_t> event_pool;   // profile mode only
@@ -54,6 +58,13 @@ struct lz_sell {
     int32_t* col = nullptr;        // device, nnz_stored, column-major inside a chunk
     double* val = nullptr;         // device, nnz_stored
     int32_t* row_of = nullptr;     // device, nchunks*32: original row handled by (chunk, lane); -1 = padding row
+    // row shards: spans (runs of `split_span` chunks = one sorting window) whose rows touch no ghost column
+    // ("interior": can be applied before the ghost exchange has completed) and the others ("boundary")
+    int split_span = 0;            // 0: not classified
+    int32_t* spans_int = nullptr;  // device, n_int span indices, ascending
+    int32_t* spans_bnd = nullptr;  // device, n_bnd span indices, ascending
+    int n_int = 0, n_bnd = 0;
+    int np_int = 0;                // CTAs (= partials) of the last interior launch
 };
 
 struct lz_op {
@@ -87,6 +98,13 @@ struct HaloPush {
 int launch_apply_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
                      double* partials, int* nparts, int* launches, const int* flag_dev = nullptr,
                      const FinTail* fin = nullptr);
+// Row shard in SELL form, split by spans (lz_sell::spans_int / spans_bnd): part 1 = interior spans
+// (partials[0 .. np_int)), part 2 = boundary spans (partials[np_int ..), *nparts = np_int + its CTAs; a fin
+// tail sums both ranges).  `stream`: where to launch (the context's second stream for the interior part).
+bool spmv_split_supported(const lz_op* op);
+int sell_classify_spans(lz_op* op);
+int launch_spmv_part(lz_op* op, int part, const double* x, const double* scale_dev, double* y, double* partials,
+                     int* nparts, const int* flag_dev, const FinTail* fin, cudaStream_t stream);
 
 // ---- "recompute" step of matrix-free operators (stencil.cu, stencil27.cu) -------------------
 // KA: launch_apply_dot with y == nullptr reduces alpha without writing w.
@@ -127,10 +145,11 @@ int launch_dot(lz_ctx* ctx, const double* x, const double* y, int64_t M, double*
 int launch_update_norm(lz_ctx* ctx, const double* w, const double* a, const double* b,
                        const double* ca_dev, const double* sa_dev, const double* cb_dev,
                        const double* sb_dev, double* out, int64_t M, double* partials, int* nparts,
-                       const HaloPush* halo = nullptr, const FinTail* fin = nullptr);
+                       const HaloPush* halo = nullptr, const FinTail* fin = nullptr,
+                       const double* sw_dev = nullptr /* w is scaled by *sw_dev first (nullable: 1) */);
 int launch_halo_push(lz_ctx* ctx, const double* x, int64_t M, const HaloPush* halo);
 int launch_ghost_push(lz_ctx* ctx, const double* x, const int32_t* send_idx, int nsend, int world,
-                      const int* seg_start, double* const* dst, const int* flag_dev);
+                      const int* seg_start, double* const* dst, const int* flag_dev, cudaStream_t stream = nullptr);
 int launch_scale(lz_ctx* ctx, double* x, int64_t M, double s);
 
 // ---- Gram-Schmidt block GEMV pair (reorth.cu) --------------------------------------------

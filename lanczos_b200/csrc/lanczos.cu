@@ -259,6 +259,8 @@ struct ShardRun {           // per-shard state of one run
     double* om_prev = nullptr;
     KernelTimer kt;
     int np = 0;
+    int np_beta = 0;        // sparse row shards: CTAs of the last update kernel (its partials: first half of ctx->partials;
+                            // the apply kernels of that mode write theirs to the second half)
     int np_kb = 0;          // CTAs of the last KB launch (its alpha partials sit in the second half of ctx->partials)
     int ncg = 0;
     double* row(int j) const { return V ? V + (int64_t)j * ldv : ring + (int64_t)(j % 3) * ld_int; }
@@ -297,14 +299,15 @@ void bind_gather(const lz_team* team, ShardRun& r, int parity) {
 }
 
 // sparse row shard: send the entries of `x` that other ranks need (gather + NVLink peer stores)
-int push_ghosts(const lz_team* team, ShardRun& r, const double* x, int parity, const int* flag, int* launches) {
+int push_ghosts(const lz_team* team, ShardRun& r, const double* x, int parity, const int* flag, int* launches,
+                cudaStream_t stream = nullptr) {
     if (!team || !r.sh || r.op->kind == LZ_OP_STENCIL || r.sh->nsend == 0) return LZ_OK;
     double* dst[kMaxWorld];
     for (int q = 0; q < team->world; ++q)
         dst[q] = reinterpret_cast<double*>((char*)r.sh->comm[q] + team->layout.gather_off) +
                  (size_t)parity * team->nghost + r.sh->dst_off[q];
     ++*launches;
-    return launch_ghost_push(r.ctx, x, r.sh->send_idx, r.sh->nsend, team->world, r.sh->seg_start, dst, flag);
+    return launch_ghost_push(r.ctx, x, r.sh->send_idx, r.sh->nsend, team->world, r.sh->seg_start, dst, flag, stream);
 }
 
 // The loop over `nl` local shards (nl == 1 and team == nullptr: the plain single-GPU solve).
@@ -432,6 +435,32 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     for (int s = 0; s < nl && kb_alpha; ++s)
         kb_alpha = update_alpha_supported(R[s].op, R[s].V ? R[s].V : R[s].ring, R[s].V ? R[s].V : R[s].ring);
 
+    // Row shards of a stored (sparse) operator.  (1) The ghost entries of a new vector are pushed by a kernel
+    // of their own AFTER the update kernel, and the flag of the beta exchange is what publishes them - so that
+    // exchange runs as a kernel after the push, not in the update kernel's tail.  (2) H is applied to the
+    // un-normalised row and 1/beta is folded in afterwards (alpha = s^2 r.Hr; K3 scales w on load), so the
+    // apply needs nothing from the beta exchange.  (3) Overlap: the interior spans of the next apply (no ghost
+    // column) run on the main stream while push + exchange run on a second, high-priority stream; only the
+    // boundary spans wait for the neighbours.  Not with full re-orthogonalisation (the sweep rewrites the row
+    // the early apply would read; Gram-Schmidt dominates there anyway).
+    const bool sparse_team = team && !recompute && !fused && ops[0]->kind != LZ_OP_STENCIL;
+    bool overlap = sparse_team && reorth != LZ_REORTH_FULL && !(opts->flags & 8);
+    for (int s = 0; s < nl && overlap; ++s) overlap = spmv_split_supported(R[s].op);
+    if (overlap) {
+        for (int s = 0; s < nl; ++s) {
+            lz_ctx* c = R[s].ctx;
+            LZ_CUDA(cudaSetDevice(c->device));
+            if (!c->stream2) {
+                int lo = 0, hi = 0;
+                LZ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                LZ_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi));
+                LZ_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+                LZ_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+            }
+        }
+    }
+    bool interior_done = false;          // the interior spans of H row_j were applied during the previous step
+
     // run `fn(shard)` on every local shard, on its device
     auto each = [&](auto&& fn) -> int {
         for (int s = 0; s < nl; ++s) {
@@ -453,7 +482,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     // (fin.cuh): produce(shard, tail) launches it.  One shard per process: the tail also does the cross-rank
     // sum.  Several local shards: the tails push, then one combine kernel per shard.  `pred`: the kernel
     // (and its combine) is predicated on the re-orthogonalisation flag of the step.
-    auto produce_fin = [&](auto&& op_of, auto&& produce, bool pred) -> int {
+    auto produce_fin = [&](auto&& op_of, auto&& produce, bool pred, int part_off = 0) -> int {
         unsigned long long seq = 0;
         if (team) seq = ++team->seq;
         LZ_CHECK(each([&](ShardRun& r) {
@@ -468,8 +497,8 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         }));
         if (!split) return LZ_OK;
         return each([&](ShardRun& r) {
-            LZ_CUDA(launch_k(fin_scalar_kernel, dim3(1), dim3(kThreads), 0, r.ctx->stream, (const double*)r.ctx->partials,
-                             r.np, op_of(r), r.st, r.pc, seq, (int)LZ_XCHG_COMBINE,
+            LZ_CUDA(launch_k(fin_scalar_kernel, dim3(1), dim3(kThreads), 0, r.ctx->stream,
+                             (const double*)(r.ctx->partials + part_off), r.np, op_of(r), r.st, r.pc, seq, (int)LZ_XCHG_COMBINE,
                              pred ? (const int*)(r.st.flags + 1) : (const int*)nullptr));
             ++launches;
             return LZ_OK;
@@ -498,6 +527,17 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
             f.delta = delta; f.eps1 = eps1; f.psi = psi;
         }
         return f;
+    };
+    // the beta exchange of row jn (+ omega) as a kernel of its own (sparse row shards: after the ghost push);
+    // `side`: on the shard's second stream
+    auto fin_beta_kernel = [&](int jn, auto&& mag_of, int omega_j, bool side) -> int {
+        return exchange([&](ShardRun& r, unsigned long long seq, int mode) -> int {
+            LZ_CUDA(launch_k(fin_scalar_kernel, dim3(1), dim3(kThreads), 0, side ? r.ctx->stream2 : r.ctx->stream,
+                             (const double*)r.ctx->partials, r.np_beta, op_beta(r, jn, mag_of(r), omega_j), r.st, r.pc, seq,
+                             mode, (const int*)nullptr));
+            ++launches;
+            return LZ_OK;
+        });
     };
     // alpha of row jn from the in-tile partials KB left in the second half of the partials buffer (r.np of
     // them) plus the border kernel's own
@@ -555,6 +595,15 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
                                  launches += l2;
                                  return rc;
                              }, false));
+        if (sparse_team) {
+            LZ_CHECK(each([&](ShardRun& r) {
+                ++launches;
+                LZ_CHECK(launch_update_norm(r.ctx, r.w, r.v0, nullptr, r.st.alpha_pre, r.st.v0scale, nullptr, nullptr,
+                                            r.row(0), r.M, r.ctx->partials, &r.np_beta, nullptr, nullptr));
+                return push_ghosts(team, r, r.row(0), 0, nullptr, &launches);
+            }));
+            LZ_CHECK(fin_beta_kernel(0, [](ShardRun& r) { return (const double*)r.st.alpha_pre; }, -1, false));
+        } else
         LZ_CHECK(produce_fin([&](ShardRun& r) { return op_beta(r, 0, r.st.alpha_pre, -1); },
                              [&](ShardRun& r, const FinTail* t) {
                                  HaloPush h = halo_for(team, r, 0);
@@ -713,7 +762,34 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         }
         // ---- w = H q_j, alpha_j = q_j . w ------------------------------------------------------
         // (alpha_j known from KB + border kernel of the previous step: only if a sweep just rewrote row j)
-        if (!alpha_known || maybe_reorth) {
+        if (sparse_team) {
+            // alpha_j = s_j^2 (r_j . H r_j), H applied to the un-normalised row; partials in the second half of the
+            // buffer (the beta exchange of the previous step may still be reading the first half)
+            if (interior_done && maybe_reorth) {
+                // a sweep that fired rewrote row j after its interior spans were applied: apply them again
+                LZ_CHECK(each([&](ShardRun& r) {
+                    ++launches;
+                    return launch_spmv_part(r.op, 1, r.row(j), nullptr, r.w, r.ctx->partials + kMaxPartials, &r.np,
+                                            r.st.flags + 1, nullptr, r.ctx->stream);
+                }));
+            }
+            const bool early = interior_done;
+            LZ_CHECK(produce_fin([&](ShardRun& r) { FinOp f; f.kind = FIN_ALPHA_S2; f.jn = j; f.out = r.st.alpha + j; return f; },
+                                 [&](ShardRun& r, const FinTail* t) {
+                                     bind_gather(team, r, par);
+                                     int l2 = 1;
+                                     int rc;
+                                     r.kt.begin(K_APPLY);
+                                     if (early) rc = launch_spmv_part(r.op, 2, r.row(j), nullptr, r.w, r.ctx->partials + kMaxPartials,
+                                                                      &r.np, nullptr, t, r.ctx->stream);
+                                     else rc = launch_apply_dot(r.op, r.row(j), nullptr, r.w, r.ctx->partials + kMaxPartials, &r.np,
+                                                                &l2, nullptr, t);
+                                     r.kt.end();
+                                     launches += l2;
+                                     return rc;
+                                 }, false, kMaxPartials));
+            interior_done = false;
+        } else if (!alpha_known || maybe_reorth) {
             const bool pred = alpha_known;
             LZ_CHECK(produce_fin([&](ShardRun& r) { return op_alpha(r.st.alpha + j); },
                                  [&](ShardRun& r, const FinTail* t) {
@@ -733,6 +809,41 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         }
         // ---- r = w - alpha_j q_j - beta_j q_{j-1}; beta_{j+1} = |r| --------------------------
         const bool want_alpha = kb_alpha && (j + 1 < n);
+        if (sparse_team) {
+            const bool ahead = overlap && (j + 1 < n);
+            LZ_CHECK(each([&](ShardRun& r) {
+                double* out = (j + 1 < n) ? r.row(j + 1) : r.w;
+                r.kt.begin(K_UPDATE);
+                const int rc = launch_update_norm(r.ctx, r.w, r.row(j), j > 0 ? r.row(j - 1) : nullptr, r.st.alpha + j,
+                                                  r.st.scale + j, r.st.beta + j, j > 0 ? r.st.scale + j - 1 : nullptr, out,
+                                                  r.M, r.ctx->partials, &r.np_beta, nullptr, nullptr, r.st.scale + j);
+                r.kt.end();
+                ++launches;
+                LZ_CHECK(rc);
+                if (ahead) {
+                    // fork: ghost push + beta exchange on the second stream, interior spans of H row_{j+1} here
+                    LZ_CUDA(cudaEventRecord(r.ctx->ev_fork, r.ctx->stream));
+                    LZ_CUDA(cudaStreamWaitEvent(r.ctx->stream2, r.ctx->ev_fork, 0));
+                }
+                if (j + 1 < n) return push_ghosts(team, r, out, (j + 1) & 1, nullptr, &launches, ahead ? r.ctx->stream2 : nullptr);
+                return LZ_OK;
+            }));
+            LZ_CHECK(fin_beta_kernel(j + 1, [](ShardRun& r) { return (const double*)r.st.alpha; }, (sel && j + 1 < n) ? j : -1, ahead));
+            if (ahead) {
+                LZ_CHECK(each([&](ShardRun& r) {
+                    LZ_CUDA(cudaEventRecord(r.ctx->ev_join, r.ctx->stream2));
+                    ++launches;
+                    r.kt.begin(K_APPLY);
+                    const int rc = launch_spmv_part(r.op, 1, r.row(j + 1), nullptr, r.w, r.ctx->partials + kMaxPartials, &r.np,
+                                                    nullptr, nullptr, r.ctx->stream);
+                    r.kt.end();
+                    LZ_CHECK(rc);
+                    LZ_CUDA(cudaStreamWaitEvent(r.ctx->stream, r.ctx->ev_join, 0));      // join: beta, scale, flags, ghosts
+                    return LZ_OK;
+                }));
+                interior_done = true;
+            }
+        } else
         LZ_CHECK(produce_fin([&](ShardRun& r) { return op_beta(r, j + 1, r.st.alpha, (sel && j + 1 < n) ? j : -1); },
                              [&](ShardRun& r, const FinTail* t) {
                                  double* out = (j + 1 < n) ? r.row(j + 1) : r.w;
@@ -846,6 +957,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         info->gsfused_ms = kms[K_GSFUSED]; info->gsfused_launches = kcnt[K_GSFUSED];
         info->border_ms = kms[K_BORDER]; info->border_launches = kcnt[K_BORDER];
         info->alpha_in_update = kb_alpha ? 1 : 0;
+        info->overlap = overlap ? 1 : 0;
     }
     return status;
 }

@@ -79,16 +79,20 @@ spmv_sell_dot_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __res
                      const double* __restrict__ val, const int32_t* __restrict__ row_of,
                      const double* __restrict__ x, const double* __restrict__ scale,
                      double* __restrict__ y, int64_t nchunks, double* __restrict__ partials,
-                     const double* __restrict__ xg, int32_t M, int span, const FinTail fin) {
+                     const double* __restrict__ xg, int32_t M, int span, const FinTail fin,
+                     const int32_t* __restrict__ span_list, int nlist, const int* __restrict__ flag) {
     pdl_prologue();
+    if (flag && *flag == 0) return;
     __shared__ double red[kWarps];
     const double s = scale ? __ldg(scale) : 1.0;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const double* const xgs = xg ? xg - M : x;        // ghost columns (>= M) of a sharded operator
-    const int64_t nspans = (nchunks + span - 1) / span;
+    // all spans, or the listed ones (interior / boundary part of a row shard)
+    const int64_t nspans = span_list ? (int64_t)nlist : (nchunks + span - 1) / span;
     double acc = 0.0;
-    for (int64_t sp = blockIdx.x; sp < nspans; sp += gridDim.x) {
+    for (int64_t si = blockIdx.x; si < nspans; si += gridDim.x) {
+        const int64_t sp = span_list ? (int64_t)__ldg(span_list + si) : si;
         const int64_t c_end = min(nchunks, (sp + 1) * span);
         for (int64_t c = sp * span + warp; c < c_end; c += kWarps) {
             const int64_t o0 = __ldg(chunk_off + c), o1 = __ldg(chunk_off + c + 1);
@@ -163,8 +167,85 @@ int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double*
     const int64_t nspans = (sl.nchunks + span - 1) / span;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nspans, std::min<int64_t>((int64_t)ctx->sms * 16, kMaxPartials)));
     LZ_CUDA(launch_k(spmv_sell_dot_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, sl.chunk_off, sl.col,
-                     sl.val, sl.row_of, x, scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, span, ft));
+                     sl.val, sl.row_of, x, scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, span, ft,
+                     (const int32_t*)nullptr, 0, flag_dev));
     if (nparts) *nparts = grid;
+    return LZ_OK;
+}
+
+static int upload(void** dev, const void* host, size_t bytes, cudaStream_t s);
+
+// ---- row shards: interior / boundary spans ---------------------------------------------------------
+// A span (one sorting window of sigma rows = sigma/32 chunks) is "boundary" when any entry stored in it
+// refers to a ghost column (>= M).  With a locality-preserving row order the boundary spans are the few
+// windows next to the block ends; everything else can be applied while the ghost entries are in flight.
+__global__ void __launch_bounds__(kThreads)
+sell_span_ghost_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __restrict__ col, int64_t nchunks,
+                       int32_t M, int span, int* __restrict__ span_has_ghost) {
+    const int64_t c = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    if (c >= nchunks) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t o0 = chunk_off[c], o1 = chunk_off[c + 1];
+    int any = 0;
+    for (int64_t k = o0 + lane; k < o1; k += 32) any |= (col[k] >= M);
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0 && any) span_has_ghost[c / span] = 1;
+}
+
+bool spmv_split_supported(const lz_op* op) {
+    return op->kind == LZ_OP_SELL && op->sell.split_span > 0 && op->sell.n_int > 0;
+}
+
+int sell_classify_spans(lz_op* op) {
+    lz_ctx* ctx = op->ctx;
+    lz_sell& sl = op->sell;
+    if (op->kind != LZ_OP_SELL || op->ncols <= op->M || sl.nchunks == 0) return LZ_OK;
+    const int span = std::max(kWarps, sl.sigma / 32);
+    const int64_t nspans = (sl.nchunks + span - 1) / span;
+    int* flags = nullptr;
+    LZ_CUDA(cudaMalloc((void**)&flags, (size_t)nspans * sizeof(int)));
+    LZ_CUDA(cudaMemsetAsync(flags, 0, (size_t)nspans * sizeof(int), ctx->stream));
+    const unsigned cgrid = (unsigned)((sl.nchunks + kWarps - 1) / kWarps);
+    sell_span_ghost_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(sl.chunk_off, sl.col, sl.nchunks, (int32_t)op->M, span, flags);
+    std::vector<int> h((size_t)nspans);
+    cudaError_t e = cudaMemcpyAsync(h.data(), flags, (size_t)nspans * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(flags);
+    if (e != cudaSuccess) { set_error("sell_classify_spans: %s", cudaGetErrorString(e)); return LZ_ERR_CUDA; }
+    std::vector<int32_t> in, bd;
+    for (int64_t s = 0; s < nspans; ++s) (h[(size_t)s] ? bd : in).push_back((int32_t)s);
+    sl.split_span = span;
+    sl.n_int = (int)in.size();
+    sl.n_bnd = (int)bd.size();
+    LZ_CHECK(upload((void**)&sl.spans_int, in.data(), in.size() * 4, ctx->stream));
+    LZ_CHECK(upload((void**)&sl.spans_bnd, bd.data(), bd.size() * 4, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LZ_OK;
+}
+
+int launch_spmv_part(lz_op* op, int part, const double* x, const double* scale_dev, double* y, double* partials,
+                     int* nparts, const int* flag_dev, const FinTail* fin, cudaStream_t stream) {
+    lz_ctx* ctx = op->ctx;
+    lz_sell& sl = op->sell;
+    LZ_REQUIRE(spmv_split_supported(op) && (part == 1 || part == 2), "launch_spmv_part: operator is not split");
+    const int32_t* list = part == 1 ? sl.spans_int : sl.spans_bnd;
+    const int nlist = part == 1 ? sl.n_int : sl.n_bnd;
+    // finer grid than the plain launch: CTAs leave the SMs often, so that the one-CTA exchange kernels of the
+    // main stream find a slot while the interior part is running
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nlist, std::min<int64_t>((int64_t)ctx->sms * 16, kMaxPartials / 2)));
+    FinTail ft = fin ? *fin : FinTail{};
+    double* pout = partials;
+    if (part == 1) {
+        sl.np_int = grid;
+    } else {
+        pout = partials + sl.np_int;            // boundary partials follow the interior ones
+        if (ft.op.kind != FIN_NONE) { ft.op.extra = partials; ft.op.nextra = sl.np_int; }
+    }
+    // an empty list still launches one CTA: its partial is 0 and its tail runs the bookkeeping / the exchange
+    LZ_CUDA(launch_k(spmv_sell_dot_kernel, dim3(grid), dim3(kThreads), 0, stream, sl.chunk_off, sl.col, sl.val,
+                     sl.row_of, x, scale_dev, y, sl.nchunks, pout, op->xghost, (int32_t)op->M, sl.split_span, ft,
+                     list, nlist, flag_dev));
+    if (nparts) *nparts = (part == 1) ? grid : sl.np_int + grid;
     return LZ_OK;
 }
 
@@ -193,7 +274,7 @@ ghost_push_kernel(const double* __restrict__ x, const GhostPushArgs g, const int
 }
 
 int launch_ghost_push(lz_ctx* ctx, const double* x, const int32_t* send_idx, int nsend, int world,
-                      const int* seg_start, double* const* dst, const int* flag_dev) {
+                      const int* seg_start, double* const* dst, const int* flag_dev, cudaStream_t stream) {
     if (nsend <= 0) return LZ_OK;
     GhostPushArgs g;
     g.send_idx = send_idx;
@@ -203,7 +284,7 @@ int launch_ghost_push(lz_ctx* ctx, const double* x, const int32_t* send_idx, int
     for (int q = world + 1; q < 17; ++q) g.seg_start[q] = nsend;
     for (int q = 0; q < 16; ++q) g.dst[q] = q < world ? dst[q] : nullptr;
     const int grid = std::max(1, std::min((nsend + kThreads - 1) / kThreads, ctx->sms * 4));
-    LZ_CUDA(launch_k(ghost_push_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, g, flag_dev));
+    LZ_CUDA(launch_k(ghost_push_kernel, dim3(grid), dim3(kThreads), 0, stream ? stream : ctx->stream, x, g, flag_dev));
     return LZ_OK;
 }
 

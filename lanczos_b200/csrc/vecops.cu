@@ -75,9 +75,11 @@ update_norm_kernel(const double* w, const double* __restrict__ a, const double* 
                    const double* __restrict__ ca, const double* __restrict__ sa,
                    const double* __restrict__ cb, const double* __restrict__ sb,
                    double* out, int64_t M, int vec_ok, double* __restrict__ partials,
-                   const HaloPush halo, const FinTail fin) {
+                   const HaloPush halo, const FinTail fin, const double* __restrict__ sw_p) {
     pdl_prologue();
     __shared__ double red[kWarps];
+    // w may arrive un-normalised (H applied to the un-normalised row before beta was known): r = sw*w - ...
+    const double sw = sw_p ? __ldg(sw_p) : 1.0;
     const double fa = (ca ? __ldg(ca) : 1.0) * (sa ? __ldg(sa) : 1.0);
     const double fb = HAS_B ? (cb ? __ldg(cb) : 1.0) * (sb ? __ldg(sb) : 1.0) : 0.0;
     double acc0 = 0.0, acc1 = 0.0;
@@ -92,8 +94,8 @@ update_norm_kernel(const double* w, const double* __restrict__ a, const double* 
             const double2 w0 = ld_stream2_rw(w + 2 * i), w1 = ld_stream2_rw(w + 2 * i1);
             const double2 a0 = ld_stream2(a + 2 * i), a1 = ld_stream2(a + 2 * i1);
             double2 r0, r1;
-            r0.x = fma(-fa, a0.x, w0.x); r0.y = fma(-fa, a0.y, w0.y);
-            r1.x = fma(-fa, a1.x, w1.x); r1.y = fma(-fa, a1.y, w1.y);
+            r0.x = fma(-fa, a0.x, sw * w0.x); r0.y = fma(-fa, a0.y, sw * w0.y);
+            r1.x = fma(-fa, a1.x, sw * w1.x); r1.y = fma(-fa, a1.y, sw * w1.y);
             if (HAS_B) {
                 const double2 b0 = ld_stream2(b + 2 * i), b1 = ld_stream2(b + 2 * i1);
                 r0.x = fma(-fb, b0.x, r0.x); r0.y = fma(-fb, b0.y, r0.y);
@@ -110,7 +112,7 @@ update_norm_kernel(const double* w, const double* __restrict__ a, const double* 
             const double2 w0 = ld_stream2_rw(w + 2 * i);
             const double2 a0 = ld_stream2(a + 2 * i);
             double2 r0;
-            r0.x = fma(-fa, a0.x, w0.x); r0.y = fma(-fa, a0.y, w0.y);
+            r0.x = fma(-fa, a0.x, sw * w0.x); r0.y = fma(-fa, a0.y, sw * w0.y);
             if (HAS_B) {
                 const double2 b0 = ld_stream2(b + 2 * i);
                 r0.x = fma(-fb, b0.x, r0.x); r0.y = fma(-fb, b0.y, r0.y);
@@ -120,7 +122,7 @@ update_norm_kernel(const double* w, const double* __restrict__ a, const double* 
             acc0 = fma(r0.x, r0.x, acc0); acc1 = fma(r0.y, r0.y, acc1);
         }
         if (tid == 0 && (M & 1)) {
-            double r = fma(-fa, a[M - 1], w[M - 1]);
+            double r = fma(-fa, a[M - 1], sw * w[M - 1]);
             if (HAS_B) r = fma(-fb, b[M - 1], r);
             out[M - 1] = r;
             halo_store1<HALO>(halo, M - 1, M, r);
@@ -128,7 +130,7 @@ update_norm_kernel(const double* w, const double* __restrict__ a, const double* 
         }
     } else {
         for (int64_t i = tid; i < M; i += nthr) {
-            double r = fma(-fa, ld_stream1(a + i), w[i]);
+            double r = fma(-fa, ld_stream1(a + i), sw * w[i]);
             if (HAS_B) r = fma(-fb, ld_stream1(b + i), r);
             out[i] = r;
             halo_store1<HALO>(halo, i, M, r);
@@ -143,7 +145,7 @@ update_norm_kernel(const double* w, const double* __restrict__ a, const double* 
 int launch_update_norm(lz_ctx* ctx, const double* w, const double* a, const double* b,
                        const double* ca_dev, const double* sa_dev, const double* cb_dev,
                        const double* sb_dev, double* out, int64_t M, double* partials, int* nparts,
-                       const HaloPush* halo, const FinTail* fin) {
+                       const HaloPush* halo, const FinTail* fin, const double* sw_dev) {
     const int grid = stream_grid(ctx, M, 4);
     const FinTail ft = fin ? *fin : FinTail{};
     HaloPush h{};
@@ -155,7 +157,7 @@ int launch_update_norm(lz_ctx* ctx, const double* w, const double* a, const doub
 #define LZ_UPD(HB, HL, bb, cbb, sbb)                                                               \
     LZ_CUDA(launch_k(update_norm_kernel<HB, HL>, dim3(grid), dim3(kThreads), 0, ctx->stream, w, a,       \
                      (const double*)bb, ca_dev, sa_dev, (const double*)cbb, (const double*)sbb, out, M,  \
-                     vec_ok, partials, h, ft))
+                     vec_ok, partials, h, ft, sw_dev))
     if (b) { if (push) LZ_UPD(true, true, b, cb_dev, sb_dev); else LZ_UPD(true, false, b, cb_dev, sb_dev); }
     else { if (push) LZ_UPD(false, true, nullptr, nullptr, nullptr); else LZ_UPD(false, false, nullptr, nullptr, nullptr); }
 #undef LZ_UPD

@@ -30,10 +30,12 @@ def _torch():
     return torch
 
 
-def run_flags(cgs_fused: bool = True, sweep_form: int = 0, kb_alpha: bool = False) -> int:
+def run_flags(cgs_fused: bool = True, sweep_form: int = 0, kb_alpha: bool = False, overlap: bool = True) -> int:
     """lz_run_opts.flags: bit 0 = CGS2 without K4c, bit 1 = the Regular GPU sweep form (LZ_SWEEP_GPU),
-    bit 2 = recompute step with a KA pass per step instead of alpha accumulated inside KB."""
-    return (0 if cgs_fused else 1) | (2 if sweep_form == _capi.LZ_SWEEP_GPU else 0) | (0 if kb_alpha else 4)
+    bit 2 = recompute step with a KA pass per step instead of alpha accumulated inside KB,
+    bit 3 = sparse row shards without the interior/boundary overlap."""
+    return ((0 if cgs_fused else 1) | (2 if sweep_form == _capi.LZ_SWEEP_GPU else 0) | (0 if kb_alpha else 4) |
+            (0 if overlap else 8))
 
 
 def padded_ld(M: int) -> int:
@@ -350,6 +352,7 @@ class LanczosResult:
                           "gs_fused": (float(info.gsfused_ms), info.gsfused_launches),
                           "border": (float(info.border_ms), info.border_launches)}
         self.alpha_in_update = bool(info.alpha_in_update)
+        self.overlap = bool(info.overlap)
 
     def tridiagonal(self) -> np.ndarray:
         """Dense H_eff like Lanczos.py:121-130."""

@@ -422,7 +422,7 @@ class _TeamBase:
 
     def execute_Lanczos(self, n, seed=99, use_cuda=True, v0=None, *, reorth="full", cgs_passes=1,
                         ref_compat=True, keep_basis=True, breakdown_tol=0.0, select_tol=0.0,
-                        profile=False, step_kernel="auto", cgs_fused=True, sweep_form=0, kb_alpha=False, **_ignored):
+                        profile=False, step_kernel="auto", cgs_fused=True, sweep_form=0, kb_alpha=False, overlap=True, **_ignored):
         torch = engine._torch()
         n = int(n)
         if n > self.M:
@@ -444,7 +444,7 @@ class _TeamBase:
                 Vs.append(torch.empty((n, ld), dtype=torch.float64, device=s.ctx.torch_device) if need_basis else None)
         alpha, beta, scale = np.zeros(n), np.zeros(max(n - 1, 0)), np.ones(n)
         opts = RunOpts(mode, int(cgs_passes), 1 if ref_compat else 0, 1 if profile else 0,
-                       engine.STEP_KERNEL[step_kernel], engine.run_flags(cgs_fused, sweep_form, kb_alpha), float(breakdown_tol), float(select_tol))
+                       engine.STEP_KERNEL[step_kernel], engine.run_flags(cgs_fused, sweep_form, kb_alpha, overlap), float(breakdown_tol), float(select_tol))
         info = RunInfo()
         ops = (C.c_void_p * nl)(*[s.op_handle for s in self.shards])
         v0p = (C.c_void_p * nl)(*[t.data_ptr() for t in starts])

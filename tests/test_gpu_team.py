@@ -317,3 +317,33 @@ def test_dropin_one_process_per_gpu(lz, tmp_path):
     np.testing.assert_allclose(z["theta"], one.H_eigvals, rtol=1e-10, atol=1e-12)
     assert np.max(np.abs(z["V"] - one.V[:, :4])) < 1e-11
     assert np.max(np.abs(z["ip"] - one.print_good_eigs(print_nr=2))) < 1e-9
+
+
+@pytest.mark.parametrize("world,reorth,passes", [(3, "selective", 2), (2, "none", 1), (4, "selective", 1)])
+def test_sparse_shards_overlap_interior_apply_with_exchange(lz, world, reorth, passes):
+    """Row shards of a SELL operator: the spans whose rows touch no ghost column are applied while the ghost
+    entries and the beta sum travel on a second stream (lz_run_info.overlap); against the same run without
+    the overlap, the single-GPU run and the oracle.  sigma = 64 so that these small shards have interior
+    spans at all; select_tol small enough that sweeps fire (the early interior apply is then redone)."""
+    from lanczos_b200.team import LocalTeamLanczos
+    H = orc.rgg_graph_laplacian(24000, mean_degree=13.0, seed=4)        # cell-ordered: ghosts only near block ends
+    n = 30
+    kw = dict(reorth=reorth, cgs_passes=passes, select_tol=1e-12 if reorth == "selective" else 0.0)
+    one = lz.IrrLanczos(H)
+    one.execute_LanczosOld(n, seed=3, sigma=64, **kw)
+    T = {}
+    for ov in (True, False):
+        team = LocalTeamLanczos(H, world, fmt="sell", sigma=64)
+        team.execute_LanczosOld(n, seed=3, overlap=ov, **kw)
+        assert team.result.overlap == ov
+        if reorth == "selective":
+            assert team.result.reorth_count > 0
+        T[ov] = team.H_eff.copy()
+        team.execute_LanczosOld(n, seed=3, overlap=ov, **kw)
+        assert np.array_equal(T[ov], team.H_eff)                        # two streams, still bit-reproducible
+    tol = 1e-12 if reorth != "none" else 1e-9
+    assert rel(np.diag(T[True]), np.diag(T[False])) < tol and rel(np.diag(T[True], 1), np.diag(T[False], 1)) < tol
+    assert rel(np.diag(T[True]), np.diag(one.H_eff)) < tol and rel(np.diag(T[True], 1), np.diag(one.H_eff, 1)) < tol
+    if reorth == "selective":
+        ref = orc.lanczos(H, n, seed=3)
+        assert rel(np.diag(T[True])[:12], ref["alpha"][:12]) < 1e-11
