@@ -193,7 +193,7 @@ sell_span_ghost_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __r
 }
 
 bool spmv_split_supported(const lz_op* op) {
-    return op->kind == LZ_OP_SELL && op->sell.split_span > 0 && op->sell.n_int > 0;
+    return op->kind == LZ_OP_SELL && op->sell.split_span > 0;     // either list may be empty
 }
 
 int sell_classify_spans(lz_op* op) {
