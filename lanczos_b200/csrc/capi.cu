@@ -20,10 +20,15 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+// Off unless LZ_PDL=1.  Measured on B200 at 512^3 it is worth 0.7 % of a step (0.8472 -> 0.8415 ms), and it is
+// not safe with this library's loads: a dependent grid's CTAs - and with them the L1 invalidation that normally
+// separates two kernels - may start while the primary is still writing, and data the primary produced is then
+// read through the non-coherent path (ld.global.nc / __ldg), which griddepcontrol.wait does not cover.  Seen as
+// wrong alpha from step 2-3 on in row-sharded two-pass runs (tools/dbg1.py), never with the attribute off.
 bool pdl_enabled() {
     static const bool on = []() {
         const char* e = getenv("LZ_PDL");
-        return !(e && e[0] == '0');
+        return e && e[0] == '1';
     }();
     return on;
 }
