@@ -390,6 +390,8 @@ def main():
     ap.add_argument("--no-cgs-fusion", action="store_true", help="CGS2 as four separate sweeps (comparison runs)")
     ap.add_argument("--kb-alpha", action="store_true",
                     help="recompute step with alpha accumulated inside KB + border kernel instead of a KA pass (comparison runs)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="sparse row shards without the interior/boundary overlap on a second stream (comparison runs)")
     ap.add_argument("--min-region-s", type=float, default=1.2,
                     help="the K-step solve is repeated until the timed region is at least this long")
     ap.add_argument("--step-kernel", default="auto", choices=["auto", "two_pass", "recompute", "fused"],
@@ -448,6 +450,7 @@ def main():
         from lanczos_b200 import team as lzteam
         solver = lzteam.TeamLanczos(H, rank=rank, world=world)
         M_local = solver.M_local
+        opts["overlap"] = not args.no_overlap
     else:
         solver = lz.Lanczos(H) if "grid" in wl else lz.IrrLanczos(H)
         M_local = M_total
@@ -513,6 +516,7 @@ def main():
     reorths = 0
     solve_ms = []
     alpha_in_update = False
+    overlap_used = False
     for _ in range(R):
         ms = 0.0
         for c in chunks:
@@ -521,6 +525,7 @@ def main():
             reorths += res.reorth_count
             ms += res.gpu_ms
             alpha_in_update = getattr(res, "alpha_in_update", False)
+            overlap_used = getattr(res, "overlap", False)
             del res                       # the result owns the basis (~100 GB at K = 100); the next solve reuses it
         solve_ms.append(ms)
     ev1.record()
@@ -668,7 +673,7 @@ def main():
         step_note = ("bytes per plain step: 32*N with the recompute step (KA2 8N + KB 24N: H v is re-evaluated instead of "
                      "written and re-read), 48*N with the two-pass step (SURVEY 8d), + the operator's own bytes for stored operators")
     moved_gbs = step_bytes / ms_per_step / 1e6
-    fused = {"step_kernel": step_kernel, "alpha_in_update": bool(alpha_in_update),
+    fused = {"step_kernel": step_kernel, "alpha_in_update": bool(alpha_in_update), "overlap": bool(overlap_used),
              "moved_bytes_per_step": step_bytes,                       # what this implementation actually moves
              "achieved_gbs": moved_gbs if plain else None,
              "frac_of_measured_peak": moved_gbs / peak if plain else None,

@@ -151,7 +151,7 @@ def evaluate_potential(potential, x, y, z, ctx: Context = None):
     except Exception:
         vals = np.vectorize(potential, otypes=[np.float64])(X, Y, Z)
         how = "host-scalar"
-    return torch.from_numpy(np.ascontiguousarray(vals).reshape(-1)).to(ctx.torch_device), how
+    return torch.from_numpy(np.array(vals, dtype=np.float64).reshape(-1)).to(ctx.torch_device), how
 
 
 class MatrixFreeMatrix(StencilOperator):
