@@ -212,8 +212,17 @@ int sell_classify_spans(lz_op* op) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(flags);
     if (e != cudaSuccess) { set_error("sell_classify_spans: %s", cudaGetErrorString(e)); return LZ_ERR_CUDA; }
+    // interior: whole spans (a CTA stays inside one sorting window: its gathers are reused out of L1);
+    // boundary: the same spans cut into pieces of kWarps chunks (one chunk per warp), so that the few boundary
+    // windows spread over many CTAs - one CTA per window would take ~90 us at 50 M rows, as long as a tenth
+    // of the whole interior part
     std::vector<int32_t> in, bd;
-    for (int64_t s = 0; s < nspans; ++s) (h[(size_t)s] ? bd : in).push_back((int32_t)s);
+    const int pieces = span / kWarps;
+    for (int64_t s = 0; s < nspans; ++s) {
+        if (!h[(size_t)s]) { in.push_back((int32_t)s); continue; }
+        for (int k = 0; k < pieces; ++k)
+            if ((s * pieces + k) * (int64_t)kWarps < sl.nchunks) bd.push_back((int32_t)(s * pieces + k));
+    }
     sl.split_span = span;
     sl.n_int = (int)in.size();
     sl.n_bnd = (int)bd.size();
@@ -230,6 +239,7 @@ int launch_spmv_part(lz_op* op, int part, const double* x, const double* scale_d
     LZ_REQUIRE(spmv_split_supported(op) && (part == 1 || part == 2), "launch_spmv_part: operator is not split");
     const int32_t* list = part == 1 ? sl.spans_int : sl.spans_bnd;
     const int nlist = part == 1 ? sl.n_int : sl.n_bnd;
+    const int span = part == 1 ? sl.split_span : kWarps;         // boundary entries are pieces of kWarps chunks
     // finer grid than the plain launch: CTAs leave the SMs often, so that the one-CTA exchange kernels of the
     // main stream find a slot while the interior part is running
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nlist, std::min<int64_t>((int64_t)ctx->sms * 16, kMaxPartials / 2)));
@@ -243,7 +253,7 @@ int launch_spmv_part(lz_op* op, int part, const double* x, const double* scale_d
     }
     // an empty list still launches one CTA: its partial is 0 and its tail runs the bookkeeping / the exchange
     LZ_CUDA(launch_k(spmv_sell_dot_kernel, dim3(grid), dim3(kThreads), 0, stream, sl.chunk_off, sl.col, sl.val,
-                     sl.row_of, x, scale_dev, y, sl.nchunks, pout, op->xghost, (int32_t)op->M, sl.split_span, ft,
+                     sl.row_of, x, scale_dev, y, sl.nchunks, pout, op->xghost, (int32_t)op->M, span, ft,
                      list, nlist, flag_dev));
     if (nparts) *nparts = (part == 1) ? grid : sl.np_int + grid;
     return LZ_OK;

@@ -293,8 +293,9 @@ def _rank_dropin(rank, world, port, out):
         L.execute_Lanczos(30, seed=7, devices="auto", verbose=False)
         L.get_H_eigs()
         ip = L.print_good_eigs(print_nr=2)
+        V = L.V                           # assembling the global basis is a collective: every rank asks for it
         if rank == 0:
-            np.savez(out, T=L.H_eff, theta=L.H_eigvals, Y=L.H_eigvecs[:, :3], ip=ip, V=L.V[:, :4])
+            np.savez(out, T=L.H_eff, theta=L.H_eigvals, Y=L.H_eigvecs[:, :3], ip=ip, V=V[:, :4])
         del L
     finally:
         dist.destroy_process_group()
