@@ -31,7 +31,10 @@ struct RunState {          // all device pointers
     double* alpha_pre;     // [1]    alpha of the pre-step (discarded by the reference)
     double* anorm;         // [1]    running estimate of |H|
     int* flags;            // [0] first breakdown step (-1: none), [1] reorth flag of the coming step,
-                           // [2] reorth count, [3] force-next flag, [4] peer timeout
+                           // [2] reorth count, [3] force-next flag, [4] peer timeout,
+                           // [5 + (r & 1)] speculate: the interior part of H row_r may be applied before the monitor
+                           //               has decided about row r (sparse row shards, lanczos.cu),
+                           // [7] the interior part of the coming row must (still / again) be applied after the join
 };
 
 enum { FIN_NONE = -1, FIN_V0NORM = 0, FIN_ALPHA = 1, FIN_BETA = 2, FIN_ALPHA_S2 = 3 };
@@ -145,6 +148,12 @@ __device__ __forceinline__ void omega_body(const RunState& st, int j, double* om
         if (st.flags[3]) { fire = 1; st.flags[3] = 0; }          // second vector of a pair
         else if (m > delta) { fire = 1; st.flags[3] = 1; }
         st.flags[1] = fire;
+        // Overlapped apply of sparse row shards: the interior part of H row_{j+1} was started (or not) on the
+        // strength of the guess made one step ago; it has to run after all if that guess was "do not start" or
+        // if row j+1 is about to be swept.  The guess for row j+2: start early unless a sweep is due or the
+        // estimate is within a factor 64 of the threshold (it grows by a few |H|/beta per step at most).
+        st.flags[7] = (fire || !st.flags[5 + ((j + 1) & 1)]) ? 1 : 0;
+        st.flags[5 + (j & 1)] = (!fire && m * 64.0 < delta) ? 1 : 0;          // (j + 2) & 1 == j & 1
     }
 }
 

@@ -405,7 +405,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         LZ_CUDA(cudaMemsetAsync(st.anorm, 0, 8, q));
         const double one = 1.0;                       // omega_{0,0} = 1
         LZ_CUDA(cudaMemcpyAsync(st.omega_a, &one, 8, cudaMemcpyHostToDevice, q));
-        const int h_flags[8] = {-1, reorth == LZ_REORTH_FULL ? 1 : 0, 0, 0, 0, 0, 0, 0};
+        const int h_flags[8] = {-1, reorth == LZ_REORTH_FULL ? 1 : 0, 0, 0, 0, 0, 0, 1};   // [5],[6]: no speculation yet, [7]: apply late
         LZ_CUDA(cudaMemcpyAsync(st.flags, h_flags, sizeof(h_flags), cudaMemcpyHostToDevice, q));
         r.kt.ctx = r.ctx;
         r.kt.on = (opts->profile != 0);
@@ -765,12 +765,13 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         if (sparse_team) {
             // alpha_j = s_j^2 (r_j . H r_j), H applied to the un-normalised row; partials in the second half of the
             // buffer (the beta exchange of the previous step may still be reading the first half)
-            if (interior_done && maybe_reorth) {
-                // a sweep that fired rewrote row j after its interior spans were applied: apply them again
+            if (interior_done && sel) {
+                // the early interior apply was speculative (flags[5 + (j & 1)]): it runs now if it was not started,
+                // or again if a sweep just rewrote row j (flags[7], set by the monitor of the previous step)
                 LZ_CHECK(each([&](ShardRun& r) {
                     ++launches;
                     return launch_spmv_part(r.op, 1, r.row(j), nullptr, r.w, r.ctx->partials + kMaxPartials, &r.np,
-                                            r.st.flags + 1, nullptr, r.ctx->stream);
+                                            r.st.flags + 7, nullptr, r.ctx->stream);
                 }));
             }
             const bool early = interior_done;
@@ -835,7 +836,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
                     ++launches;
                     r.kt.begin(K_APPLY);
                     const int rc = launch_spmv_part(r.op, 1, r.row(j + 1), nullptr, r.w, r.ctx->partials + kMaxPartials, &r.np,
-                                                    nullptr, nullptr, r.ctx->stream);
+                                                    sel ? r.st.flags + 5 + ((j + 1) & 1) : nullptr, nullptr, r.ctx->stream);
                     r.kt.end();
                     LZ_CHECK(rc);
                     LZ_CUDA(cudaStreamWaitEvent(r.ctx->stream, r.ctx->ev_join, 0));      // join: beta, scale, flags, ghosts

@@ -842,3 +842,28 @@ def test_writes_stay_inside_the_callers_buffers(lz, case):
         t.execute_Lanczos(16, seed=3, reorth="selective", cgs_passes=2, select_tol=1e-14, kb_alpha=True)
         ref = orc.lanczos(orc.laplacian_csr(grid, 6.0, -1.0, periodic=True), 16, seed=3)
         assert rel(np.diag(t.H_eff)[:10], ref["alpha"][:10]) < 1e-10
+
+
+@pytest.mark.parametrize("M,n,k", [(1000, 60, 60), (777, 130, 70), (256 * 3 + 1, 5, 1), (64, 2, 2), (5003, 129, 64), (20001, 33, 17)])
+def test_ritz_lift_gemm_against_numpy(lz, M, n, k):
+    """K5 (lz_ritz_vectors, the lift loop of get_H_eigs, Lanczos.py:154-156) as a tall-skinny GEMM: row blocks
+    of 128 (accumulating passes), column blocks of 64, ragged last tile, odd M - against V.T @ (scale * S)."""
+    import ctypes as C
+    import torch
+    from lanczos_b200 import _capi, engine
+    ctx = engine.Context.default()
+    rs = np.random.RandomState(M + n)
+    ld = engine.padded_ld(M)
+    Vh = rs.uniform(-1, 1, (n, M))
+    S = np.asfortranarray(rs.uniform(-1, 1, (n, k)))
+    scale = rs.uniform(0.5, 2.0, n)
+    V = torch.zeros((n, ld), dtype=torch.float64, device=ctx.torch_device)
+    V[:, :M] = torch.from_numpy(Vh).to(ctx.torch_device)
+    Y = torch.full((k, ld), -3.0, dtype=torch.float64, device=ctx.torch_device)
+    torch.cuda.synchronize()
+    _capi.check(ctx.lib.lz_ritz_vectors(ctx.handle, C.c_void_p(V.data_ptr()), ld, n, M, scale.ctypes.data_as(C.c_void_p),
+                                        S.ctypes.data_as(C.c_void_p), k, C.c_void_p(Y.data_ptr()), ld))
+    want = (S * scale[:, None]).T @ Vh
+    got = Y[:, :M].cpu().numpy()
+    assert np.max(np.abs(got - want)) < 1e-12 * n
+    assert bool((Y[:, M:] == -3.0).all())                     # the pad of every row is left alone
