@@ -206,6 +206,9 @@ typedef struct lz_run_info {
                                  instead of a KA pass over the vector                   */
     int32_t overlap;          /* 1: sparse row shards - the interior rows of the next apply ran while the ghost
                                  entries and the beta sum travelled on a second stream  */
+    int32_t graph;            /* launch-bound solves (<= 4 M unknowns, one GPU): 1 = this call captured the whole
+                                 solve into a CUDA graph and launched it, 2 = it replayed a cached graph, 0 = plain
+                                 launches (first call of a solve, large problems, profile mode, LZ_GRAPH=0) */
 } lz_run_info;
 
 /* Runs n steps from v0_dev (M doubles).  Outputs: alpha_host[n], beta_host[n-1]

@@ -44,7 +44,7 @@ class RunInfo(C.Structure):
                 ("dots_ms", C.c_float), ("gsupd_ms", C.c_float), ("fused_ms", C.c_float),
                 ("step_kernel", C.c_int32), ("gsfused_launches", C.c_int32), ("gsfused_ms", C.c_float),
                 ("border_launches", C.c_int32), ("border_ms", C.c_float), ("alpha_in_update", C.c_int32),
-                ("overlap", C.c_int32)]
+                ("overlap", C.c_int32), ("graph", C.c_int32)]
 
 
 _vp, _i32, _i64, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double

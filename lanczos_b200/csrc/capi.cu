@@ -25,6 +25,9 @@ const char* get_error() { return g_err; }
 // separates two kernels - may start while the primary is still writing, and data the primary produced is then
 // read through the non-coherent path (ld.global.nc / __ldg), which griddepcontrol.wait does not cover.  Seen as
 // wrong alpha from step 2-3 on in row-sharded two-pass runs (tools/dbg1.py), never with the attribute off.
+}  // namespace lz
+void lz_ctx_drop_graphs(lz_ctx* c);     // lanczos.cu
+namespace lz {
 bool pdl_enabled() {
     static const bool on = []() {
         const char* e = getenv("LZ_PDL");
@@ -153,6 +156,8 @@ int lz_ctx_create(int device, void* cuda_stream, lz_ctx** out) {
 int lz_ctx_destroy(lz_ctx* c) {
     if (!c) return LZ_OK;
     cudaSetDevice(c->device);
+    lz_ctx_drop_graphs(c);
+    if (c->gstream) cudaStreamDestroy(c->gstream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);

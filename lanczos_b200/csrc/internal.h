@@ -16,6 +16,8 @@ struct lz_ctx {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // second stream: the interior part of a row shard's SpMV runs here while the ghost entries and the beta
     // sum travel over NVLink on `stream` (created on first use; lower priority than nothing - see lanczos.cu)
+    cudaStream_t gstream = nullptr;            // capture stream of the CUDA-graph path (lanczos.cu)
+    std::vector<struct lz_graph_slot*> graphs; // captured solves, keyed on every pointer / scalar they bake in
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void* arena = nullptr;         // grow-only device workspace of lz_lanczos_run
@@ -74,6 +76,7 @@ struct lz_op {
     lz_stencil st;
     lz_csr csr;
     lz_sell sell;
+    unsigned long long serial = 0; // unique per operator ever created (keys the captured-solve cache)
     int fused_per_sm = 0;          // cached occupancy of the fused step kernel
     int kb_zc = 0;                 // z-chunk length of the last KB launch that accumulated alpha (border kernel)
     int64_t ncols = 0;             // sparse: number of columns (> M for a row shard: M owned + ghosts)

@@ -21,6 +21,7 @@
 // to every peer and add the P contributions in rank order (peer.cuh) - that flag also
 // publishes the halo.  No NCCL call, no extra pass over HBM, no extra launch per step.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "internal.h"
@@ -310,6 +311,52 @@ int push_ghosts(const lz_team* team, ShardRun& r, const double* x, int parity, c
     return launch_ghost_push(r.ctx, x, r.sh->send_idx, r.sh->nsend, team->world, r.sh->seg_start, dst, flag, stream);
 }
 
+// ---- cache of captured solves (see run_loop) -----------------------------------------------------------
+struct GraphKey {
+    unsigned long long op_serial;
+    const void* op; const void* v0; const void* V; const void* arena; const void* diag;
+    int64_t ldv, M;
+    int32_t n;
+    lz_run_opts opts;
+};
+}  // namespace
+struct lz_graph_slot {
+    GraphKey key;
+    cudaGraphExec_t exec = nullptr;
+    int seen = 0;
+    int launches = 0;
+    unsigned long long stamp = 0;
+};
+namespace {
+using GraphSlot = lz_graph_slot;
+
+bool same_key(const GraphKey& a, const GraphKey& b) {
+    return a.op_serial == b.op_serial && a.op == b.op && a.v0 == b.v0 && a.V == b.V && a.arena == b.arena && a.diag == b.diag && a.ldv == b.ldv &&
+           a.M == b.M && a.n == b.n && memcmp(&a.opts, &b.opts, sizeof(lz_run_opts)) == 0;
+}
+
+// the slot for `key` in the context's small cache (least recently used slot recycled)
+GraphSlot* graph_lookup(lz_ctx* ctx, const GraphKey& key) {
+    static unsigned long long clock = 0;
+    constexpr size_t kSlots = 4;
+    auto& slots = ctx->graphs;
+    for (GraphSlot* s : slots)
+        if (same_key(s->key, key)) { s->stamp = ++clock; return s; }
+    GraphSlot* s = nullptr;
+    if (slots.size() < kSlots) {
+        s = new GraphSlot();
+        slots.push_back(s);
+    } else {
+        s = slots[0];
+        for (GraphSlot* t : slots) if (t->stamp < s->stamp) s = t;
+        if (s->exec) cudaGraphExecDestroy(s->exec);
+        *s = GraphSlot();
+    }
+    s->key = key;
+    s->stamp = ++clock;
+    return s;
+}
+
 // The loop over `nl` local shards (nl == 1 and team == nullptr: the plain single-GPU solve).
 int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s, int32_t n,
              const lz_run_opts* opts, double* alpha_host, double* beta_host, double* const* Vs,
@@ -564,8 +611,44 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
                            }, false);
     };
 
-    LZ_CHECK(each([&](ShardRun& r) { LZ_CUDA(cudaEventRecord(r.ctx->ev_begin, r.ctx->stream)); return LZ_OK; }));
+    // ---- CUDA graph for launch-bound solves ---------------------------------------------------------
+    // Up to a few million unknowns a step is 4-6 kernels of a few microseconds each and the loop is bound by
+    // launch latency (config 1, 200 x 200: 28 us/step of which ~5 us is arithmetic).  The whole enqueue below
+    // - start vector, pre-step, n steps - is then captured once into a CUDA graph and replayed: inside a graph
+    // the kernels follow each other without a trip through the launch queue.  The graph bakes in every
+    // pointer and scalar, so it is keyed on all of them; it is captured the second time the same solve is
+    // asked for (a one-off solve would pay more for capture + instantiation than it saves) and replayed from
+    // then on.  Single shard only, not in profile mode; LZ_GRAPH=0 turns it off, LZ_GRAPH=1 forces it for
+    // any size and captures on the first call.
+    GraphKey gkey{};
+    GraphSlot* gslot = nullptr;
+    bool capturing = false;
+    cudaStream_t user_stream = nullptr;
+    {
+        static const int gmode = []() { const char* e = getenv("LZ_GRAPH"); return e ? atoi(e) : -1; }();
+        const bool small = M_local <= ((int64_t)1 << 22);
+        if (!team && nl == 1 && !opts->profile && gmode != 0 && (small || gmode == 1)) {
+            ShardRun& r = R[0];
+            if (r.op->serial == 0) { static unsigned long long next_serial = 0; r.op->serial = ++next_serial; }
+            gkey.op_serial = r.op->serial;
+            gkey.op = r.op; gkey.v0 = r.v0; gkey.V = r.V; gkey.arena = r.ctx->arena; gkey.ldv = r.ldv; gkey.M = r.M;
+            gkey.n = n; gkey.opts = *opts; gkey.diag = r.op->st.diag;
+            gslot = graph_lookup(r.ctx, gkey);
+            if (gslot->exec == nullptr && (gslot->seen >= 1 || gmode == 1)) {
+                if (!r.ctx->gstream) LZ_CUDA(cudaStreamCreateWithFlags(&r.ctx->gstream, cudaStreamNonBlocking));
+                LZ_CUDA(cudaStreamBeginCapture(r.ctx->gstream, cudaStreamCaptureModeRelaxed));
+                user_stream = r.ctx->stream;
+                r.ctx->stream = r.ctx->gstream;              // every launch below goes into the capture
+                capturing = true;
+            }
+            gslot->seen += 1;
+        }
+    }
+    const bool replay = gslot && gslot->exec && !capturing;
 
+    if (!capturing) LZ_CHECK(each([&](ShardRun& r) { LZ_CUDA(cudaEventRecord(r.ctx->ev_begin, r.ctx->stream)); return LZ_OK; }));
+
+    auto enqueue_all = [&]() -> int {
     // ---- start: |v0| ---------------------------------------------------------------------
     LZ_CHECK(produce_fin([](ShardRun&) { FinOp f; f.kind = FIN_V0NORM; return f; },
                          [&](ShardRun& r, const FinTail* t) {
@@ -886,6 +969,37 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
             alpha_known = true;
         }
     }
+    return LZ_OK;
+    };   // enqueue_all
+
+    if (replay) {
+        launches = gslot->launches;
+        LZ_CUDA(cudaGraphLaunch(gslot->exec, R[0].ctx->stream));
+    } else {
+        const int rc_enq = enqueue_all();
+        if (capturing) {
+            ShardRun& r = R[0];
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(r.ctx->gstream, &graph);
+            r.ctx->stream = user_stream;
+            if (rc_enq != LZ_OK) { if (graph) cudaGraphDestroy(graph); return rc_enq; }
+            if (ce != cudaSuccess || !graph) {
+                set_error("lz_lanczos_run: graph capture failed: %s", cudaGetErrorString(ce));
+                (void)cudaGetLastError();
+                return LZ_ERR_CUDA;
+            }
+            cudaGraphExec_t exec = nullptr;
+            const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) { set_error("lz_lanczos_run: cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return LZ_ERR_CUDA; }
+            gslot->exec = exec;
+            gslot->launches = launches;
+            LZ_CUDA(cudaEventRecord(r.ctx->ev_begin, r.ctx->stream));
+            LZ_CUDA(cudaGraphLaunch(exec, r.ctx->stream));
+        } else {
+            LZ_CHECK(rc_enq);
+        }
+    }
     LZ_CHECK(each([&](ShardRun& r) {
         LZ_CUDA(cudaGetLastError());
         LZ_CUDA(cudaEventRecord(r.ctx->ev_end, r.ctx->stream));
@@ -959,11 +1073,20 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         info->border_ms = kms[K_BORDER]; info->border_launches = kcnt[K_BORDER];
         info->alpha_in_update = kb_alpha ? 1 : 0;
         info->overlap = overlap ? 1 : 0;
+        info->graph = replay ? 2 : (capturing ? 1 : 0);
     }
     return status;
 }
 
 }  // namespace
+
+void lz_ctx_drop_graphs(lz_ctx* c) {
+    for (lz_graph_slot* s : c->graphs) {
+        if (s->exec) cudaGraphExecDestroy(s->exec);
+        delete s;
+    }
+    c->graphs.clear();
+}
 
 extern "C" int lz_lanczos_run(lz_ctx* ctx, lz_op* op, const double* v0_dev, int32_t n,
                               const lz_run_opts* opts, double* alpha_host, double* beta_host,

@@ -556,20 +556,24 @@ ritz_lift_gemm_kernel(const double* __restrict__ V, int64_t ldv, int n, int64_t 
     const int my_tiles = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const int64_t total = (int64_t)my_tiles * n;         // (tile, row) slots of this CTA, in order
     // producer side: thread t copies chunk (t & 127) of rows 2*u + (t >> 7), u = 0, 1, of a step
+    // (no division in the loops: the producer and the consumer each carry their own (tile, row) cursor)
     const int chunk = threadIdx.x & 127, rsub = threadIdx.x >> 7;
-    auto issue_step = [&](int64_t step) {
+    int64_t pq = rsub;                                   // producer: next slot of this thread (slots rsub, rsub + 2, ...)
+    int pr = rsub % n;
+    int64_t ptile = blockIdx.x + (int64_t)(rsub / n) * gridDim.x;
+    auto issue_step = [&](int64_t) {
 #pragma unroll
         for (int u = 0; u < kGemmRowsPerStep / 2; ++u) {
-            const int64_t q = step * kGemmRowsPerStep + 2 * u + rsub;
-            if (q < total) {
-                const int64_t tile = blockIdx.x + (q / n) * (int64_t)gridDim.x;
-                const int r = (int)(q % n);
-                const int64_t col = tile * kGemmTile + 2 * chunk;
+            if (pq < total) {
+                const int64_t col = ptile * kGemmTile + 2 * chunk;
                 const int64_t left = M - col;
                 const int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
-                const double* src = V + (int64_t)r * ldv + (bytes ? col : 0);
-                cp_async16_zfill(ring + (size_t)(q % kGemmRing) * kGemmTile + 2 * chunk, src, bytes);
+                const double* src = V + (int64_t)pr * ldv + (bytes ? col : 0);
+                cp_async16_zfill(ring + (size_t)(pq & (kGemmRing - 1)) * kGemmTile + 2 * chunk, src, bytes);
             }
+            pq += 2;
+            pr += 2;
+            while (pr >= n) { pr -= n; ptile += gridDim.x; }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -578,6 +582,9 @@ ritz_lift_gemm_kernel(const double* __restrict__ V, int64_t ldv, int n, int64_t 
     for (int s = 0; s < kGemmDepth - 1; ++s) issue_step(s);
     double acc[16][4];
     const int cbase = half * 128 + 2 * lane;             // this thread's columns: cbase, +1, cbase + 64, +65
+    int r = 0;                                           // consumer cursor
+    int64_t tile = blockIdx.x;
+    static_assert((kGemmRing & (kGemmRing - 1)) == 0, "ring size must be a power of two");
 #pragma unroll 1
     for (int64_t step = 0; step < nsteps; ++step) {
         issue_step(step + kGemmDepth - 1);
@@ -587,8 +594,6 @@ ritz_lift_gemm_kernel(const double* __restrict__ V, int64_t ldv, int n, int64_t 
         for (int u = 0; u < kGemmRowsPerStep; ++u) {
             const int64_t q = step * kGemmRowsPerStep + u;
             if (q >= total) break;
-            const int r = (int)(q % n);
-            const int64_t tile = blockIdx.x + (q / n) * (int64_t)gridDim.x;
             const int64_t col = tile * kGemmTile + cbase;
             if (r == 0) {
 #pragma unroll
@@ -603,7 +608,7 @@ ritz_lift_gemm_kernel(const double* __restrict__ V, int64_t ldv, int n, int64_t 
                     }
                 }
             }
-            const double* row = ring + (size_t)(q % kGemmRing) * kGemmTile + cbase;
+            const double* row = ring + (size_t)(q & (kGemmRing - 1)) * kGemmTile + cbase;
             const double2 va = *reinterpret_cast<const double2*>(row);
             const double2 vb = *reinterpret_cast<const double2*>(row + 64);
             const double* sr = ss + (size_t)r * kGemmOut + grp * 16;
@@ -631,6 +636,7 @@ ritz_lift_gemm_kernel(const double* __restrict__ V, int64_t ldv, int n, int64_t 
                     }
                 }
             }
+            if (++r == n) { r = 0; tile += gridDim.x; }
         }
         __syncthreads();                                 // everybody is done with the slots the next step refills
     }

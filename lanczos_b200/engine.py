@@ -353,6 +353,7 @@ class LanczosResult:
                           "border": (float(info.border_ms), info.border_launches)}
         self.alpha_in_update = bool(info.alpha_in_update)
         self.overlap = bool(info.overlap)
+        self.graph = {0: "none", 1: "captured", 2: "replayed"}.get(int(info.graph), "none")
 
     def tridiagonal(self) -> np.ndarray:
         """Dense H_eff like Lanczos.py:121-130."""

@@ -867,3 +867,41 @@ def test_ritz_lift_gemm_against_numpy(lz, M, n, k):
     got = Y[:, :M].cpu().numpy()
     assert np.max(np.abs(got - want)) < 1e-12 * n
     assert bool((Y[:, M:] == -3.0).all())                     # the pad of every row is left alone
+
+
+@pytest.mark.parametrize("kind", ["stencil_full", "stencil_selective", "sparse_full"])
+def test_graph_replay_is_bit_identical(lz, kind):
+    """Launch-bound solves are captured into a CUDA graph the second time the same solve is asked for and
+    replayed afterwards (lz_run_info.graph): same bits as the plain launches, and a change of any baked-in
+    argument (start vector buffer, step count) falls back to plain launches."""
+    import torch
+    from lanczos_b200 import engine
+    ctx = engine.Context.default()
+    if kind.startswith("stencil"):
+        grid = (200, 200)
+        H = orc.laplacian_csr(grid, 4.0, -1.0, periodic=False)
+        dop = lz.StencilOperator(grid, 4.0, -1.0, bc="dirichlet").device_handle(ctx)
+    else:
+        H = orc.delaunay_graph_laplacian(20000, seed=4)
+        dop = engine.as_device_operator(H, ctx)
+    M, n = H.shape[0], 40
+    kw = dict(reorth="selective", cgs_passes=2, select_tol=1e-12) if kind == "stencil_selective" else dict(reorth="full")
+    v0 = torch.from_numpy(orc.start_vector(M, seed=9)).to(ctx.torch_device)
+    V = torch.empty((n, engine.padded_ld(M)), dtype=torch.float64, device=ctx.torch_device)
+    runs = []
+    for _ in range(4):
+        V.fill_(float("nan"))
+        res = engine.run_lanczos(dop, v0, n, V_dev=V, **kw)
+        runs.append((res.graph, res.alpha.copy(), res.beta.copy(), V[:, :M].clone(), res.launches))
+    assert [r[0] for r in runs] == ["none", "captured", "replayed", "replayed"]
+    for g, a, b, Vc, nl in runs[1:]:
+        assert np.array_equal(a, runs[0][1]) and np.array_equal(b, runs[0][2]) and nl == runs[0][4]
+        assert torch.equal(Vc, runs[0][3])
+    ref = orc.lanczos(H, n, seed=9)
+    if kind != "stencil_selective":
+        assert rel(runs[2][1], ref["alpha"]) < TOL_AB and rel(runs[2][2], ref["beta"]) < TOL_AB
+    # another start-vector buffer: not the captured solve
+    res = engine.run_lanczos(dop, v0.clone(), n, V_dev=V, **kw)
+    assert res.graph == "none" and np.array_equal(res.alpha, runs[0][1])
+    res = engine.run_lanczos(dop, v0, n - 1, V_dev=V, **kw)
+    assert res.graph == "none" and np.array_equal(res.alpha, runs[0][1][:n - 1])
