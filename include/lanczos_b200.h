@@ -177,7 +177,8 @@ typedef struct lz_run_opts {
                               takes the LZ_SWEEP_GPU form of Regular/Lanczos.py:236-238 instead of
                               the (2 - |v|^2) form; bit 2: do not accumulate alpha inside KB (recompute
                               step: a KA pass per step instead of the border kernel); bit 3: sparse row shards without
-                              the interior/boundary overlap on a second stream; 0 = defaults */
+                              the interior/boundary overlap on a second stream; bit 4: recompute step as KA + KB
+                              instead of the single KBA kernel; 0 = defaults */
     double  breakdown_tol; /* stop when beta <= breakdown_tol * |alpha_0| (0: only 0/NaN) */
     double  select_tol;    /* selective: orthogonality level that triggers (0 -> sqrt(eps)) */
 } lz_run_opts;
@@ -203,7 +204,8 @@ typedef struct lz_run_info {
     int32_t border_launches;  /* ... the border kernel that completes alpha when KB accumulates it */
     float   border_ms;
     int32_t alpha_in_update;  /* 1: alpha of the next vector was accumulated inside KB (+ border kernel)
-                                 instead of a KA pass over the vector                   */
+                                 instead of a KA pass over the vector; 2: one kernel per step (KBA) - the
+                                 alpha reduction chases KB's output through L2 (24*M B of HBM per step) */
     int32_t overlap;          /* 1: sparse row shards - the interior rows of the next apply ran while the ghost
                                  entries and the beta sum travelled on a second stream  */
     int32_t graph;            /* launch-bound solves (<= 4 M unknowns, one GPU): 1 = this call captured the whole

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblanczos_b200.so")
 SYNTH_LIB = os.path.join(HERE, "liblz_synth.so")          # synthetic benchmark inputs (include/lz_synth.h)
 SYNTH_SOURCES = ["synth_rgg.cu"]
-SOURCES = ["capi.cu", "stencil.cu", "stencil27.cu", "vecops.cu", "reorth.cu", "spmv.cu", "fused.cu", "lanczos.cu", "potential.cu"]
+SOURCES = ["capi.cu", "stencil.cu", "stencil27.cu", "vecops.cu", "reorth.cu", "spmv.cu", "fused.cu", "lanczos.cu", "potential.cu", "kba.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
@@ -69,5 +69,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(out: str, defines: list[str]) -> str:
+    """Kernel-tuning aid: another build of the same library with extra -D macros, loaded through
+    LANCZOS_B200_LIB (see _capi.py).  python -m lanczos_b200.build --variant out.so -DLZ_KBA_MINBLOCKS=3"""
+    cmd = [_nvcc()] + NVCC_FLAGS + list(defines) + ["-o", out] + sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

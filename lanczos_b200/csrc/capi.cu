@@ -140,6 +140,8 @@ int lz_ctx_create(int device, void* cuda_stream, lz_ctx** out) {
     c->sms = prop.multiProcessorCount;
     cudaError_t e = cudaMalloc((void**)&c->partials, (size_t)2 * kMaxPartials * 8);
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->scratch, 64 * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->kba_done, 4096 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(c->kba_done, 0, 4096 * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->tickets, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(c->tickets, 0, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_begin);
@@ -164,6 +166,7 @@ int lz_ctx_destroy(lz_ctx* c) {
     if (c->partials) cudaFree(c->partials);
     if (c->scratch) cudaFree(c->scratch);
     if (c->tickets) cudaFree(c->tickets);
+    if (c->kba_done) cudaFree(c->kba_done);
     if (c->arena) cudaFree(c->arena);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);

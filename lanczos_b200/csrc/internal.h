@@ -12,6 +12,7 @@ struct lz_ctx {
     int sms = 148;
     double* partials = nullptr;    // 2 * kMaxPartials doubles: CTA partial sums of streaming kernels
     double* scratch = nullptr;     // 64 doubles of device scratch (lz_dot, lz_reorthogonalize, ...)
+    int* kba_done = nullptr;           // per-z-chunk completion counters of the KBA kernel (kba.cu); zero between launches
     unsigned int* tickets = nullptr;   // last-CTA tickets of the fin tails (fin.cuh); zero between launches
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // second stream: the interior part of a row shard's SpMV runs here while the ghost entries and the beta
@@ -132,6 +133,11 @@ int launch_apply_update_norm(lz_op* op, const double* x, const double* scale_dev
 bool update_alpha_supported(const lz_op* op, const double* x, const double* out);
 // the edges KB could not reach (across tile borders and z-chunks, slab top): partials[cta] of out . H out over them
 int launch_alpha_border(lz_op* op, const double* v, double* partials, int* nparts, const FinTail* fin);
+
+// ---- KB with the alpha reduction of its output chasing it through L2 (kba.cu) ------------------------
+bool kba_step_supported(const lz_op* op, const double* x, const double* b, const double* out);
+int launch_kba_step(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd, double* out,
+                    const FinTail* fin_beta, const FinOp* fin_alpha, int* nparts);
 
 // ---- single-pass fused step (fused.cu) ---------------------------------------------------
 bool fused_step_supported(const lz_op* op);

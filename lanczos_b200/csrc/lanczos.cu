@@ -478,7 +478,15 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     // alpha of the NEXT vector accumulated inside KB while that vector is in registers, plus a small border
     // kernel for the edges that cross CTA tiles (stencil.cu): replaces KA2's full pass over the vector.  Not
     // with full re-orthogonalisation (the sweep rewrites the vector, alpha must be taken afterwards anyway).
-    bool kb_alpha = recompute && reorth != LZ_REORTH_FULL && !(opts->flags & 4);
+    // KBA (kba.cu): one kernel per step - KB plus the alpha reduction of the vector it writes, read back through
+    // L2 a few z-planes behind: 24*M bytes of HBM per step instead of 32*M.  One GPU, whole tiles.
+    bool kba = recompute && !team && nl == 1 && reorth != LZ_REORTH_FULL && !(opts->flags & 16);
+    if (kba) {
+        const double* any_row = R[0].V ? R[0].V : R[0].ring;
+        kba = kba_step_supported(R[0].op, any_row, any_row, any_row) && ((reinterpret_cast<uintptr_t>(R[0].v0) & 15) == 0) &&
+              (((R[0].V ? R[0].ldv : R[0].ld_int) & 1) == 0);
+    }
+    bool kb_alpha = !kba && recompute && reorth != LZ_REORTH_FULL && !(opts->flags & 4);
     for (int s = 0; s < nl && kb_alpha; ++s)
         kb_alpha = update_alpha_supported(R[s].op, R[s].V ? R[s].V : R[s].ring, R[s].V ? R[s].V : R[s].ring);
 
@@ -690,6 +698,15 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         LZ_CHECK(produce_fin([&](ShardRun& r) { return op_beta(r, 0, r.st.alpha_pre, -1); },
                              [&](ShardRun& r, const FinTail* t) {
                                  HaloPush h = halo_for(team, r, 0);
+                                 if (kba) {
+                                     StencilUpdate u;
+                                     u.ca = r.st.alpha_pre;
+                                     u.sa = r.st.v0scale;
+                                     FinOp fa;
+                                     fa.kind = FIN_ALPHA_S2; fa.jn = 0; fa.out = r.st.alpha;
+                                     ++launches;
+                                     return launch_kba_step(r.op, r.v0, r.st.v0scale, &u, r.row(0), t, &fa, &r.np);
+                                 }
                                  if (recompute) {
                                      StencilUpdate u;
                                      u.ca = r.st.alpha_pre;
@@ -712,6 +729,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
             LZ_CHECK(alpha_border(0));
             alpha_known = true;
         }
+        if (kba) alpha_known = true;
     } else {
         LZ_CHECK(each([&](ShardRun& r) {
             LZ_CUDA(cudaMemcpyAsync(r.row(0), r.v0, (size_t)r.M * 8, cudaMemcpyDeviceToDevice, r.ctx->stream));
@@ -932,6 +950,22 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
                              [&](ShardRun& r, const FinTail* t) {
                                  double* out = (j + 1 < n) ? r.row(j + 1) : r.w;
                                  HaloPush h = (j + 1 < n) ? halo_for(team, r, (j + 1) & 1) : HaloPush{};
+                                 if (kba) {
+                                     StencilUpdate u;
+                                     u.b = j > 0 ? r.row(j - 1) : nullptr;
+                                     u.ca = r.st.alpha + j;
+                                     u.sa = r.st.scale + j;
+                                     u.cb = r.st.beta + j;
+                                     u.sb = j > 0 ? r.st.scale + j - 1 : nullptr;
+                                     FinOp fa;
+                                     fa.kind = FIN_ALPHA_S2; fa.jn = j + 1; fa.out = r.st.alpha + j + 1;
+                                     r.kt.begin(K_UPDATE);
+                                     const int rc3 = launch_kba_step(r.op, r.row(j), r.st.scale + j, &u, out, t,
+                                                                     (j + 1 < n) ? &fa : nullptr, &r.np);
+                                     r.kt.end();
+                                     ++launches;
+                                     return rc3;
+                                 }
                                  if (recompute) {
                                      StencilUpdate u;
                                      u.b = j > 0 ? r.row(j - 1) : nullptr;
@@ -968,6 +1002,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
             LZ_CHECK(alpha_border(j + 1));
             alpha_known = true;
         }
+        if (kba && j + 1 < n) alpha_known = true;
     }
     return LZ_OK;
     };   // enqueue_all
@@ -1071,7 +1106,7 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
         info->step_kernel = fused ? 2 : (recompute ? 3 : 1);
         info->gsfused_ms = kms[K_GSFUSED]; info->gsfused_launches = kcnt[K_GSFUSED];
         info->border_ms = kms[K_BORDER]; info->border_launches = kcnt[K_BORDER];
-        info->alpha_in_update = kb_alpha ? 1 : 0;
+        info->alpha_in_update = kb_alpha ? 1 : (kba ? 2 : 0);
         info->overlap = overlap ? 1 : 0;
         info->graph = replay ? 2 : (capturing ? 1 : 0);
     }

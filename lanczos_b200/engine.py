@@ -30,12 +30,14 @@ def _torch():
     return torch
 
 
-def run_flags(cgs_fused: bool = True, sweep_form: int = 0, kb_alpha: bool = False, overlap: bool = True) -> int:
+def run_flags(cgs_fused: bool = True, sweep_form: int = 0, kb_alpha: bool = False, overlap: bool = True,
+              kba: bool = True) -> int:
     """lz_run_opts.flags: bit 0 = CGS2 without K4c, bit 1 = the Regular GPU sweep form (LZ_SWEEP_GPU),
     bit 2 = recompute step with a KA pass per step instead of alpha accumulated inside KB,
-    bit 3 = sparse row shards without the interior/boundary overlap."""
+    bit 3 = sparse row shards without the interior/boundary overlap, bit 4 = recompute step as KA + KB
+    instead of the single KBA kernel."""
     return ((0 if cgs_fused else 1) | (2 if sweep_form == _capi.LZ_SWEEP_GPU else 0) | (0 if kb_alpha else 4) |
-            (0 if overlap else 8))
+            (0 if overlap else 8) | (0 if kba else 16))
 
 
 def padded_ld(M: int) -> int:
@@ -351,7 +353,8 @@ class LanczosResult:
                           "fused": (float(info.fused_ms), info.fused_launches),
                           "gs_fused": (float(info.gsfused_ms), info.gsfused_launches),
                           "border": (float(info.border_ms), info.border_launches)}
-        self.alpha_in_update = bool(info.alpha_in_update)
+        self.alpha_in_update = int(info.alpha_in_update) == 1
+        self.kba = int(info.alpha_in_update) == 2
         self.overlap = bool(info.overlap)
         self.graph = {0: "none", 1: "captured", 2: "replayed"}.get(int(info.graph), "none")
 
@@ -399,7 +402,7 @@ class LanczosResult:
 
 def run_lanczos(op: DeviceOperator, v0, n: int, *, reorth="full", cgs_passes=1, ref_compat=True,
                 keep_basis=True, breakdown_tol=0.0, select_tol=0.0, V_dev=None,
-                profile=False, step_kernel="auto", cgs_fused=True, sweep_form=0, kb_alpha=False) -> LanczosResult:
+                profile=False, step_kernel="auto", cgs_fused=True, sweep_form=0, kb_alpha=False, kba=True) -> LanczosResult:
     """Enqueue and run the n-step loop (lz_lanczos_run).  `v0` is a host array (copied through
     pinned memory) or a CUDA tensor of M doubles."""
     torch = _torch()
@@ -429,7 +432,7 @@ def run_lanczos(op: DeviceOperator, v0, n: int, *, reorth="full", cgs_passes=1, 
         beta = np.zeros(max(n - 1, 0))
         scale = np.ones(n)
         opts = RunOpts(mode, int(cgs_passes), 1 if ref_compat else 0, 1 if profile else 0,
-                       STEP_KERNEL[step_kernel], run_flags(cgs_fused, sweep_form, kb_alpha), float(breakdown_tol), float(select_tol))
+                       STEP_KERNEL[step_kernel], run_flags(cgs_fused, sweep_form, kb_alpha, True, kba), float(breakdown_tol), float(select_tol))
         info = RunInfo()
         status = ctx.lib.lz_lanczos_run(
             ctx.handle, op.handle, C.c_void_p(v0_dev.data_ptr()), n, C.byref(opts),

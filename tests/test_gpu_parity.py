@@ -905,3 +905,42 @@ def test_graph_replay_is_bit_identical(lz, kind):
     assert res.graph == "none" and np.array_equal(res.alpha, runs[0][1])
     res = engine.run_lanczos(dop, v0, n - 1, V_dev=V, **kw)
     assert res.graph == "none" and np.array_equal(res.alpha, runs[0][1][:n - 1])
+
+
+KBA_CASES = [((64, 16, 12), "periodic", False), ((128, 32, 5), "dirichlet", False), ((64, 16, 2), "periodic", True),
+             ((192, 48, 40), "periodic", True), ((64, 64, 33), "dirichlet", True), ((256, 64, 70), "periodic", False)]
+
+
+@pytest.mark.parametrize("grid,bc,pot", KBA_CASES)
+def test_kba_step_matches_ka_kb(lz, grid, bc, pot):
+    """One kernel per step (KBA: KB plus the alpha reduction of its output, read back through L2 behind
+    per-chunk completion counters) against KA2 + KB: same arithmetic per point, so alpha/beta agree to
+    the order of the partial sums; and against the oracle."""
+    M = int(np.prod(grid))
+    diag = np.cos(np.arange(M) * 0.37) * 0.3 if pot else None
+    off = [-1.0, -0.7, -1.2]
+    op = lz.StencilOperator(grid, 6.5, off, bc=bc, diag=diag)
+    H = orc.laplacian_csr(grid, 6.5, off, periodic=(bc == "periodic"), diag=diag)
+    n = 14
+    ref = orc.lanczos(H, n, seed=5, reorth=False)
+    res = {}
+    for flag in (True, False):
+        L = lz.Lanczos(op)
+        L.execute_Lanczos(n, seed=5, reorth="none", kba=flag)
+        assert L.result.step_kernel == "recompute" and L.result.kba == flag
+        res[flag] = (np.diag(L.H_eff).copy(), np.diag(L.H_eff, 1).copy(), L.V.copy(), L.result.launches)
+        L.execute_Lanczos(n, seed=5, reorth="none", kba=flag)
+        assert np.array_equal(np.diag(L.H_eff), res[flag][0])           # static item -> CTA deal: bit-reproducible
+    assert res[True][3] < res[False][3]                                  # one launch per step instead of two
+    k = 8
+    assert rel(res[True][0][:k], res[False][0][:k]) < 1e-12 and rel(res[True][1][:k], res[False][1][:k]) < 1e-12
+    assert rel(res[True][0][:k], ref["alpha"][:k]) < 1e-12 and rel(res[True][1][:k], ref["beta"][:k]) < 1e-12
+    assert np.max(np.abs(res[True][2][:, :3] - res[False][2][:, :3])) < 1e-13
+    R = lz.Lanczos(op)
+    R.execute_Lanczos(n, seed=5, reorth="none", keep_basis=False)       # three-row ring
+    assert R.result.kba and rel(np.diag(R.H_eff)[:k], res[True][0][:k]) < 1e-12
+    full = orc.lanczos(H, 30, seed=5)
+    S = lz.Lanczos(op)
+    S.execute_Lanczos(30, seed=5, reorth="selective", cgs_passes=2, select_tol=1e-15)      # sweeps fire: alpha re-taken by KA2
+    assert S.result.kba and S.result.reorth_count >= 25
+    assert rel(np.diag(S.H_eff), full["alpha"]) < 1e-11 and rel(np.diag(S.H_eff, 1), full["beta"]) < 1e-11

@@ -1,0 +1,21 @@
+#!/bin/bash
+# 8 GPUs: real multi-process tests, c4 strong scaling (overlap A/B), c3 weak scaling point
+mkdir -p gpurun_out
+nvidia-smi -L | wc -l > gpurun_out/r2_ngpu.txt
+timeout 240 python -m pytest tests/test_gpu_team.py -m gpu -x -q -k "one_process_per_gpu or multi_device" > gpurun_out/r2_pytest_team8.log 2>&1; echo "team pytest rc=$?" | tee -a gpurun_out/r2_pytest_team8.log
+tail -3 gpurun_out/r2_pytest_team8.log
+tr() { name=$1; shift; timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err; echo "$name rc=$?"; }
+tr r2e_c4_n8 --workload c4 --steps 100
+tr r2e_c4_n8_nooverlap --workload c4 --steps 100 --no-overlap --no-parity-check
+tr r2e_c3_n8 --steps 20 --no-parity-check
+for f in gpurun_out/r2e_*.json; do python - "$f" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    k=d.get("kernels",{})
+    print(sys.argv[1].split('/')[-1], "ms/step %.4f burst %.4f value %.1f e2e %.1f R=%s" % (d["ms_per_step"], d["burst"]["ms_per_step"], d["value"], d["e2e"]["value"], d["config"]["repeats"]),
+          {n:(round(v["avg_ms"],4), round(v["achieved_gbs"])) for n,v in k.items()}, "overlap", d["fused_step"].get("overlap"), "parity", (d.get("parity_check") or {}).get("ok"), d["config"].get("host"), "reorth", d["reorth_steps"])
+except Exception as e:
+    print(sys.argv[1], "unreadable", e); print(open(sys.argv[1].replace('.json','.err')).read()[-1500:])
+PY
+done
