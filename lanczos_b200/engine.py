@@ -31,7 +31,7 @@ def _torch():
 
 
 def run_flags(cgs_fused: bool = True, sweep_form: int = 0, kb_alpha: bool = False, overlap: bool = True,
-              kba: bool = True) -> int:
+              kba: bool = False) -> int:
     """lz_run_opts.flags: bit 0 = CGS2 without K4c, bit 1 = the Regular GPU sweep form (LZ_SWEEP_GPU),
     bit 2 = recompute step with a KA pass per step instead of alpha accumulated inside KB,
     bit 3 = sparse row shards without the interior/boundary overlap, bit 4 = recompute step as KA + KB
@@ -402,7 +402,7 @@ class LanczosResult:
 
 def run_lanczos(op: DeviceOperator, v0, n: int, *, reorth="full", cgs_passes=1, ref_compat=True,
                 keep_basis=True, breakdown_tol=0.0, select_tol=0.0, V_dev=None,
-                profile=False, step_kernel="auto", cgs_fused=True, sweep_form=0, kb_alpha=False, kba=True) -> LanczosResult:
+                profile=False, step_kernel="auto", cgs_fused=True, sweep_form=0, kb_alpha=False, kba=False) -> LanczosResult:
     """Enqueue and run the n-step loop (lz_lanczos_run).  `v0` is a host array (copied through
     pinned memory) or a CUDA tensor of M doubles."""
     torch = _torch()

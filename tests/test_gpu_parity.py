@@ -937,10 +937,10 @@ def test_kba_step_matches_ka_kb(lz, grid, bc, pot):
     assert rel(res[True][0][:k], ref["alpha"][:k]) < 1e-12 and rel(res[True][1][:k], ref["beta"][:k]) < 1e-12
     assert np.max(np.abs(res[True][2][:, :3] - res[False][2][:, :3])) < 1e-13
     R = lz.Lanczos(op)
-    R.execute_Lanczos(n, seed=5, reorth="none", keep_basis=False)       # three-row ring
+    R.execute_Lanczos(n, seed=5, reorth="none", keep_basis=False, kba=True)       # three-row ring
     assert R.result.kba and rel(np.diag(R.H_eff)[:k], res[True][0][:k]) < 1e-12
     full = orc.lanczos(H, 30, seed=5)
     S = lz.Lanczos(op)
-    S.execute_Lanczos(30, seed=5, reorth="selective", cgs_passes=2, select_tol=1e-15)      # sweeps fire: alpha re-taken by KA2
+    S.execute_Lanczos(30, seed=5, reorth="selective", cgs_passes=2, select_tol=1e-15, kba=True)      # sweeps fire: alpha re-taken by KA2
     assert S.result.kba and S.result.reorth_count >= 25
     assert rel(np.diag(S.H_eff), full["alpha"]) < 1e-11 and rel(np.diag(S.H_eff, 1), full["beta"]) < 1e-11
