@@ -17,12 +17,8 @@
 //     16-byte cp.async copies (LDGSTS), every thread copying exactly the operands it reads back
 //     itself, two planes ahead: completion is a per-thread cp.async.wait_group, no barrier, and
 //     the bytes in flight per SM are set by the ring depth, not by registers or occupancy.
-//     (Measured alternatives on B200, 512^3, ms per step: plain LDG.128 loads consumed in the same
-//     iteration 1.41; 1-D bulk-TMA row copies (cp.async.bulk, 544 B each) issued by one producer
-//     warp 1.89, by three producer warps 1.19, by lane 0 of every warp 1.43 - the per-copy issue
-//     cost of ~30 small bulk copies per plane dominates; warp-autonomous 64x4 register tiles
-//     without shared memory 1.51 - 30 % extra DRAM reads for the halo rows and serialised loads;
-//     this cp.async version 1.07-1.11, on par with the two-pass step at 1.10.)
+//     (The alternatives that were measured - plain loads, 1-D bulk-TMA row copies, register tiles - are in
+//     DESIGN.md section 8.)
 //   * Compute: warps 1..8 own the tile rows, warps 0 and 9 recompute r on the two halo rows, lanes
 //     0 / 31 on the two halo columns, the first / last iteration on the two halo planes - the
 //     stencil needs r_{j+1} on the tile's one-point halo and that is cheaper to recompute (extra

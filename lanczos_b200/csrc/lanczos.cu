@@ -1,7 +1,7 @@
-// The Lanczos tridiagonalisation loop: host-side launch sequence plus the single-CTA
-// "fin" kernels that finish every reduction deterministically on the device - across CTAs and,
-// in a row-sharded run, across GPUs through NVLink peer memory - and keep alpha, beta, the lazy
-// normalisation factors and the Gram-Schmidt coefficients in HBM, so that the host never
+// The Lanczos tridiagonalisation loop: the host-side launch sequence.  Every reduction is finished
+// deterministically on the device - across CTAs and, in a row-sharded run, across GPUs through NVLink
+// peer memory - by the tail of the kernel that produced it (fin.cuh); alpha, beta, the lazy
+// normalisation factors and the Gram-Schmidt coefficients stay in HBM, so that the host never
 // synchronises inside the loop.
 //
 // Replaces Lanczos.execute_Lanczos lines 100-119 (Python/Regular/Lanczos.py) and
@@ -9,15 +9,16 @@
 //
 // Per step j (device kernels, one stream per shard):
 //   [K4a cgs_dots -> fin_ip -> K4b cgs_update] x passes   (full: every step; selective: predicated)
-//   K1 apply_dot(row j, s_j) -> w, partials            fin_alpha -> alpha[j]
-//   K3 update_norm(w, row j, row j-1) -> row j+1       fin_beta  -> beta[j+1], s_{j+1} = 1/beta
-//   [omega recurrence -> flag for step j+1]             (selective only)
+//   matrix-free operators:  KA2(row j) -> alpha[j] in its tail;  KB(row j, row j-1) -> row j+1, beta[j+1],
+//                           s_{j+1} = 1/beta and the omega recurrence in its tail              (32*M bytes)
+//   stored operators:       K2 apply_dot(row j) -> w, alpha[j];  K3 update_norm(w, row j, row j-1) -> row j+1,
+//                           beta[j+1], ...                                  (48*M bytes + the operator's own)
 // Basis rows are stored un-normalised (row j = r_j, q_j = s_j * row j) unless a Gram-Schmidt
-// sweep rewrote them (then s_j = 1): the plain step moves 48*M bytes.
+// sweep rewrote them (then s_j = 1).
 //
 // Sharded runs (lz_team): every vector and basis row is split into contiguous row blocks, one
-// per GPU (z-slabs of a structured grid).  K3 / K4b store the boundary planes of the vector they
-// produce straight into the neighbours' ghost buffers; the fin kernels push their partial sums
+// per GPU (z-slabs of a structured grid).  KB / K3 / K4b store the boundary planes of the vector they
+// produce straight into the neighbours' ghost buffers; the tails push their partial sums
 // to every peer and add the P contributions in rank order (peer.cuh) - that flag also
 // publishes the halo.  No NCCL call, no extra pass over HBM, no extra launch per step.
 #include <math.h>

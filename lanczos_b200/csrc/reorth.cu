@@ -269,9 +269,7 @@ cgs_update_dots_kernel(const double* __restrict__ V, int64_t ldv, int k, double*
 // byte count and issues a single cp.async.bulk.tensor.2d; the TMA unit walks the rows, zero-fills the
 // columns past M and lands the box densely in shared memory.  Two stages: the box of the CTA's next
 // tile is in flight while the current one is reduced, so one CTA keeps 60-120 KB of HBM reads in flight
-// with no registers or issue slots spent on them.  (Per-row 1-D bulk copies, one per thread, were
-// measured first: 60 copies of 1 KB per tile made the fused kernel 1.7x slower than the cp.async
-// form - the per-copy cost of small bulk transfers dominates.)
+// with no registers or issue slots spent on them.
 template <int TC, int RMAX>
 __global__ void __launch_bounds__(TC)
 cgs_update_dots_tma_kernel(const __grid_constant__ CUtensorMap tmap, int k, double* target,

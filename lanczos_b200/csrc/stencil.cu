@@ -68,14 +68,8 @@ __device__ __forceinline__ void zero_vec(double (&v)[VEC]) {
     for (int e = 0; e < VEC; ++e) v[e] = 0.0;
 }
 
-// Occupancy matters more than unrolling here (the kernel is latency-bound): 6 CTAs/SM (40
-// registers, 48 warps) and no unrolling measured 0.376 ms at 512^3 against 0.403 ms for the
-// compiler's default 48 registers / 5 CTAs; forcing 7-8 CTAs spills and is slower.
-// Resident CTAs per SM the register budget is cut for (best measured on B200 at 512^3: K1 / KA
-// 6 x 40 registers, KB 4 x 64 registers without spills: 0.555 ms against 0.623 ms at 5 x 48).
-// A register queue of planes further ahead (loads of z+2.. in flight) was tried and is slower
-// (KA 0.25 -> 0.35-0.41 ms, KB 0.55 -> 0.89 ms): the y-neighbour rows are served by L1, and more
-// planes in flight per CTA push them out.
+// Resident CTAs per SM the register budget is cut for (the kernels are latency-bound: occupancy matters
+// more than unrolling).  K1 / KA: 6 x 40 registers; KB: 4 x 64 registers, no spills.
 #ifndef LZ_K1_MINBLOCKS
 #define LZ_K1_MINBLOCKS 6
 #endif
@@ -440,11 +434,8 @@ stencil_alpha_kernel(const StencilArgs a) {
 // thread is active, so nothing is predicated.  Boundary cases are folded into data instead of control
 // flow: an absent neighbour (Dirichlet wall, missing plane) is read from a clamped valid address and
 // its coupling coefficient is zero; the plane base is a uniform pointer bumped once per plane and the
-// per-thread offsets are 32-bit.  The general kernel above spends ~130 instructions per plane and
-// thread (address arithmetic, re-materialised constants, zeroing for predicated loads) and runs at
-// 66 % issue utilisation; this loop needs ~60.  Measured at 512^3: 0.215 ms either way, and the same
-// for CTA tiles of 64x16, 128x8, 256x4 and 512x2 points (LZ_KA2_WX) - the kernel is bound by the
-// latency of the HBM stream at ~5.0 TB/s, not by issue slots or by the tile shape.
+// per-thread offsets are 32-bit.  With three planes in registers (the loads of plane z + 2 in flight
+// while plane z is reduced) it runs at 0.181 ms at 512^3 against 0.215 ms for the general form.
 #ifndef LZ_KA2_WX
 #define LZ_KA2_WX 1          // warps side by side in x: the CTA tile is (64 * WX) x (16 / WX) points
 #endif
@@ -556,25 +547,8 @@ stencil_alpha_fast_kernel(const StencilArgs a) {
     fin_tail(a.fin, a.partials, red);
 }
 
-// KB with its two HBM streams (own values of the plane above, v_{j-1}) fetched 2-4 planes ahead by
-// per-thread cp.async copies into thread-private shared-memory slots was measured too: 0.550 ms at best
-// (ring of 4, 5 CTAs/SM) against 0.558 ms - within noise of the plain kernel, which is what runs.
-// A lean KB in the style of the lean KA2 kernel (2 x-points on 2 rows per thread, boundaries folded into
-// coefficients, own rows two planes ahead and neighbour rows / v_{j-1} one plane ahead in registers) was
-// built and measured: bit-identical results, 128 registers with spills at 2 CTAs per SM, 0.573 ms at 512^3
-// against 0.558 ms for MODE 2 of the general kernel at 4 CTAs per SM - the staging registers cost the
-// occupancy they were meant to replace, so KB stays with the general kernel.
-
-// KB-TMA (git history: "KB-TMA: producer warp + full/empty mbarriers"): KB with every 64 x 8 plane tile of
-// x and of v_{j-1} fetched by one cp.async.bulk.tensor.3d into a ring of shared-memory slots, y-neighbours
-// read from the slots, z-neighbours in registers, outside rows / columns by plain loads one plane ahead.
-// Correct on every test (single GPU, sharded, both boundary types) but slower than the general kernel at
-// 512^3: 0.582 ms with an elected thread and one __syncthreads per plane (ring of 6, 3 CTAs/SM), 0.675 ms
-// with a producer warp and full/empty mbarriers (deeper rings: 0.77-0.99 ms), against 0.558 ms.  Two tensor
-// copies of 4 KB per plane and CTA are too small: the K4c experience (reorth.cu) is that the cost of a bulk
-// copy is per instruction, and K4c moves 60 KB with one.  Wider tiles confirm it - 128x4: 0.71 ms, 256x4 (16
-// consumer warps): 0.79-0.97 ms (spills at 2 CTAs/SM), 512x2 (whole 4 KB rows per copy): 0.557 ms, i.e. parity
-// with the general kernel at three times its code.  KB therefore stays with the general kernel.
+// (KB variants that were built and measured - cp.async rings, a lean two-row form, TMA-staged tiles - are
+// recorded in DESIGN.md section 8; the general kernel above is what runs.)
 
 template <int VEC, bool HAS_Y, bool HAS_Z, int MODE>
 static const void* pick_diag(bool has_diag) {
