@@ -67,6 +67,18 @@ struct FinTail {
                                        // phase runs as fin_scalar_kernel once every shard has pushed
 };
 
+// Tail of a kernel that produced Gram-Schmidt dot partials part[r * ncg + g] (K4a, K4c): the coefficients of
+// the sweep of row j, see fin_ip_body.
+struct IpTail {
+    int on = 0;                        // 0: the kernel only writes its partials
+    int j = 0, self_included = 0, ref_form = 0, count = 0;
+    unsigned int* ticket = nullptr;
+    RunState st{};
+    PeerComm pc;
+    unsigned long long seq = 0;
+    int mode = LZ_XCHG_FUSED;
+};
+
 #ifdef __CUDACC__
 
 // Fixed-order sum of n partials by one CTA: thread t adds p[t], p[t+256], ... then the
@@ -182,6 +194,72 @@ __device__ __forceinline__ void fin_scalar_body(const FinOp& f, const RunState& 
     if (threadIdx.x == 0) fin_apply(f, st, s);
     if (f.kind == FIN_BETA && f.omega_j >= 0)
         omega_body(st, f.omega_j, f.om_cur, f.om_prev, f.delta, f.eps1, f.psi, red);
+}
+
+// Gram-Schmidt coefficients from the dots partials (whole CTA, any block size):
+//   ip_r = scale[r] * scale[j] * sum_ranks sum_g part[r*ncg + g]            r < j
+//   coef[r] = ip_r * scale[r]
+//   cself = (ref_form ? 2 - scale[j]^2 * (row_j . row_j) : 1) * scale[j];  scale[j] <- 1
+__device__ __forceinline__ void fin_ip_body(const double* part, int ncg, int j, int self_included, int ref_form,
+                                            const RunState& st, const PeerComm& pc, unsigned long long seq, int mode,
+                                            int count) {
+    const int nrows = self_included ? j + 1 : j;
+    const bool sharded = pc.world > 1;
+    const int nthr = blockDim.x;
+    __shared__ double s_self;
+    if (threadIdx.x == 0) s_self = 0.0;
+    __syncthreads();
+    if (mode != LZ_XCHG_COMBINE) {
+        const double sj0 = st.scale[j];
+        for (int r = threadIdx.x; r < nrows; r += nthr) {
+            const double* p = part + (int64_t)r * ncg;
+            double a = 0.0;
+            for (int g = 0; g < ncg; ++g) a += __ldcg(p + g);
+            if (sharded) peer_store(pc, seq, r, a);
+            else if (r < j) { const double sr = st.scale[r]; st.coef[r] = (a * sr * sj0) * sr; }
+            else s_self = a;
+        }
+        if (sharded) {
+            peer_publish(pc, seq);
+            if (mode == LZ_XCHG_PUSH) return;
+        }
+    }
+    if (sharded) {
+        peer_wait(pc, seq);
+        const double sj0 = st.scale[j];
+        for (int r = threadIdx.x; r < nrows; r += nthr) {
+            const double a = peer_sum(pc, seq, r);
+            if (r < j) { const double sr = st.scale[r]; st.coef[r] = (a * sr * sj0) * sr; }
+            else s_self = a;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double sj = st.scale[j];
+        double c = 1.0;
+        if (self_included && ref_form) c = 2.0 - s_self * sj * sj;
+        st.cself[0] = c * sj;
+        st.scale[j] = 1.0;           // K4b stores the row normalised
+        if (count) st.flags[2] += 1;
+    }
+}
+
+// Tail of a kernel that wrote dot partials: the last CTA to finish turns them into coefficients.  Call with
+// the whole CTA after its partials have been stored.
+__device__ __forceinline__ void ip_tail(const IpTail& t, const double* part, int ncg) {
+    if (!t.on) return;
+    __shared__ int s_last_ip;
+    __syncthreads();                                       // every thread's partial stores are issued
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int k = atomicAdd(t.ticket, 1u);
+        s_last_ip = (k == gridDim.x - 1);
+        if (s_last_ip) *t.ticket = 0;
+    }
+    __syncthreads();
+    if (!s_last_ip) return;
+    __threadfence();
+    fin_ip_body(part, ncg, t.j, t.self_included, t.ref_form, t.st, t.pc, t.seq, t.mode, t.count);
 }
 
 // Tail of a producing kernel.  Call with the whole CTA after thread 0 has stored

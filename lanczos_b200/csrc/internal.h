@@ -163,8 +163,9 @@ int launch_scale(lz_ctx* ctx, double* x, int64_t M, double s);
 
 // ---- Gram-Schmidt block GEMV pair (reorth.cu) --------------------------------------------
 // dots: part[(r * ncg) + g] = partial of V[r,:] . V[j,:]   for r in [0, nrows)   (nrows <= j+1)
+// `tail` (nullable): the last CTA turns the partials into the sweep's coefficients (fin.cuh IpTail)
 int launch_cgs_dots(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, const double* target,
-                    int64_t M, double* part, int* ncg_out, const int* flag_dev);
+                    int64_t M, double* part, int* ncg_out, const int* flag_dev, const IpTail* tail = nullptr);
 // update: out = cself * target - sum_{r<nrows} coef[r] * V[r,:]   (coef, cself on the device)
 int launch_cgs_update(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, const double* target,
                       const double* coef_dev, const double* cself_dev, double* out, int64_t M,
@@ -174,7 +175,7 @@ int launch_cgs_update(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, cons
 bool cgs_update_dots_supported(const double* V, int64_t ldv, int k, const double* target);
 int launch_cgs_update_dots(lz_ctx* ctx, const double* V, int64_t ldv, int k, double* target,
                            const double* coef_dev, const double* cself_dev, int64_t M, double* part,
-                           int* ncg_out, const int* flag_dev);
+                           int* ncg_out, const int* flag_dev, const IpTail* tail = nullptr);
 // Y[c,:] = sum_r S[r + c*n] * V[r,:]  (S on the device, n x k column-major)
 int launch_ritz_lift(lz_ctx* ctx, const double* V, int64_t ldv, int n, int64_t M,
                      const double* S_dev, int k, double* Y, int64_t ldy);

@@ -71,54 +71,16 @@ __global__ void init_first_row_kernel(RunState st) {
     }
 }
 
-// Gram-Schmidt coefficients from the dots partials:
-//   ip_r = scale[r] * scale[j] * sum_ranks sum_g part[r*ncg + g]            r < j
-//   coef[r] = ip_r * scale[r]
-//   cself = (ref_form ? 2 - scale[j]^2 * (row_j . row_j) : 1) * scale[j];  scale[j] <- 1
+// Gram-Schmidt coefficients from the dots partials as a kernel of its own (fin_ip_body, fin.cuh): the
+// combine phase when one process drives several shards, and the opt-in single-pass step; elsewhere it is
+// the tail of the kernel that produced the partials.
 __global__ void __launch_bounds__(kThreads)
 fin_ip_kernel(const double* __restrict__ part, int ncg, int j, int self_included, int ref_form,
               RunState st, PeerComm pc, unsigned long long seq, int mode,
               const int* __restrict__ flag, int count) {
     pdl_prologue();
     if (flag && *flag == 0) return;
-    const int nrows = self_included ? j + 1 : j;
-    const bool sharded = pc.world > 1;
-    __shared__ double s_self;
-    if (threadIdx.x == 0) s_self = 0.0;
-    __syncthreads();
-    if (mode != LZ_XCHG_COMBINE) {
-        const double sj0 = st.scale[j];
-        for (int r = threadIdx.x; r < nrows; r += kThreads) {
-            const double* p = part + (int64_t)r * ncg;
-            double a = 0.0;
-            for (int g = 0; g < ncg; ++g) a += p[g];
-            if (sharded) peer_store(pc, seq, r, a);
-            else if (r < j) { const double sr = st.scale[r]; st.coef[r] = (a * sr * sj0) * sr; }
-            else s_self = a;
-        }
-        if (sharded) {
-            peer_publish(pc, seq);
-            if (mode == LZ_XCHG_PUSH) return;
-        }
-    }
-    if (sharded) {
-        peer_wait(pc, seq);
-        const double sj0 = st.scale[j];
-        for (int r = threadIdx.x; r < nrows; r += kThreads) {
-            const double a = peer_sum(pc, seq, r);
-            if (r < j) { const double sr = st.scale[r]; st.coef[r] = (a * sr * sj0) * sr; }
-            else s_self = a;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const double sj = st.scale[j];
-        double c = 1.0;
-        if (self_included && ref_form) c = 2.0 - s_self * sj * sj;
-        st.cself[0] = c * sj;
-        st.scale[j] = 1.0;           // K4b stores the row normalised
-        if (count) st.flags[2] += 1;
-    }
+    fin_ip_body(part, ncg, j, self_included, ref_form, st, pc, seq, mode, count);
 }
 
 // Flag-only exchange: publishes the halo planes that the preceding kernel of this stream stored
@@ -814,33 +776,53 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
             // one fused kernel (K4c) when the staged tile fits shared memory
             bool fuse = allow_gs_fusion && j >= 1;
             for (int s = 0; s < nl && fuse; ++s) fuse = cgs_update_dots_supported(R[s].V, R[s].ldv, j, R[s].row(j));
+            // the coefficients of a sweep are formed in the tail of the kernel that produced the dots (fin.cuh
+            // IpTail); several local shards: the tails push, one combine kernel per shard follows
+            auto dots_with_coefficients = [&](int form, int count_it, auto&& produce) -> int {
+                unsigned long long seq = 0;
+                if (team) seq = ++team->seq;
+                LZ_CHECK(each([&](ShardRun& r) {
+                    IpTail t;
+                    t.on = 1;
+                    t.j = j;
+                    t.self_included = form;
+                    t.ref_form = form;
+                    t.count = (count_it && !split) ? 1 : 0;
+                    t.ticket = r.ctx->tickets;
+                    t.st = r.st;
+                    t.pc = r.pc;
+                    t.seq = seq;
+                    t.mode = split ? (int)LZ_XCHG_PUSH : (int)LZ_XCHG_FUSED;
+                    return produce(r, &t);
+                }));
+                if (!split) return LZ_OK;
+                return each([&](ShardRun& r) {
+                    LZ_CUDA(launch_k(fin_ip_kernel, dim3(1), dim3(kThreads), 0, r.ctx->stream, (const double*)r.gs_part,
+                                     r.ncg, j, form, form, r.st, r.pc, seq, (int)LZ_XCHG_COMBINE,
+                                     sel ? (const int*)(r.st.flags + 1) : (const int*)nullptr, count_it));
+                    ++launches;
+                    return LZ_OK;
+                });
+            };
             for (int p = 0; p < passes; ++p) {
                 const int ref_form = (ref && p == 0 && !gpu_sweep) ? 1 : 0;   // (2 - |v|^2) form incl. the self term
                 const int nrows = ref_form ? j + 1 : j;      // the reference's sum includes row j itself
                 if (nrows == 0) continue;
-                if (!(fuse && p == 1)) {
-                    LZ_CHECK(each([&](ShardRun& r) {
+                if (!(fuse && p == 1)) {                     // (fused CGS2: K4c already left the second sweep's coefficients)
+                    LZ_CHECK(dots_with_coefficients(ref_form, p == 0 ? 1 : 0, [&](ShardRun& r, const IpTail* t) {
                         r.kt.begin(K_DOTS);
                         const int rc = launch_cgs_dots(r.ctx, r.V, r.ldv, nrows, r.row(j), r.M, r.gs_part, &r.ncg,
-                                                       sel ? r.st.flags + 1 : nullptr);
+                                                       sel ? r.st.flags + 1 : nullptr, t);
                         r.kt.end();
                         ++launches;
                         return rc;
                     }));
                 }
-                LZ_CHECK(exchange([&](ShardRun& r, unsigned long long seq, int mode) -> int {
-                    LZ_CUDA(launch_k(fin_ip_kernel, dim3(1), dim3(kThreads), 0, r.ctx->stream, (const double*)r.gs_part,
-                                     r.ncg, j, ref_form, ref_form, r.st, r.pc, seq, mode,
-                                     sel ? (const int*)(r.st.flags + 1) : (const int*)nullptr,
-                                     (p == 0 && mode != LZ_XCHG_PUSH) ? 1 : 0));
-                    ++launches;
-                    return LZ_OK;
-                }));
                 if (fuse && p == 0) {
-                    LZ_CHECK(each([&](ShardRun& r) {
+                    LZ_CHECK(dots_with_coefficients(0, 0, [&](ShardRun& r, const IpTail* t) {
                         r.kt.begin(K_GSFUSED);
                         const int rc = launch_cgs_update_dots(r.ctx, r.V, r.ldv, j, r.row(j), r.st.coef, r.st.cself, r.M,
-                                                              r.gs_part, &r.ncg, sel ? r.st.flags + 1 : nullptr);
+                                                              r.gs_part, &r.ncg, sel ? r.st.flags + 1 : nullptr, t);
                         r.kt.end();
                         ++launches;
                         return rc;

@@ -26,7 +26,7 @@ constexpr int kRowsPerCta = 8;     // register-blocked rows of the dots kernel
 __global__ void __launch_bounds__(kThreads)
 cgs_dots_kernel(const double* __restrict__ V, int64_t ldv, int nrows,
                 const double* __restrict__ target, int64_t M, int64_t chunk, int nrb, int ncg,
-                int vec_ok, double* __restrict__ part, const int* __restrict__ flag) {
+                int vec_ok, double* __restrict__ part, const int* __restrict__ flag, const IpTail tail) {
     pdl_prologue();
     if (flag && *flag == 0) return;
     __shared__ double red[kWarps];
@@ -83,10 +83,11 @@ cgs_dots_kernel(const double* __restrict__ V, int64_t ldv, int nrows,
         const double tot = block_sum(acc[r], red);
         if (threadIdx.x == 0 && r < nr) part[(int64_t)(r0 + r) * ncg + g] = tot;
     }
+    ip_tail(tail, part, ncg);
 }
 
 int launch_cgs_dots(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, const double* target,
-                    int64_t M, double* part, int* ncg_out, const int* flag_dev) {
+                    int64_t M, double* part, int* ncg_out, const int* flag_dev, const IpTail* tail) {
     const int nrb = (nrows + kRowsPerCta - 1) / kRowsPerCta;
     const int64_t target_ctas = (int64_t)ctx->sms * 8;
     int64_t ncg = std::max<int64_t>(1, (target_ctas + nrb - 1) / nrb);
@@ -98,7 +99,8 @@ int launch_cgs_dots(lz_ctx* ctx, const double* V, int64_t ldv, int nrows, const 
     ncg = (M + chunk - 1) / chunk;
     const int vec_ok = ((((uintptr_t)V | (uintptr_t)target) & 15) == 0) && ((ldv & 1) == 0);
     LZ_CUDA(launch_k(cgs_dots_kernel, dim3((unsigned)(nrb * ncg)), dim3(kThreads), 0, ctx->stream,
-                     V, ldv, nrows, target, M, chunk, nrb, (int)ncg, vec_ok, part, flag_dev));
+                     V, ldv, nrows, target, M, chunk, nrb, (int)ncg, vec_ok, part, flag_dev,
+                     tail ? *tail : IpTail{}));
     if (ncg_out) *ncg_out = (int)ncg;
     return LZ_OK;
 }
@@ -203,7 +205,7 @@ template <int TC, int RMAX>
 __global__ void __launch_bounds__(TC)
 cgs_update_dots_kernel(const double* __restrict__ V, int64_t ldv, int k, double* target,
                        const double* __restrict__ coef, const double* __restrict__ cself_p, int64_t M,
-                       int64_t ntiles, double* __restrict__ part, const int* __restrict__ flag) {
+                       int64_t ntiles, double* __restrict__ part, const int* __restrict__ flag, const IpTail tail) {
     pdl_prologue();
     if (flag && *flag == 0) return;
     extern __shared__ __align__(128) double sm[];
@@ -261,6 +263,7 @@ cgs_update_dots_kernel(const double* __restrict__ V, int64_t ldv, int k, double*
         const double tot = warp_sum(acc[q]);
         if (lane == 0 && r < k) part[(int64_t)r * gridDim.x + blockIdx.x] = tot;
     }
+    ip_tail(tail, part, (int)gridDim.x);
 }
 
 // ---- K4c with TMA: the same computation, the tile fetched by ONE tensor copy ----------------------
@@ -274,7 +277,7 @@ template <int TC, int RMAX>
 __global__ void __launch_bounds__(TC)
 cgs_update_dots_tma_kernel(const __grid_constant__ CUtensorMap tmap, int k, double* target,
                            const double* __restrict__ coef, const double* __restrict__ cself_p, int64_t M,
-                           int64_t ntiles, double* __restrict__ part, const int* __restrict__ flag) {
+                           int64_t ntiles, double* __restrict__ part, const int* __restrict__ flag, const IpTail tail) {
     pdl_prologue();
     if (flag && *flag == 0) return;
     extern __shared__ __align__(128) double sm[];
@@ -346,6 +349,7 @@ cgs_update_dots_tma_kernel(const __grid_constant__ CUtensorMap tmap, int k, doub
         const double tot = warp_sum(acc[q]);
         if (lane == 0 && r < k) part[(int64_t)r * gridDim.x + blockIdx.x] = tot;
     }
+    ip_tail(tail, part, (int)gridDim.x);
 }
 
 struct UpdDotsCfg { int tc, rmax; size_t smem; };
@@ -400,7 +404,8 @@ bool cgs_update_dots_supported(const double* V, int64_t ldv, int k, const double
 // target <- cself * target - V_k coef (in place), part[r * ncg + g] = partial of V[r, :] . target_new
 int launch_cgs_update_dots(lz_ctx* ctx, const double* V, int64_t ldv, int k, double* target,
                            const double* coef_dev, const double* cself_dev, int64_t M, double* part,
-                           int* ncg_out, const int* flag_dev) {
+                           int* ncg_out, const int* flag_dev, const IpTail* tail) {
+    IpTail tl = tail ? *tail : IpTail{};
     UpdDotsCfg c;
     LZ_REQUIRE(cgs_update_dots_supported(V, ldv, k, target), "fused Gram-Schmidt update+dots: unsupported shape (k = %d)", k);
     update_dots_config(k, &c);
@@ -438,11 +443,11 @@ int launch_cgs_update_dots(lz_ctx* ctx, const double* V, int64_t ldv, int k, dou
     int kk = k;
     if (tma) {
         void* targs[] = {(void*)&tmap, (void*)&kk, (void*)&target, (void*)&coef_dev, (void*)&cself_dev,
-                         (void*)&M, (void*)&ntiles, (void*)&part, (void*)&flag_dev};
+                         (void*)&M, (void*)&ntiles, (void*)&part, (void*)&flag_dev, (void*)&tl};
         LZ_CUDA(launch_fn(fn, dim3(grid), dim3(c.tc), c.smem, ctx->stream, targs));
     } else {
         void* args[] = {(void*)&V, (void*)&ldv, (void*)&kk, (void*)&target, (void*)&coef_dev, (void*)&cself_dev,
-                        (void*)&M, (void*)&ntiles, (void*)&part, (void*)&flag_dev};
+                        (void*)&M, (void*)&ntiles, (void*)&part, (void*)&flag_dev, (void*)&tl};
         LZ_CUDA(launch_fn(fn, dim3(grid), dim3(c.tc), c.smem, ctx->stream, args));
     }
     if (ncg_out) *ncg_out = grid;
