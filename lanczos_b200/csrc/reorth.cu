@@ -523,101 +523,99 @@ ritz_lift_kernel(const double* __restrict__ V, int64_t ldv, int n, int64_t M,
 // K5 as a tall-skinny GEMM: Y (k x M) = S^T (k x n) . V (n x M), the whole lift of get_H_eigs
 // (Lanczos.py:154-156) from ONE read of the basis per 64 Ritz vectors instead of one per 4.
 //
-// A CTA of 8 warps owns a tile of 256 columns of M and 64 output rows (Ritz vectors): warp w works on
-// the 128 columns of half (w & 1) and the 16 Ritz vectors of group (w >> 1); a thread holds a 16 x 4 block
+// A CTA of 16 warps owns a tile of 256 columns of M and 64 output rows (Ritz vectors): warp w works on
+// the 128 columns of half (w & 1) and the 8 Ritz vectors of group (w >> 1); a thread holds an 8 x 4 block
 // of accumulators (columns 2*lane, 2*lane+1 of each 64-column quarter).  The rows of the basis tile stream
-// through a shared-memory ring filled by 16-byte cp.async copies four rows per step and four steps ahead
-// (32 KB in flight per SM); the ring index runs on across tiles, so the pipeline never drains.  Per basis row
-// a thread issues 2 + 8 shared-memory loads (its 4 values, 16 broadcast coefficients) for 64 fp64 FMAs: the
-// FMA pipe, not the load/store unit, is what limits it.  S sits in shared memory (<= 128 rows per launch,
-// more rows accumulate into Y in further launches).  At n = k = 60, 512^3: 2 n 8 M = 129 GB of compulsory
-// traffic and 0.97 TFLOP - the two roofs (6.5 TB/s, 40 TFLOP/s) are 20 ms and 24 ms apart.
+// through a shared-memory ring filled by 16-byte cp.async copies, four rows per step (one copy per thread)
+// and four steps ahead (32 KB in flight per SM); the ring runs on across tiles, so the pipeline never
+// drains.  A tile's rows are padded to a multiple of four with zero-filled copies, so a step never straddles
+// two tiles and its four rows are straight-line code: per basis row a thread issues 2 + 4 shared-memory
+// loads (its 4 values, 8 broadcast coefficients) for 32 fp64 FMAs.  S sits in shared memory (<= 128 rows per
+// launch, more rows accumulate into Y in further launches).  At n = k = 60, 512^3: 2 n 8 M = 129 GB of
+// compulsory traffic and 0.97 TFLOP - the two roofs (6.5 TB/s, 37 TFLOP/s) are 20 ms and 26 ms.
+constexpr int kGemmThreads = 512;
 constexpr int kGemmTile = 256;          // columns of M per CTA tile
 constexpr int kGemmOut = 64;            // Ritz vectors per pass
 constexpr int kGemmRowsPerStep = 4;     // basis rows per pipeline step
 constexpr int kGemmDepth = 4;           // steps in flight
 constexpr int kGemmRing = kGemmRowsPerStep * kGemmDepth;
 constexpr int kGemmRowsSmem = 128;      // rows of S per launch
+constexpr int kGemmAcc = 8;             // Ritz vectors per thread
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, int src_bytes) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(s), "l"(gmem), "r"(src_bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 ritz_lift_gemm_kernel(const double* __restrict__ V, int64_t ldv, int n, int64_t M, const double* __restrict__ S,
                       int lds, int ncols, double* Y, int64_t ldy, int accumulate, int64_t ntiles) {
     extern __shared__ __align__(128) double gsm[];
-    double* ss = gsm;                                    // [n][kGemmOut], zero-padded beyond ncols
+    double* ss = gsm;                                        // [nr4][kGemmOut], zero beyond n rows / ncols columns
     double* ring = gsm + (size_t)kGemmRowsSmem * kGemmOut;   // [kGemmRing][kGemmTile]
-    for (int q = threadIdx.x; q < n * kGemmOut; q += kThreads) {
+    const int nr4 = (n + kGemmRowsPerStep - 1) / kGemmRowsPerStep * kGemmRowsPerStep;
+    for (int q = threadIdx.x; q < nr4 * kGemmOut; q += kGemmThreads) {
         const int r = q / kGemmOut, c = q % kGemmOut;
-        ss[q] = (c < ncols) ? S[(int64_t)c * lds + r] : 0.0;
+        ss[q] = (r < n && c < ncols) ? S[(int64_t)c * lds + r] : 0.0;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int half = warp & 1, grp = warp >> 1;
+    const int steps_per_tile = nr4 / kGemmRowsPerStep;
     const int my_tiles = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
-    const int64_t total = (int64_t)my_tiles * n;         // (tile, row) slots of this CTA, in order
-    // producer side: thread t copies chunk (t & 127) of rows 2*u + (t >> 7), u = 0, 1, of a step
-    // (no division in the loops: the producer and the consumer each carry their own (tile, row) cursor)
+    const int64_t nsteps = (int64_t)my_tiles * steps_per_tile;
+    // producer: thread t copies 16-byte chunk (t & 127) of row (t >> 7) of every step (own (tile, step) cursor)
     const int chunk = threadIdx.x & 127, rsub = threadIdx.x >> 7;
-    int64_t pq = rsub;                                   // producer: next slot of this thread (slots rsub, rsub + 2, ...)
-    int pr = rsub % n;
-    int64_t ptile = blockIdx.x + (int64_t)(rsub / n) * gridDim.x;
-    auto issue_step = [&](int64_t) {
-#pragma unroll
-        for (int u = 0; u < kGemmRowsPerStep / 2; ++u) {
-            if (pq < total) {
-                const int64_t col = ptile * kGemmTile + 2 * chunk;
-                const int64_t left = M - col;
-                const int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
-                const double* src = V + (int64_t)pr * ldv + (bytes ? col : 0);
-                cp_async16_zfill(ring + (size_t)(pq & (kGemmRing - 1)) * kGemmTile + 2 * chunk, src, bytes);
-            }
-            pq += 2;
-            pr += 2;
-            while (pr >= n) { pr -= n; ptile += gridDim.x; }
+    int64_t pstep = 0;
+    int pst = 0;                                             // step inside the tile
+    int64_t ptile = blockIdx.x;
+    auto issue_step = [&]() {
+        if (pstep < nsteps) {
+            const int r = pst * kGemmRowsPerStep + rsub;
+            const int64_t col = ptile * kGemmTile + 2 * chunk;
+            const int64_t left = M - col;
+            const int bytes = (r < n) ? (left >= 2 ? 16 : (left == 1 ? 8 : 0)) : 0;
+            const double* src = bytes ? V + (int64_t)r * ldv + col : V;
+            cp_async16_zfill(ring + (size_t)((pstep & (kGemmDepth - 1)) * kGemmRowsPerStep + rsub) * kGemmTile + 2 * chunk, src, bytes);
         }
+        ++pstep;
+        if (++pst == steps_per_tile) { pst = 0; ptile += gridDim.x; }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    const int64_t nsteps = (total + kGemmRowsPerStep - 1) / kGemmRowsPerStep;
+    static_assert((kGemmDepth & (kGemmDepth - 1)) == 0, "ring depth must be a power of two");
 #pragma unroll 1
-    for (int s = 0; s < kGemmDepth - 1; ++s) issue_step(s);
-    double acc[16][4];
-    const int cbase = half * 128 + 2 * lane;             // this thread's columns: cbase, +1, cbase + 64, +65
-    int r = 0;                                           // consumer cursor
+    for (int s = 0; s < kGemmDepth - 1; ++s) issue_step();
+    double acc[kGemmAcc][4];
+    const int cbase = half * 128 + 2 * lane;                 // this thread's columns: cbase, +1, cbase + 64, +65
+    int st = 0;                                              // consumer: step inside the tile
     int64_t tile = blockIdx.x;
-    static_assert((kGemmRing & (kGemmRing - 1)) == 0, "ring size must be a power of two");
 #pragma unroll 1
     for (int64_t step = 0; step < nsteps; ++step) {
-        issue_step(step + kGemmDepth - 1);
+        issue_step();
         asm volatile("cp.async.wait_group %0;" :: "n"(kGemmDepth - 1) : "memory");
-        __syncthreads();                                 // the rows of `step` have landed (and ss on the first pass)
-#pragma unroll 1
-        for (int u = 0; u < kGemmRowsPerStep; ++u) {
-            const int64_t q = step * kGemmRowsPerStep + u;
-            if (q >= total) break;
-            const int64_t col = tile * kGemmTile + cbase;
-            if (r == 0) {
+        __syncthreads();                                     // the rows of `step` have landed (and ss on the first pass)
+        const int64_t col = tile * kGemmTile + cbase;
+        if (st == 0) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0;
-                    if (accumulate && grp * 16 + c < ncols) {
-                        double* py = Y + (int64_t)(grp * 16 + c) * ldy + col;
-                        if (col + 1 < M) { const double2 y = ld_stream2_rw(py); acc[c][0] = y.x; acc[c][1] = y.y; }
-                        else if (col < M) acc[c][0] = py[0];
-                        if (col + 65 < M) { const double2 y = ld_stream2_rw(py + 64); acc[c][2] = y.x; acc[c][3] = y.y; }
-                        else if (col + 64 < M) acc[c][2] = py[64];
-                    }
+            for (int c = 0; c < kGemmAcc; ++c) {
+                acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0;
+                if (accumulate && grp * kGemmAcc + c < ncols) {
+                    double* py = Y + (int64_t)(grp * kGemmAcc + c) * ldy + col;
+                    if (col + 1 < M) { const double2 y = ld_stream2_rw(py); acc[c][0] = y.x; acc[c][1] = y.y; }
+                    else if (col < M) acc[c][0] = py[0];
+                    if (col + 65 < M) { const double2 y = ld_stream2_rw(py + 64); acc[c][2] = y.x; acc[c][3] = y.y; }
+                    else if (col + 64 < M) acc[c][2] = py[64];
                 }
             }
-            const double* row = ring + (size_t)(q & (kGemmRing - 1)) * kGemmTile + cbase;
-            const double2 va = *reinterpret_cast<const double2*>(row);
-            const double2 vb = *reinterpret_cast<const double2*>(row + 64);
-            const double* sr = ss + (size_t)r * kGemmOut + grp * 16;
+        }
+        const double* rows = ring + (size_t)((step & (kGemmDepth - 1)) * kGemmRowsPerStep) * kGemmTile + cbase;
+        const double* sr = ss + (size_t)(st * kGemmRowsPerStep) * kGemmOut + grp * kGemmAcc;
 #pragma unroll
-            for (int c = 0; c < 16; c += 2) {
-                const double2 sc = *reinterpret_cast<const double2*>(sr + c);
+        for (int u = 0; u < kGemmRowsPerStep; ++u) {
+            const double2 va = *reinterpret_cast<const double2*>(rows + (size_t)u * kGemmTile);
+            const double2 vb = *reinterpret_cast<const double2*>(rows + (size_t)u * kGemmTile + 64);
+#pragma unroll
+            for (int c = 0; c < kGemmAcc; c += 2) {
+                const double2 sc = *reinterpret_cast<const double2*>(sr + (size_t)u * kGemmOut + c);
                 acc[c][0] = fma(sc.x, va.x, acc[c][0]);
                 acc[c][1] = fma(sc.x, va.y, acc[c][1]);
                 acc[c][2] = fma(sc.x, vb.x, acc[c][2]);
@@ -627,21 +625,22 @@ ritz_lift_gemm_kernel(const double* __restrict__ V, int64_t ldv, int n, int64_t 
                 acc[c + 1][2] = fma(sc.y, vb.x, acc[c + 1][2]);
                 acc[c + 1][3] = fma(sc.y, vb.y, acc[c + 1][3]);
             }
-            if (r == n - 1) {
+        }
+        if (++st == steps_per_tile) {
+            st = 0;
+            tile += gridDim.x;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    if (grp * 16 + c < ncols) {
-                        double* py = Y + (int64_t)(grp * 16 + c) * ldy + col;
-                        if (col + 1 < M) st_stream2(py, make_double2(acc[c][0], acc[c][1]));
-                        else if (col < M) py[0] = acc[c][0];
-                        if (col + 65 < M) st_stream2(py + 64, make_double2(acc[c][2], acc[c][3]));
-                        else if (col + 64 < M) py[64] = acc[c][2];
-                    }
+            for (int c = 0; c < kGemmAcc; ++c) {
+                if (grp * kGemmAcc + c < ncols) {
+                    double* py = Y + (int64_t)(grp * kGemmAcc + c) * ldy + col;
+                    if (col + 1 < M) st_stream2(py, make_double2(acc[c][0], acc[c][1]));
+                    else if (col < M) py[0] = acc[c][0];
+                    if (col + 65 < M) st_stream2(py + 64, make_double2(acc[c][2], acc[c][3]));
+                    else if (col + 64 < M) py[64] = acc[c][2];
                 }
             }
-            if (++r == n) { r = 0; tile += gridDim.x; }
         }
-        __syncthreads();                                 // everybody is done with the slots the next step refills
+        __syncthreads();                                     // everybody is done with the slots the next step refills
     }
 }
 
@@ -658,7 +657,7 @@ int launch_ritz_lift(lz_ctx* ctx, const double* V, int64_t ldv, int n, int64_t M
             const int nc = std::min(kGemmOut, k - c0);
             for (int w0 = 0; w0 < n; w0 += kGemmRowsSmem) {
                 const int wn = std::min(kGemmRowsSmem, n - w0);
-                ritz_lift_gemm_kernel<<<grid, kThreads, smem, ctx->stream>>>(
+                ritz_lift_gemm_kernel<<<grid, kGemmThreads, smem, ctx->stream>>>(
                     V + (int64_t)w0 * ldv, ldv, wn, M, S_dev + (int64_t)c0 * n + w0, n, nc,
                     Y + (int64_t)c0 * ldy, ldy, w0 > 0, ntiles);
                 LZ_CUDA(cudaGetLastError());
