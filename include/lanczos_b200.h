@@ -172,13 +172,14 @@ typedef struct lz_run_opts {
                               nx % 64 == 0, ny % 8 == 0, one GPU, reorth != full);
                               3 recompute step (matrix-free operators: KA reduces alpha without
                               writing H v, KB applies H again inside the update: 32*M B)       */
-    int32_t flags;         /* bit 0: do not fuse the middle of CGS2 (K4c: update of sweep 1 + dots of
-                              sweep 2 from one read of the basis); bit 1 (with ref_compat): the sweep
-                              takes the LZ_SWEEP_GPU form of Regular/Lanczos.py:236-238 instead of
-                              the (2 - |v|^2) form; bit 2: do not accumulate alpha inside KB (recompute
-                              step: a KA pass per step instead of the border kernel); bit 3: sparse row shards without
-                              the interior/boundary overlap on a second stream; bit 4: recompute step as KA + KB
-                              instead of the single KBA kernel; 0 = defaults */
+    int32_t flags;         /* 0 = defaults.  bit 0: do not fuse the middle of CGS2 (K4c: update of sweep 1 + dots of
+                              sweep 2 from one read of the basis); bit 1 (with ref_compat): the sweep takes the
+                              LZ_SWEEP_GPU form of Regular/Lanczos.py:236-238 instead of the (2 - |v|^2) form;
+                              bit 2: recompute step with alpha accumulated inside KB + a border kernel instead
+                              of a KA pass (measured slower); bit 3: sparse row shards
+                              without the interior/boundary overlap on a second stream; bit 4: recompute step
+                              as the single KBA kernel (measured slower); bit 5: small problems through the
+                              kernel-per-phase loop instead of the persistent cooperative kernel             */
     double  breakdown_tol; /* stop when beta <= breakdown_tol * |alpha_0| (0: only 0/NaN) */
     double  select_tol;    /* selective: orthogonality level that triggers (0 -> sqrt(eps)) */
 } lz_run_opts;
@@ -198,7 +199,8 @@ typedef struct lz_run_info {
     float   dots_ms;       /* ... K4a Gram-Schmidt dots                              */
     float   gsupd_ms;      /* ... K4b Gram-Schmidt update                            */
     float   fused_ms;      /* ... KF single-pass fused step                          */
-    int32_t step_kernel;   /* the step kernel that ran (1, 2 or 3 as in lz_run_opts)  */
+    int32_t step_kernel;   /* the step kernel that ran (1, 2 or 3 as in lz_run_opts; 4: the whole solve ran in
+                              the persistent cooperative kernel for small matrix-free problems) */
     int32_t gsfused_launches; /* ... K4c fused Gram-Schmidt update + dots              */
     float   gsfused_ms;
     int32_t border_launches;  /* ... the border kernel that completes alpha when KB accumulates it */

@@ -139,6 +139,12 @@ bool kba_step_supported(const lz_op* op, const double* x, const double* b, const
 int launch_kba_step(lz_op* op, const double* x, const double* scale_dev, const StencilUpdate* upd, double* out,
                     const FinTail* fin_beta, const FinOp* fin_alpha, int* nparts);
 
+// ---- the whole solve of a small matrix-free problem in one persistent cooperative kernel (small.cu) ----
+bool small_solve_supported(const lz_op* op, const lz_run_opts* opts, int32_t n, const double* V_dev, int64_t ldv);
+int launch_small_solve(lz_ctx* ctx, lz_op* op, const double* v0_dev, int32_t n, const lz_run_opts* opts,
+                       double* alpha_host, double* beta_host, double* V_dev, int64_t ldv, double* row_scale_host,
+                       lz_run_info* info);
+
 // ---- single-pass fused step (fused.cu) ---------------------------------------------------
 bool fused_step_supported(const lz_op* op);
 int launch_fused_step(lz_op* op, const double* u, const double* rj, const double* rjm1,

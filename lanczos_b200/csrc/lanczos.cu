@@ -443,13 +443,13 @@ int run_loop(lz_team* team, int nl, lz_op* const* ops, const double* const* v0s,
     // with full re-orthogonalisation (the sweep rewrites the vector, alpha must be taken afterwards anyway).
     // KBA (kba.cu): one kernel per step - KB plus the alpha reduction of the vector it writes, read back through
     // L2 a few z-planes behind: 24*M bytes of HBM per step instead of 32*M.  One GPU, whole tiles.
-    bool kba = recompute && !team && nl == 1 && reorth != LZ_REORTH_FULL && !(opts->flags & 16);
+    bool kba = recompute && !team && nl == 1 && reorth != LZ_REORTH_FULL && (opts->flags & 16);
     if (kba) {
         const double* any_row = R[0].V ? R[0].V : R[0].ring;
         kba = kba_step_supported(R[0].op, any_row, any_row, any_row) && ((reinterpret_cast<uintptr_t>(R[0].v0) & 15) == 0) &&
               (((R[0].V ? R[0].ldv : R[0].ld_int) & 1) == 0);
     }
-    bool kb_alpha = !kba && recompute && reorth != LZ_REORTH_FULL && !(opts->flags & 4);
+    bool kb_alpha = !kba && recompute && reorth != LZ_REORTH_FULL && (opts->flags & 4);
     for (int s = 0; s < nl && kb_alpha; ++s)
         kb_alpha = update_alpha_supported(R[s].op, R[s].V ? R[s].V : R[s].ring, R[s].V ? R[s].V : R[s].ring);
 
@@ -1113,6 +1113,11 @@ extern "C" int lz_lanczos_run(lz_ctx* ctx, lz_op* op, const double* v0_dev, int3
     LZ_REQUIRE(op->ctx == ctx, "lz_lanczos_run: operator belongs to another context");
     LZ_REQUIRE(!op->st.sharded, "lz_lanczos_run: this operator is a shard of a team; use lz_team_lanczos_run");
     LZ_CUDA(cudaSetDevice(ctx->device));
+    // launch-bound sizes: the whole solve in one persistent kernel (small.cu)
+    if (n >= 1 && !(opts->ref_compat && n < 2) && n <= op->M && (n < 2 || beta_host) && opts->cgs_passes <= 2 &&
+        (opts->reorth == LZ_REORTH_NONE || opts->reorth == LZ_REORTH_FULL) &&
+        small_solve_supported(op, opts, n, V_dev, ldv))
+        return launch_small_solve(ctx, op, v0_dev, n, opts, alpha_host, beta_host, V_dev, ldv, row_scale_host, info);
     lz_op* ops[1] = {op};
     const double* v0s[1] = {v0_dev};
     double* Vs[1] = {V_dev};

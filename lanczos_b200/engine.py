@@ -20,7 +20,7 @@ _REORTH = {"none": LZ_REORTH_NONE, "full": LZ_REORTH_FULL, "selective": LZ_REORT
 
 
 STEP_KERNEL = {"auto": 0, "two_pass": 1, "fused": 2, "recompute": 3, 0: 0, 1: 1, 2: 2, 3: 3}
-STEP_KERNEL_NAME = {1: "two_pass", 2: "fused", 3: "recompute"}
+STEP_KERNEL_NAME = {1: "two_pass", 2: "fused", 3: "recompute", 4: "persistent"}
 
 
 def _torch():
@@ -31,13 +31,13 @@ def _torch():
 
 
 def run_flags(cgs_fused: bool = True, sweep_form: int = 0, kb_alpha: bool = False, overlap: bool = True,
-              kba: bool = False) -> int:
-    """lz_run_opts.flags: bit 0 = CGS2 without K4c, bit 1 = the Regular GPU sweep form (LZ_SWEEP_GPU),
-    bit 2 = recompute step with a KA pass per step instead of alpha accumulated inside KB,
-    bit 3 = sparse row shards without the interior/boundary overlap, bit 4 = recompute step as KA + KB
-    instead of the single KBA kernel."""
-    return ((0 if cgs_fused else 1) | (2 if sweep_form == _capi.LZ_SWEEP_GPU else 0) | (0 if kb_alpha else 4) |
-            (0 if overlap else 8) | (0 if kba else 16))
+              kba: bool = False, persistent: bool = True) -> int:
+    """lz_run_opts.flags (0 = the library defaults): bit 0 = CGS2 without K4c, bit 1 = the Regular GPU sweep
+    form (LZ_SWEEP_GPU), bit 2 = alpha accumulated inside KB + border kernel, bit 3 = sparse row shards without
+    the interior/boundary overlap, bit 4 = the single KBA kernel per step, bit 5 = small problems through the
+    kernel-per-phase loop instead of the persistent cooperative kernel."""
+    return ((0 if cgs_fused else 1) | (2 if sweep_form == _capi.LZ_SWEEP_GPU else 0) | (4 if kb_alpha else 0) |
+            (0 if overlap else 8) | (16 if kba else 0) | (0 if persistent else 32))
 
 
 def padded_ld(M: int) -> int:
@@ -402,7 +402,7 @@ class LanczosResult:
 
 def run_lanczos(op: DeviceOperator, v0, n: int, *, reorth="full", cgs_passes=1, ref_compat=True,
                 keep_basis=True, breakdown_tol=0.0, select_tol=0.0, V_dev=None,
-                profile=False, step_kernel="auto", cgs_fused=True, sweep_form=0, kb_alpha=False, kba=False) -> LanczosResult:
+                profile=False, step_kernel="auto", cgs_fused=True, sweep_form=0, kb_alpha=False, kba=False, persistent=True) -> LanczosResult:
     """Enqueue and run the n-step loop (lz_lanczos_run).  `v0` is a host array (copied through
     pinned memory) or a CUDA tensor of M doubles."""
     torch = _torch()
@@ -432,7 +432,7 @@ def run_lanczos(op: DeviceOperator, v0, n: int, *, reorth="full", cgs_passes=1, 
         beta = np.zeros(max(n - 1, 0))
         scale = np.ones(n)
         opts = RunOpts(mode, int(cgs_passes), 1 if ref_compat else 0, 1 if profile else 0,
-                       STEP_KERNEL[step_kernel], run_flags(cgs_fused, sweep_form, kb_alpha, True, kba), float(breakdown_tol), float(select_tol))
+                       STEP_KERNEL[step_kernel], run_flags(cgs_fused, sweep_form, kb_alpha, True, kba, persistent), float(breakdown_tol), float(select_tol))
         info = RunInfo()
         status = ctx.lib.lz_lanczos_run(
             ctx.handle, op.handle, C.c_void_p(v0_dev.data_ptr()), n, C.byref(opts),

@@ -96,7 +96,7 @@ class LanczosBase:
     # ---- the loop ---------------------------------------------------------------------------
     def _execute(self, n, seed, use_cuda, v0, *, reorth="full", cgs_passes=1, ref_compat=True,
                  fmt="auto", sigma=0, device=None, keep_basis=True, breakdown_tol=0.0,
-                 select_tol=0.0, profile=False, step_kernel="auto", cgs_fused=True, kb_alpha=False, kba=False, verbose=True,
+                 select_tol=0.0, profile=False, step_kernel="auto", cgs_fused=True, kb_alpha=False, kba=False, persistent=True, verbose=True,
                  devices=None):
         """Keyword-only extras (all default to the reference's behaviour):
         reorth 'full' | 'selective' | 'none'; cgs_passes 1 | 2; ref_compat (the v0-discarding
@@ -166,7 +166,8 @@ class LanczosBase:
                                           ref_compat=ref_compat, keep_basis=keep_basis,
                                           breakdown_tol=breakdown_tol, select_tol=select_tol,
                                           profile=profile, step_kernel=step_kernel, cgs_fused=cgs_fused,
-                                          sweep_form=self._GPU_SWEEP_FORM if use_cuda else 0, kb_alpha=kb_alpha, kba=kba)
+                                          sweep_form=self._GPU_SWEEP_FORM if use_cuda else 0, kb_alpha=kb_alpha, kba=kba,
+                                          persistent=persistent)
         self._H_eff = self._result.tridiagonal()
         self._V_host = None
         self._Y_dev = None

@@ -552,7 +552,7 @@ def test_recompute_step_matches_two_pass_and_oracle(lz, grid, bc, reorth):
     runs = {}
     for kern in ("two_pass", "recompute", "auto"):
         L = lz.Lanczos(op)
-        L.execute_Lanczos(n, seed=13, reorth=reorth, keep_basis=True, step_kernel=kern)
+        L.execute_Lanczos(n, seed=13, reorth=reorth, keep_basis=True, step_kernel=kern, persistent=False)
         runs[kern] = (np.diag(L.H_eff).copy(), np.diag(L.H_eff, 1).copy(), L.V.copy(), L.result.step_kernel)
     assert runs["two_pass"][3] == "two_pass" and runs["recompute"][3] == "recompute"
     assert runs["auto"][3] == "recompute"                 # the default for matrix-free operators
@@ -891,7 +891,7 @@ def test_graph_replay_is_bit_identical(lz, kind):
     runs = []
     for _ in range(4):
         V.fill_(float("nan"))
-        res = engine.run_lanczos(dop, v0, n, V_dev=V, **kw)
+        res = engine.run_lanczos(dop, v0, n, V_dev=V, persistent=False, **kw)
         runs.append((res.graph, res.alpha.copy(), res.beta.copy(), V[:, :M].clone(), res.launches))
     assert [r[0] for r in runs] == ["none", "captured", "replayed", "replayed"]
     for g, a, b, Vc, nl in runs[1:]:
@@ -901,9 +901,9 @@ def test_graph_replay_is_bit_identical(lz, kind):
     if kind != "stencil_selective":
         assert rel(runs[2][1], ref["alpha"]) < TOL_AB and rel(runs[2][2], ref["beta"]) < TOL_AB
     # another start-vector buffer: not the captured solve
-    res = engine.run_lanczos(dop, v0.clone(), n, V_dev=V, **kw)
+    res = engine.run_lanczos(dop, v0.clone(), n, V_dev=V, persistent=False, **kw)
     assert res.graph == "none" and np.array_equal(res.alpha, runs[0][1])
-    res = engine.run_lanczos(dop, v0, n - 1, V_dev=V, **kw)
+    res = engine.run_lanczos(dop, v0, n - 1, V_dev=V, persistent=False, **kw)
     assert res.graph == "none" and np.array_equal(res.alpha, runs[0][1][:n - 1])
 
 
@@ -926,10 +926,10 @@ def test_kba_step_matches_ka_kb(lz, grid, bc, pot):
     res = {}
     for flag in (True, False):
         L = lz.Lanczos(op)
-        L.execute_Lanczos(n, seed=5, reorth="none", kba=flag)
+        L.execute_Lanczos(n, seed=5, reorth="none", kba=flag, persistent=False)
         assert L.result.step_kernel == "recompute" and L.result.kba == flag
         res[flag] = (np.diag(L.H_eff).copy(), np.diag(L.H_eff, 1).copy(), L.V.copy(), L.result.launches)
-        L.execute_Lanczos(n, seed=5, reorth="none", kba=flag)
+        L.execute_Lanczos(n, seed=5, reorth="none", kba=flag, persistent=False)
         assert np.array_equal(np.diag(L.H_eff), res[flag][0])           # static item -> CTA deal: bit-reproducible
     assert res[True][3] < res[False][3]                                  # one launch per step instead of two
     k = 8
@@ -944,3 +944,75 @@ def test_kba_step_matches_ka_kb(lz, grid, bc, pot):
     S.execute_Lanczos(30, seed=5, reorth="selective", cgs_passes=2, select_tol=1e-15, kba=True)      # sweeps fire: alpha re-taken by KA2
     assert S.result.kba and S.result.reorth_count >= 25
     assert rel(np.diag(S.H_eff), full["alpha"]) < 1e-11 and rel(np.diag(S.H_eff, 1), full["beta"]) < 1e-11
+
+
+SMALL_CASES = [((200, 200), "dirichlet", False), ((200, 200), "periodic", False), ((1001,), "dirichlet", False),
+               ((7,), "periodic", False), ((6, 5), "periodic", True), ((70, 3), "dirichlet", False), ((33, 20, 7), "periodic", True),
+               ((64, 64, 64), "periodic", False), ((2, 2, 2), "periodic", False), ((130, 17, 4), "dirichlet", True)]
+
+
+@pytest.mark.parametrize("grid,bc,pot", SMALL_CASES)
+def test_persistent_small_problem_kernel(lz, grid, bc, pot):
+    """Launch-bound sizes run the whole solve in one persistent cooperative kernel (small.cu; step_kernel
+    "persistent", one launch): against the oracle in both sweep forms, with CGS2, without sweeps, from a clean
+    start, and against the kernel-per-phase loop."""
+    dim = len(grid)
+    M = int(np.prod(grid))
+    off = [-1.0, -0.7, -1.2][:dim]
+    diag = np.sin(np.arange(M) * 0.21) * 0.4 if pot else None
+    op = lz.StencilOperator(grid, 2.0 * dim + 0.5, off, bc=bc, diag=diag)
+    H = orc.laplacian_csr(grid, 2.0 * dim + 0.5, off, periodic=(bc == "periodic"), diag=diag)
+    n = min(24, M)
+    if n < 2:
+        pytest.skip("n >= 2")
+    tight = M >= 64                                        # tiny periodic grids exhaust their Krylov space at once
+    k = n if tight else 2
+    L = lz.Lanczos(op)
+    for use_cuda, sweep in ((True, "gpu"), (False, "cpu")):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            L.execute_Lanczos(n, seed=13, use_cuda=use_cuda)
+        assert L.result.step_kernel == "persistent" and L.result.launches == 1
+        ref = orc.lanczos(H, n, seed=13, sweep=sweep)
+        a, b = np.diag(L.H_eff), np.diag(L.H_eff, 1)
+        assert rel(a[:k], ref["alpha"][:k]) < TOL_AB and rel(b[:max(k - 1, 1)], ref["beta"][:max(k - 1, 1)]) < TOL_AB
+        if tight:
+            assert np.max(np.abs(L.V - ref["V"])) < 1e-11
+    if tight:
+        L.get_H_eigs()
+        np.testing.assert_allclose(L.H_eigvals, ref["theta"], rtol=TOL_RITZ, atol=1e-12)
+    # the kernel-per-phase loop gives the same tridiagonal matrix
+    P = lz.Lanczos(op)
+    P.execute_Lanczos(n, seed=13, persistent=False)
+    assert P.result.step_kernel != "persistent"
+    Q = lz.Lanczos(op)
+    Q.execute_Lanczos(n, seed=13)
+    assert rel(np.diag(Q.H_eff)[:k], np.diag(P.H_eff)[:k]) < TOL_AB
+    Q.execute_Lanczos(n, seed=13)
+    T1 = Q.H_eff.copy()
+    Q.execute_Lanczos(n, seed=13)
+    assert np.array_equal(T1, Q.H_eff)                     # bit-reproducible
+    if tight:
+        # CGS2, no sweeps, clean start
+        Q.execute_Lanczos(n, seed=13, cgs_passes=2)
+        P.execute_Lanczos(n, seed=13, cgs_passes=2, persistent=False)
+        assert Q.result.step_kernel == "persistent" and rel(np.diag(Q.H_eff), np.diag(P.H_eff)) < 1e-11
+        Vq = Q.V
+        assert np.max(np.abs(Vq.T @ Vq - np.eye(n))) < 1e-13
+        Q.execute_Lanczos(8, seed=13, reorth="none")
+        r0 = orc.lanczos(H, 8, seed=13, reorth=False)
+        assert Q.result.step_kernel == "persistent" and rel(np.diag(Q.H_eff)[:6], r0["alpha"][:6]) < 1e-11
+        v0 = orc.start_vector(M, seed=5)
+        Q.execute_Lanczos(10, v0=v0, ref_compat=False)
+        P.execute_Lanczos(10, v0=v0, ref_compat=False, persistent=False)
+        assert Q.result.step_kernel == "persistent" and rel(np.diag(Q.H_eff), np.diag(P.H_eff)) < 1e-11
+        assert np.max(np.abs(Q.V[:, 0] - v0 / np.linalg.norm(v0))) < 1e-15
+
+
+def test_persistent_kernel_reports_breakdown(lz):
+    op = lz.StencilOperator((4, 4, 4), 6.0, -1.0)         # 64 unknowns, few distinct eigenvalues
+    L = lz.Lanczos(op)
+    with pytest.raises(lz.LanczosBreakdown) as e:
+        L.execute_Lanczos(40, seed=1, breakdown_tol=1e-10)
+    assert 0 < e.value.steps_done < 40
