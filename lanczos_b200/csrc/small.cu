@@ -237,10 +237,13 @@ small_lanczos_kernel(const SmallArgs a) {
                 } else {
                     gs.sync();
                 }
-                for (int i = threadIdx.x; i < nrows; i += kThreads) {
+                // coefficient of row i = sum over the CTAs of its partials: a warp per row, lane l adds CTAs
+                // l, l + 32, ... in order, then the shuffle tree - a fixed order, and the loads are in flight together
+                for (int i = warp; i < nrows; i += kWarps) {
                     double s = 0.0;
-                    for (int cta = 0; cta < (int)gridDim.x; ++cta) s += ld_cg(a.dpart + (size_t)cta * a.ldp + i);
-                    scoef[i] = s;
+                    for (int cta = lane; cta < (int)gridDim.x; cta += 32) s += ld_cg(a.dpart + (size_t)cta * a.ldp + i);
+                    s = warp_sum(s);
+                    if (lane == 0) scoef[i] = s;
                 }
                 __syncthreads();
                 const double cself = ref_form ? 2.0 - self : 1.0;
@@ -248,7 +251,16 @@ small_lanczos_kernel(const SmallArgs a) {
                 for (int k = 0; k < kSmallEpt; ++k) {
                     if (on[k]) {
                         double t = cself * v[k];
-                        for (int i = 0; i < nrows; ++i) t = fma(-scoef[i], ld_cg(a.V + (int64_t)i * a.ldv + el[k]), t);
+                        const double* col = a.V + el[k];
+                        int i = 0;
+                        for (; i + 8 <= nrows; i += 8) {                 // eight rows in flight, subtracted in row order
+                            double x[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) x[u] = ld_cg(col + (int64_t)(i + u) * a.ldv);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) t = fma(-scoef[i + u], x[u], t);
+                        }
+                        for (; i < nrows; ++i) t = fma(-scoef[i], ld_cg(col + (int64_t)i * a.ldv), t);
                         v[k] = t;
                     }
                 }
