@@ -66,16 +66,25 @@ __device__ __forceinline__ double ld_cg(const double* p) {       // coherent at 
     return v;
 }
 
+// Grid barrier: arrivals are counted with one atomic per CTA; the last arriver publishes the epoch on a
+// SEPARATE cache line that everybody else polls - pollers and atomics never fight over a line (with all
+// CTAs spinning on the counter itself a barrier cost ~7 us on 148 SMs).
 struct GridSync {
-    unsigned int* ctr;
+    unsigned int* ctr;              // ctr[0]: arrivals (monotonic), ctr[32]: epoch released (128 B further on)
     unsigned int target = 0;
+    unsigned int epoch = 0;
     __device__ __forceinline__ void sync() {
         __syncthreads();
         if (threadIdx.x == 0) {
             target += gridDim.x;
+            epoch += 1;
             __threadfence();
-            atomicAdd(ctr, 1u);
-            while (ld_acq_u32(ctr) < target) {}
+            const unsigned int old = atomicAdd(ctr, 1u);
+            if (old == target - 1) {
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(ctr + 32), "r"(epoch) : "memory");
+            } else {
+                while (ld_acq_u32(ctr + 32) < epoch) {}
+            }
             __threadfence();
         }
         __syncthreads();
@@ -307,7 +316,7 @@ int launch_small_solve(lz_ctx* ctx, lz_op* op, const double* v0_dev, int32_t n, 
     const size_t nd = (size_t)n + 2;
     const int ldp = (int)((nd + 7) & ~(size_t)7);
     auto up = [](size_t b) { return (b + 511) & ~(size_t)511; };
-    const size_t need = up(nd * 8) * 2 + up((size_t)2 * grid * 8) + up((size_t)grid * ldp * 8) + up(64) * 2 +
+    const size_t need = up(nd * 8) * 2 + up((size_t)2 * grid * 8) + up((size_t)grid * ldp * 8) + up(512) + up(64) +
                         up((size_t)op->M * 8) + 4096;
     LZ_CHECK(arena_reserve(ctx, need));
     char* base = (char*)ctx->arena;
@@ -333,12 +342,12 @@ int launch_small_solve(lz_ctx* ctx, lz_op* op, const double* v0_dev, int32_t n, 
     a.red = (double*)take((size_t)2 * grid * 8);
     a.dpart = (double*)take((size_t)grid * ldp * 8);
     a.ldp = ldp;
-    a.bar = (unsigned int*)take(64);
+    a.bar = (unsigned int*)take(512);
     a.flags = (int*)take(64);
     a.tmp = (double*)take((size_t)op->M * 8);
     cudaStream_t q = ctx->stream;
     LZ_CUDA(cudaMemsetAsync(a.alpha, 0, (char*)a.red - (char*)a.alpha, q));
-    LZ_CUDA(cudaMemsetAsync(a.bar, 0, 64, q));
+    LZ_CUDA(cudaMemsetAsync(a.bar, 0, 512, q));
     const int h_flags[8] = {-1, 0, 0, 0, 0, 0, 0, 0};
     LZ_CUDA(cudaMemcpyAsync(a.flags, h_flags, sizeof(h_flags), cudaMemcpyHostToDevice, q));
     const size_t smem = nd * 8;
