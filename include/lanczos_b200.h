@@ -178,8 +178,9 @@ typedef struct lz_run_opts {
                               bit 2: recompute step with alpha accumulated inside KB + a border kernel instead
                               of a KA pass (measured slower); bit 3: sparse row shards
                               without the interior/boundary overlap on a second stream; bit 4: recompute step
-                              as the single KBA kernel (measured slower); bit 5: small problems through the
-                              kernel-per-phase loop instead of the persistent cooperative kernel             */
+                              as the single KBA kernel (measured slower); bit 5: small matrix-free problems
+                              (<= 148*256*8 unknowns, reorth full / none) in ONE persistent cooperative kernel
+                              (measured slower than the replayed CUDA graph: 30 vs 21.5 us/step at 200 x 200)  */
     double  breakdown_tol; /* stop when beta <= breakdown_tol * |alpha_0| (0: only 0/NaN) */
     double  select_tol;    /* selective: orthogonality level that triggers (0 -> sqrt(eps)) */
 } lz_run_opts;

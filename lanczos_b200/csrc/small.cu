@@ -299,7 +299,7 @@ small_lanczos_kernel(const SmallArgs a) {
 
 bool small_solve_supported(const lz_op* op, const lz_run_opts* opts, int32_t n, const double* V_dev, int64_t ldv) {
     static const bool off = []() { const char* e = getenv("LZ_SMALL"); return e && e[0] == '0'; }();
-    if (off || (opts->flags & (4 | 16 | 32)) || op->kind != LZ_OP_STENCIL || op->st.points != 7 || op->st.sharded) return false;
+    if (off || !(opts->flags & 32) || (opts->flags & (4 | 16)) || op->kind != LZ_OP_STENCIL || op->st.points != 7 || op->st.sharded) return false;
     if (!V_dev || ldv < op->M || opts->profile) return false;
     if (opts->reorth == LZ_REORTH_SELECTIVE || opts->step_kernel != 0) return false;
     const int64_t cap = (int64_t)op->ctx->sms * kThreads * kSmallEpt;

@@ -31,13 +31,13 @@ def _torch():
 
 
 def run_flags(cgs_fused: bool = True, sweep_form: int = 0, kb_alpha: bool = False, overlap: bool = True,
-              kba: bool = False, persistent: bool = True) -> int:
+              kba: bool = False, persistent: bool = False) -> int:
     """lz_run_opts.flags (0 = the library defaults): bit 0 = CGS2 without K4c, bit 1 = the Regular GPU sweep
     form (LZ_SWEEP_GPU), bit 2 = alpha accumulated inside KB + border kernel, bit 3 = sparse row shards without
-    the interior/boundary overlap, bit 4 = the single KBA kernel per step, bit 5 = small problems through the
-    kernel-per-phase loop instead of the persistent cooperative kernel."""
+    the interior/boundary overlap, bit 4 = the single KBA kernel per step, bit 5 = small problems in one persistent
+    cooperative kernel."""
     return ((0 if cgs_fused else 1) | (2 if sweep_form == _capi.LZ_SWEEP_GPU else 0) | (4 if kb_alpha else 0) |
-            (0 if overlap else 8) | (16 if kba else 0) | (0 if persistent else 32))
+            (0 if overlap else 8) | (16 if kba else 0) | (32 if persistent else 0))
 
 
 def padded_ld(M: int) -> int:
@@ -402,7 +402,7 @@ class LanczosResult:
 
 def run_lanczos(op: DeviceOperator, v0, n: int, *, reorth="full", cgs_passes=1, ref_compat=True,
                 keep_basis=True, breakdown_tol=0.0, select_tol=0.0, V_dev=None,
-                profile=False, step_kernel="auto", cgs_fused=True, sweep_form=0, kb_alpha=False, kba=False, persistent=True) -> LanczosResult:
+                profile=False, step_kernel="auto", cgs_fused=True, sweep_form=0, kb_alpha=False, kba=False, persistent=False) -> LanczosResult:
     """Enqueue and run the n-step loop (lz_lanczos_run).  `v0` is a host array (copied through
     pinned memory) or a CUDA tensor of M doubles."""
     torch = _torch()

@@ -96,7 +96,7 @@ class LanczosBase:
     # ---- the loop ---------------------------------------------------------------------------
     def _execute(self, n, seed, use_cuda, v0, *, reorth="full", cgs_passes=1, ref_compat=True,
                  fmt="auto", sigma=0, device=None, keep_basis=True, breakdown_tol=0.0,
-                 select_tol=0.0, profile=False, step_kernel="auto", cgs_fused=True, kb_alpha=False, kba=False, persistent=True, verbose=True,
+                 select_tol=0.0, profile=False, step_kernel="auto", cgs_fused=True, kb_alpha=False, kba=False, persistent=False, verbose=True,
                  devices=None):
         """Keyword-only extras (all default to the reference's behaviour):
         reorth 'full' | 'selective' | 'none'; cgs_passes 1 | 2; ref_compat (the v0-discarding

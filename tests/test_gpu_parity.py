@@ -953,8 +953,8 @@ SMALL_CASES = [((200, 200), "dirichlet", False), ((200, 200), "periodic", False)
 
 @pytest.mark.parametrize("grid,bc,pot", SMALL_CASES)
 def test_persistent_small_problem_kernel(lz, grid, bc, pot):
-    """Launch-bound sizes run the whole solve in one persistent cooperative kernel (small.cu; step_kernel
-    "persistent", one launch): against the oracle in both sweep forms, with CGS2, without sweeps, from a clean
+    """The whole solve of a small matrix-free problem in one persistent cooperative kernel (small.cu, opt-in
+    `persistent=True`; step_kernel "persistent", one launch): against the oracle in both sweep forms, with CGS2, without sweeps, from a clean
     start, and against the kernel-per-phase loop."""
     dim = len(grid)
     M = int(np.prod(grid))
@@ -972,7 +972,7 @@ def test_persistent_small_problem_kernel(lz, grid, bc, pot):
         import warnings
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            L.execute_Lanczos(n, seed=13, use_cuda=use_cuda)
+            L.execute_Lanczos(n, seed=13, use_cuda=use_cuda, persistent=True)
         assert L.result.step_kernel == "persistent" and L.result.launches == 1
         ref = orc.lanczos(H, n, seed=13, sweep=sweep)
         a, b = np.diag(L.H_eff), np.diag(L.H_eff, 1)
@@ -987,24 +987,24 @@ def test_persistent_small_problem_kernel(lz, grid, bc, pot):
     P.execute_Lanczos(n, seed=13, persistent=False)
     assert P.result.step_kernel != "persistent"
     Q = lz.Lanczos(op)
-    Q.execute_Lanczos(n, seed=13)
+    Q.execute_Lanczos(n, seed=13, persistent=True)
     assert rel(np.diag(Q.H_eff)[:k], np.diag(P.H_eff)[:k]) < TOL_AB
-    Q.execute_Lanczos(n, seed=13)
+    Q.execute_Lanczos(n, seed=13, persistent=True)
     T1 = Q.H_eff.copy()
-    Q.execute_Lanczos(n, seed=13)
+    Q.execute_Lanczos(n, seed=13, persistent=True)
     assert np.array_equal(T1, Q.H_eff)                     # bit-reproducible
     if tight:
         # CGS2, no sweeps, clean start
-        Q.execute_Lanczos(n, seed=13, cgs_passes=2)
+        Q.execute_Lanczos(n, seed=13, cgs_passes=2, persistent=True)
         P.execute_Lanczos(n, seed=13, cgs_passes=2, persistent=False)
         assert Q.result.step_kernel == "persistent" and rel(np.diag(Q.H_eff), np.diag(P.H_eff)) < 1e-11
         Vq = Q.V
         assert np.max(np.abs(Vq.T @ Vq - np.eye(n))) < 1e-13
-        Q.execute_Lanczos(8, seed=13, reorth="none")
+        Q.execute_Lanczos(8, seed=13, reorth="none", persistent=True)
         r0 = orc.lanczos(H, 8, seed=13, reorth=False)
         assert Q.result.step_kernel == "persistent" and rel(np.diag(Q.H_eff)[:6], r0["alpha"][:6]) < 1e-11
         v0 = orc.start_vector(M, seed=5)
-        Q.execute_Lanczos(10, v0=v0, ref_compat=False)
+        Q.execute_Lanczos(10, v0=v0, ref_compat=False, persistent=True)
         P.execute_Lanczos(10, v0=v0, ref_compat=False, persistent=False)
         assert Q.result.step_kernel == "persistent" and rel(np.diag(Q.H_eff), np.diag(P.H_eff)) < 1e-11
         assert np.max(np.abs(Q.V[:, 0] - v0 / np.linalg.norm(v0))) < 1e-15
@@ -1014,5 +1014,5 @@ def test_persistent_kernel_reports_breakdown(lz):
     op = lz.StencilOperator((4, 4, 4), 6.0, -1.0)         # 64 unknowns, few distinct eigenvalues
     L = lz.Lanczos(op)
     with pytest.raises(lz.LanczosBreakdown) as e:
-        L.execute_Lanczos(40, seed=1, breakdown_tol=1e-10)
+        L.execute_Lanczos(40, seed=1, breakdown_tol=1e-10, persistent=True)
     assert 0 < e.value.steps_done < 40
