@@ -63,7 +63,8 @@ struct lz_sell {
     int32_t* row_of = nullptr;     // device, nchunks*32: original row handled by (chunk, lane); -1 = padding row
     // row shards: spans (runs of `split_span` chunks = one sorting window) whose rows touch no ghost column
     // ("interior": can be applied before the ghost exchange has completed) and the others ("boundary")
-    int split_span = 0;            // 0: not classified
+    int split_span = 0;            // chunks per interior work item (0: not classified)
+    int bnd_span = 0;              // chunks per boundary work item
     int32_t* spans_int = nullptr;  // device, n_int span indices, ascending
     int32_t* spans_bnd = nullptr;  // device, n_bnd span indices, ascending
     int n_int = 0, n_bnd = 0;

@@ -132,6 +132,17 @@ spmv_sell_dot_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __res
     fin_tail(fin, partials, red);
 }
 
+// Chunks per CTA work item.  One sorting window (sigma / 32 chunks) when every CTA of the grid gets several of
+// them - a CTA that stays inside a window re-uses its gathers out of L1 - otherwise halved until each CTA has
+// >= 4 items: with 1.3 windows per CTA (50 M rows over 8 GPUs: 3057 windows, 2368 CTAs) a third of the SMs sat
+// idle while the others worked on their second window (K2 0.291 ms instead of 0.25 ms per shard).
+static int balanced_span(const lz_ctx* ctx, int64_t nchunks, int sigma) {
+    int span = std::max(kWarps, sigma / 32);
+    const int64_t want = (int64_t)ctx->sms * 16 * 4;
+    while (span >= 2 * kWarps && span % 2 == 0 && (nchunks + span - 1) / span < want) span /= 2;   // stays a divisor of the window
+    return span;
+}
+
 int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double* y,
                     double* partials, int* nparts, const int* flag_dev, const FinTail* fin) {
     (void)flag_dev;   // predicated applies exist only on the structured-grid fused path
@@ -161,9 +172,7 @@ int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double*
     const lz_sell& sl = op->sell;
     // spans: one sorting window each; shorter (down to one chunk per warp) when the operator is too
     // small to give every resident CTA a few spans
-    int span = std::max(kWarps, sl.sigma / 32);
-    while (span > kWarps && (sl.nchunks + span - 1) / span < (int64_t)ctx->sms * 16) span /= 2;
-    span = std::max(span, kWarps);
+    const int span = balanced_span(ctx, sl.nchunks, sl.sigma);
     const int64_t nspans = (sl.nchunks + span - 1) / span;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nspans, std::min<int64_t>((int64_t)ctx->sms * 16, kMaxPartials)));
     LZ_CUDA(launch_k(spmv_sell_dot_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, sl.chunk_off, sl.col,
@@ -212,18 +221,25 @@ int sell_classify_spans(lz_op* op) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(flags);
     if (e != cudaSuccess) { set_error("sell_classify_spans: %s", cudaGetErrorString(e)); return LZ_ERR_CUDA; }
-    // interior: whole spans (a CTA stays inside one sorting window: its gathers are reused out of L1);
-    // boundary: the same spans cut into pieces of kWarps chunks (one chunk per warp), so that the few boundary
-    // windows spread over many CTAs - one CTA per window would take ~90 us at 50 M rows, as long as a tenth
-    // of the whole interior part
+    // Windows are classified; the lists hold work items.  Interior windows: items of balanced_span() chunks
+    // (a whole window when the shard is large enough to keep every CTA busy with several).  Boundary windows:
+    // items of kWarps chunks (one chunk per warp), so that the few of them spread over many CTAs - one CTA per
+    // window would take ~90 us at 50 M rows, a tenth of the whole interior part.
     std::vector<int32_t> in, bd;
-    const int pieces = span / kWarps;
+    const int ipiece = balanced_span(ctx, sl.nchunks, sl.sigma);           // divides the window
+    const int bpiece = (span % kWarps == 0) ? kWarps : span;
+    const int ni = span / ipiece, nb = span / bpiece;
     for (int64_t s = 0; s < nspans; ++s) {
-        if (!h[(size_t)s]) { in.push_back((int32_t)s); continue; }
-        for (int k = 0; k < pieces; ++k)
-            if ((s * pieces + k) * (int64_t)kWarps < sl.nchunks) bd.push_back((int32_t)(s * pieces + k));
+        if (!h[(size_t)s]) {
+            for (int k = 0; k < ni; ++k)
+                if ((s * ni + k) * (int64_t)ipiece < sl.nchunks) in.push_back((int32_t)(s * ni + k));
+            continue;
+        }
+        for (int k = 0; k < nb; ++k)
+            if ((s * nb + k) * (int64_t)bpiece < sl.nchunks) bd.push_back((int32_t)(s * nb + k));
     }
-    sl.split_span = span;
+    sl.split_span = ipiece;
+    sl.bnd_span = bpiece;
     sl.n_int = (int)in.size();
     sl.n_bnd = (int)bd.size();
     LZ_CHECK(upload((void**)&sl.spans_int, in.data(), in.size() * 4, ctx->stream));
@@ -239,7 +255,7 @@ int launch_spmv_part(lz_op* op, int part, const double* x, const double* scale_d
     LZ_REQUIRE(spmv_split_supported(op) && (part == 1 || part == 2), "launch_spmv_part: operator is not split");
     const int32_t* list = part == 1 ? sl.spans_int : sl.spans_bnd;
     const int nlist = part == 1 ? sl.n_int : sl.n_bnd;
-    const int span = part == 1 ? sl.split_span : kWarps;         // boundary entries are pieces of kWarps chunks
+    const int span = part == 1 ? sl.split_span : sl.bnd_span;    // chunks per entry of the list
     // finer grid than the plain launch: CTAs leave the SMs often, so that the one-CTA exchange kernels of the
     // main stream find a slot while the interior part is running
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nlist, std::min<int64_t>((int64_t)ctx->sms * 16, kMaxPartials / 2)));

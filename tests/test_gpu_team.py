@@ -320,21 +320,22 @@ def test_dropin_one_process_per_gpu(lz, tmp_path):
     assert np.max(np.abs(z["ip"] - one.print_good_eigs(print_nr=2))) < 1e-9
 
 
-@pytest.mark.parametrize("world,reorth,passes", [(3, "selective", 2), (2, "none", 1), (4, "selective", 1)])
-def test_sparse_shards_overlap_interior_apply_with_exchange(lz, world, reorth, passes):
+@pytest.mark.parametrize("world,reorth,passes,sigma", [(3, "selective", 2, 64), (2, "none", 1, 64), (4, "selective", 1, 64),
+                                                        (2, "selective", 2, 384), (3, "none", 1, 96), (2, "none", 1, 2048)])
+def test_sparse_shards_overlap_interior_apply_with_exchange(lz, world, reorth, passes, sigma):
     """Row shards of a SELL operator: the spans whose rows touch no ghost column are applied while the ghost
     entries and the beta sum travel on a second stream (lz_run_info.overlap); against the same run without
-    the overlap, the single-GPU run and the oracle.  sigma = 64 so that these small shards have interior
-    spans at all; select_tol small enough that sweeps fire (the early interior apply is then redone)."""
+    the overlap, the single-GPU run and the oracle.  Small sigma so that these small shards have interior
+    spans at all (and windows that are not a power of two / not a multiple of 8 chunks); select_tol small enough that sweeps fire (the early interior apply is then redone)."""
     from lanczos_b200.team import LocalTeamLanczos
     H = orc.rgg_graph_laplacian(24000, mean_degree=13.0, seed=4)        # cell-ordered: ghosts only near block ends
     n = 30
     kw = dict(reorth=reorth, cgs_passes=passes, select_tol=1e-12 if reorth == "selective" else 0.0)
     one = lz.IrrLanczos(H)
-    one.execute_LanczosOld(n, seed=3, sigma=64, **kw)
+    one.execute_LanczosOld(n, seed=3, sigma=sigma, **kw)
     T = {}
     for ov in (True, False):
-        team = LocalTeamLanczos(H, world, fmt="sell", sigma=64)
+        team = LocalTeamLanczos(H, world, fmt="sell", sigma=sigma)
         team.execute_LanczosOld(n, seed=3, overlap=ov, **kw)
         assert team.result.overlap == ov
         if reorth == "selective":
