@@ -43,6 +43,10 @@ WORKLOADS = {
                grid=(1024, 1024, 1024), steps=60, reorth="full", cgs_passes=2, strong=True),
     "c1": dict(desc="2D 5-point Dirichlet Laplacian 200x200 fp64, full reorth",
                grid=(200, 200), steps=100, reorth="full", cgs_passes=1),
+    # the reference's own production size (3Ddeuteron.py:63-64): N = 160, n = 400, 27-point T, H = -T + V, built
+    # by the drop-in Hamiltonian class (potential traced from the NumPy function and evaluated on the device)
+    "deut": dict(desc="3Ddeuteron.py: 27-point H = -T + V on 160^3 (4.1 M unknowns), n = 400, full reorth (reference form)",
+                 grid=(160, 160, 160), steps=400, reorth="full", cgs_passes=1, deuteron=True),
 }
 METRIC = "lanczos_steps_per_sec"
 UNIT = "steps/s"
@@ -201,6 +205,20 @@ def cpu_reference_leg(workload: str, budget_s: float = 25.0):
     irregular = "grid" not in wl
     run, kind = _reference_runner(irregular)
     out = dict(unit=UNIT, cores=cores, kind=kind, numpy=np.__version__)
+    if wl.get("deuteron"):
+        full_M, n_full = int(np.prod(wl["grid"])), wl["steps"]
+        side, n = 40, 60
+        H, *_ = orc.deuteron_hamiltonian(side)
+        v0 = np.random.RandomState(99).uniform(-1, 1, side ** 3)
+        t = run(H, n, v0, True)
+        rate = n / t
+        # the sweep against all n rows every step costs ~ n * M per step: extrapolate in both
+        value = rate * (side ** 3) / full_M * n / n_full
+        out.update(value=value, reference_form_value=value,
+                   sample=f"7-point deuteron Hamiltonian at N={side}, n={n}, the reference's full sweep every step: {rate:.2f} steps/s "
+                          f"measured, x{side ** 3 / full_M:.2e} (linear in M) x{n / n_full:.2f} (the sweep reads all n rows) -> "
+                          f"{value:.4f} steps/s at N=160, n=400")
+        return out
     if "grid" in wl and len(wl["grid"]) == 3:
         full_M = int(np.prod(wl["grid"]))
         side, n = 96, 32
@@ -333,6 +351,26 @@ def parity_check(lz, world, rank, dist):
 # --------------------------------------------------------------------------- GPU arm
 def build_operator(lz, workload, world, rank):
     wl = WORKLOADS[workload]
+    if wl.get("deuteron"):
+        N, L = wl["grid"][0], 25
+
+        def potential(x, y, z):                              # 3Ddeuteron.py:51-61
+            r = np.sqrt(x**2 + y**2 + z**2)
+            eWell = 54.531
+            eWells = 65.4823128982115
+            eCores = 40.0*eWell
+            rCore = 1.0/4
+            rWell = 17.0/10
+            fPow = 4.0
+            return eCores*np.exp(-(r/rCore)**fPow) - eWells*np.exp(-(r/rWell)**fPow)
+        dx = float(L) / N
+        T_factor = 197.327**2/(2*469.4592) * 1/dx**2         # 3Ddeuteron.py:67-70
+        system = lz.Hamiltonian(N, L, potential, T_factor)
+        system.create_sparse_T()
+        system.create_sparse_V()
+        H = (-system.T_sparse + system.V_sparse)
+        H.sort_indices()
+        return H, tuple(wl["grid"])
     if "grid" in wl:
         grid = tuple(wl["grid"])
         dim = len(grid)
