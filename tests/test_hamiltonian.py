@@ -223,3 +223,28 @@ print("LOWEST", l_L[0])
     lowest = float(run.stdout.split("LOWEST")[1].split()[0])
     assert np.isfinite(lowest) and os.path.exists(tmp_path / "eigvals.npy")
     assert np.array_equal(np.sort(np.load(tmp_path / "eigvals.npy")), np.load(tmp_path / "eigvals.npy"))
+
+
+@pytest.mark.gpu
+def test_T_matrix_cache_round_trip(lz, golden, tmp_path, monkeypatch):
+    """Hamiltonian.py:48-69: `T_matrices/T_N=<N>_Laplace=<points>.npz` is honoured when it exists (the weights are read
+    back from it) and written on request in the reference's own format - a cache written here is what the
+    reference's create_sparse_T would load, and vice versa."""
+    import scipy.sparse as sp
+    monkeypatch.chdir(tmp_path)
+    N = 5
+    a = lz.Hamiltonian(N, 25, deuteron, 1.75)
+    a.create_sparse_T("27", save_cache=True)
+    path = tmp_path / "T_matrices" / "T_N=5_Laplace=27.npz"
+    assert path.exists()
+    T = sp.csr_matrix(sp.load_npz(str(path)))
+    T.sort_indices()
+    assert np.array_equal(T.indices, golden["T27_N5_indices"]) and np.array_equal(T.data, _csr(golden, "T27_N5", N).data)
+    b = lz.Hamiltonian(N, 25, deuteron, 99.0)              # another T_factor: the cached matrix wins, as in the reference
+    b.create_sparse_T("27")
+    assert b.T_sparse.weights == a.T_sparse.weights
+    # a cache written by the reference (here: the golden 7-point matrix) is read back as a 7-point stencil
+    sp.save_npz(str(tmp_path / "T_matrices" / "T_N=5_Laplace=7.npz"), _csr(golden, "T7_N5", N))
+    c = lz.Hamiltonian(N, 25, deuteron, 1.0)
+    c.create_sparse_T("7")
+    assert c.T_sparse.weights == (1.75 * -6.0, 1.75, 0.0, 0.0) and c.T_sparse.weights27 is None
