@@ -132,13 +132,13 @@ spmv_sell_dot_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __res
     fin_tail(fin, partials, red);
 }
 
-// Chunks per CTA work item.  One sorting window (sigma / 32 chunks) when every CTA of the grid gets several of
-// them - a CTA that stays inside a window re-uses its gathers out of L1 - otherwise halved until each CTA has
-// >= 4 items: with 1.3 windows per CTA (50 M rows over 8 GPUs: 3057 windows, 2368 CTAs) a third of the SMs sat
-// idle while the others worked on their second window (K2 0.291 ms instead of 0.25 ms per shard).
+// Chunks per CTA work item: one sorting window (a CTA that stays inside a window re-uses its gathers out of L1),
+// halved while the operator is too small to give every CTA of the grid one.  (Sizing the items so that every CTA
+// gets >= 4 was measured at 8 GPUs x 6.3 M rows: 0.448 instead of 0.436 ms/step - the block scheduler already
+// balances the 1.3 windows per CTA, and shorter items lose L1 reuse.)
 static int balanced_span(const lz_ctx* ctx, int64_t nchunks, int sigma) {
     int span = std::max(kWarps, sigma / 32);
-    const int64_t want = (int64_t)ctx->sms * 16 * 4;
+    const int64_t want = (int64_t)ctx->sms * 16;
     while (span >= 2 * kWarps && span % 2 == 0 && (nchunks + span - 1) / span < want) span /= 2;   // stays a divisor of the window
     return span;
 }
