@@ -635,7 +635,10 @@ def main():
         apply_bytes = 8.0 * N if recompute else 16.0 * N
     else:
         nnz_true, nnz_stored = solver.nnz_local() if world > 1 else solver._device_op.nnz()
-        apply_bytes = 12.0 * nnz_true + 16.0 * N
+        value_free = solver.value_free_local() if world > 1 else solver._device_op.value_free()
+        # 12 B per entry (value + column index) + x and y.  An unweighted graph Laplacian is applied
+        # from its column indices alone: 4 B per entry + x, y and the per-row diagonal coefficient
+        apply_bytes = (4.0 * nnz_true + 24.0 * N) if value_free else (12.0 * nnz_true + 16.0 * N)
     per_kernel = {}
     # K3 reads w, v_j, v_{j-1}, writes r; KB (recompute) reads v_j, v_{j-1}, writes r and applies H again
     update_bytes = 24.0 * N if recompute else 32.0 * N
@@ -776,6 +779,10 @@ def main():
                           "note": "halo / ghost / scalar exchange is a fraction of a percent of the link; it rides inside "
                                   "the producing kernels (no NCCL call, no copy-engine transfer on the data path)"}
     if not is_stencil:
+        line["config"]["value_free_spmv"] = bool(value_free)
+        line["config"]["spmv_bytes"] = ("4*nnz + 24*N: every off-diagonal entry of the operator is equal, so the kernel reads column "
+                                        "indices only (SURVEY 8d's 12*nnz + 16*N would be %.3f GB per launch)" % ((12.0 * nnz_true + 16.0 * N) / 1e9)
+                                        ) if value_free else "12*nnz + 16*N (SURVEY 8d)"
         line["config"]["nnz_per_gpu"] = int(nnz_true)
         line["config"]["sell_stored_over_true"] = float(nnz_stored) / max(1, nnz_true)
     if rank == 0:

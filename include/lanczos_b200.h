@@ -46,7 +46,9 @@ extern "C" {
 
 /* sparse storage used on the device */
 #define LZ_FMT_CSR   0          /* CSR, sub-warp per row */
-#define LZ_FMT_SELL  1          /* SELL-C-sigma, C = 32 */
+#define LZ_FMT_SELL  1          /* SELL-C-sigma, C = 32; operators whose off-diagonal entries are all equal (an
+                                   unweighted graph Laplacian) are applied without reading their values */
+#define LZ_FMT_SELL_VALUES 2    /* SELL-C-sigma, always with the stored values (comparison runs, tests) */
 
 /* re-orthogonalisation policy */
 #define LZ_REORTH_NONE       0
@@ -144,6 +146,9 @@ int lz_potential_eval(lz_ctx* ctx, const int64_t* shape, const double* x_host, c
 
 int lz_op_rows(const lz_op* op, int64_t* M);
 int lz_op_nnz(const lz_op* op, int64_t* nnz_true, int64_t* nnz_stored);
+/* *value_free = 1 when the operator is applied from its column indices alone (LZ_FMT_SELL, all off-diagonal
+ * entries equal): 4 instead of 12 bytes of HBM traffic per stored entry. */
+int lz_op_value_free(const lz_op* op, int32_t* value_free);
 
 /* y = H x on the device (`H*V[j]`, Lanczos.py:108,116).  Enqueues only. */
 int lz_op_apply(lz_op* op, const double* x_dev, double* y_dev);

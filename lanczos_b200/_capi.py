@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("LANCZOS_B200_LIB") or os.path.join(_HERE, "liblanczos
 
 LZ_OK, LZ_ERR_INVALID, LZ_ERR_CUDA, LZ_ERR_NOMEM, LZ_ERR_BREAKDOWN, LZ_ERR_UNSUPPORTED, LZ_ERR_PEER = range(7)
 LZ_BC_PERIODIC, LZ_BC_DIRICHLET = 0, 1
-LZ_FMT_CSR, LZ_FMT_SELL = 0, 1
+LZ_FMT_CSR, LZ_FMT_SELL, LZ_FMT_SELL_VALUES = 0, 1, 2
 LZ_REORTH_NONE, LZ_REORTH_FULL, LZ_REORTH_SELECTIVE = 0, 1, 2
 LZ_SWEEP_CPU, LZ_SWEEP_GPU = 0, 1
 
@@ -66,6 +66,7 @@ SIGNATURES = {
     "lz_potential_eval": (C.c_int, [_vp, _P(_i64), _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "lz_op_rows": (C.c_int, [_vp, _P(_i64)]),
     "lz_op_nnz": (C.c_int, [_vp, _P(_i64), _P(_i64)]),
+    "lz_op_value_free": (C.c_int, [_vp, _P(_i32)]),
     "lz_op_apply": (C.c_int, [_vp, _vp, _vp]),
     "lz_op_export_csr": (C.c_int, [_vp, _P(_i64), _vp, _vp, _vp]),
     "lz_op_destroy": (C.c_int, [_vp]),

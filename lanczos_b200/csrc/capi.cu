@@ -243,7 +243,7 @@ int lz_op_csr_create_dev(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, con
     LZ_REQUIRE(ctx && indptr_dev && out && (nnz == 0 || (indices_dev && data_dev)), "lz_op_csr_create_dev: null argument");
     LZ_REQUIRE(M >= 1 && M <= 0x7fffffff && ncols >= M && ncols <= 0x7fffffff, "lz_op_csr_create_dev: M / ncols out of range");
     LZ_REQUIRE(nnz >= 0 && nnz <= 0x7fffffff, "lz_op_csr_create_dev: nnz must fit int32 indptr");
-    LZ_REQUIRE(fmt == LZ_FMT_CSR || fmt == LZ_FMT_SELL, "lz_op_csr_create_dev: unknown format %d", fmt);
+    LZ_REQUIRE(fmt == LZ_FMT_CSR || fmt == LZ_FMT_SELL || fmt == LZ_FMT_SELL_VALUES, "lz_op_csr_create_dev: unknown format %d", fmt);
     LZ_CUDA(cudaSetDevice(ctx->device));
     lz_op* op = new lz_op();
     op->ctx = ctx;
@@ -251,6 +251,7 @@ int lz_op_csr_create_dev(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, con
     if (st != LZ_OK) { lz_op_destroy(op); return st; }
     op->ncols = ncols;
     st = sell_classify_spans(op);
+    if (st == LZ_OK && fmt == LZ_FMT_SELL) st = sell_detect_uniform(op);
     if (st != LZ_OK) { lz_op_destroy(op); return st; }
     *out = op;
     return LZ_OK;
@@ -261,7 +262,7 @@ static int csr_create_impl(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, c
     LZ_REQUIRE(ctx && indptr && out && (nnz == 0 || (indices && data)), "lz_op_csr_create: null argument");
     LZ_REQUIRE(M >= 1 && M <= 0x7fffffff && ncols <= 0x7fffffff, "lz_op_csr_create: M out of range");
     LZ_REQUIRE(nnz >= 0 && nnz <= 0x7fffffff, "lz_op_csr_create: nnz must fit int32 indptr");
-    LZ_REQUIRE(fmt == LZ_FMT_CSR || fmt == LZ_FMT_SELL, "lz_op_csr_create: unknown format %d", fmt);
+    LZ_REQUIRE(fmt == LZ_FMT_CSR || fmt == LZ_FMT_SELL || fmt == LZ_FMT_SELL_VALUES, "lz_op_csr_create: unknown format %d", fmt);
     LZ_REQUIRE(indptr[0] == 0 && indptr[M] == nnz, "lz_op_csr_create: indptr does not span [0, nnz]");
     for (int64_t i = 0; i < M; ++i)
         LZ_REQUIRE(indptr[i + 1] >= indptr[i], "lz_op_csr_create: indptr not monotone at row %lld", (long long)i);
@@ -276,6 +277,7 @@ static int csr_create_impl(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, c
     if (st != LZ_OK) { lz_op_destroy(op); return st; }
     op->ncols = ncols;
     st = sell_classify_spans(op);              // row shards: interior / boundary spans for the overlapped apply
+    if (st == LZ_OK && fmt == LZ_FMT_SELL) st = sell_detect_uniform(op);   // unweighted graph Laplacians: value-free kernel
     if (st != LZ_OK) { lz_op_destroy(op); return st; }
     *out = op;
     return LZ_OK;
@@ -304,6 +306,12 @@ int lz_op_nnz(const lz_op* op, int64_t* nnz_true, int64_t* nnz_stored) {
     return LZ_OK;
 }
 
+int lz_op_value_free(const lz_op* op, int32_t* value_free) {
+    LZ_REQUIRE(op && value_free, "lz_op_value_free: null argument");
+    *value_free = (op->kind == LZ_OP_SELL && op->sell.uniform) ? 1 : 0;
+    return LZ_OK;
+}
+
 int lz_op_apply(lz_op* op, const double* x_dev, double* y_dev) {
     LZ_REQUIRE(op && x_dev && y_dev, "lz_op_apply: null argument");
     LZ_REQUIRE(x_dev != y_dev, "lz_op_apply: in-place apply is not supported");
@@ -323,6 +331,7 @@ int lz_op_destroy(lz_op* op) {
     if (op->sell.col) cudaFree(op->sell.col);
     if (op->sell.val) cudaFree(op->sell.val);
     if (op->sell.row_of) cudaFree(op->sell.row_of);
+    if (op->sell.deff) cudaFree(op->sell.deff);
     if (op->sell.spans_int) cudaFree(op->sell.spans_int);
     if (op->sell.spans_bnd) cudaFree(op->sell.spans_bnd);
     delete op;

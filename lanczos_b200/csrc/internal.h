@@ -61,6 +61,11 @@ struct lz_sell {
     int32_t* col = nullptr;        // device, nnz_stored, column-major inside a chunk
     double* val = nullptr;         // device, nnz_stored
     int32_t* row_of = nullptr;     // device, nchunks*32: original row handled by (chunk, lane); -1 = padding row
+    // value-free form (every off-diagonal entry equals uni_a, e.g. an unweighted graph Laplacian): the kernel
+    // reads no values, deff[row] corrects the slots with col == row (diagonal entry, padding)
+    int uniform = 0;
+    double uni_a = 0.0;
+    double* deff = nullptr;        // device, M
     // row shards: spans (runs of `split_span` chunks = one sorting window) whose rows touch no ghost column
     // ("interior": can be applied before the ghost exchange has completed) and the others ("boundary")
     int split_span = 0;            // chunks per interior work item (0: not classified)
@@ -108,6 +113,7 @@ int launch_apply_dot(lz_op* op, const double* x, const double* scale_dev, double
 // tail sums both ranges).  `stream`: where to launch (the context's second stream for the interior part).
 bool spmv_split_supported(const lz_op* op);
 int sell_classify_spans(lz_op* op);
+int sell_detect_uniform(lz_op* op);
 int launch_spmv_part(lz_op* op, int part, const double* x, const double* scale_dev, double* y, double* partials,
                      int* nparts, const int* flag_dev, const FinTail* fin, cudaStream_t stream);
 

@@ -12,6 +12,7 @@
 //     coalesced 128 B / 256 B transaction and the x gathers of a warp hit nearby sectors
 //     when the vertex numbering has locality.
 // Both are HBM/L2-gather bound: 12 B per stored entry + 16 B per row.
+#include <stdlib.h>
 #include <algorithm>
 #include <numeric>
 #include <vector>
@@ -74,13 +75,19 @@ __device__ __forceinline__ int32_t ld_stream_i32(const int32_t* p) {
 // left to the gathers.  Measured on the 50M-vertex config-4 graph (tools/tune_sell.py, B200):
 // 3.27 ms with a plain grid-stride over chunks and sigma = 1024, 1.93 ms with spans, sigma = 2048;
 // L2 evict-first hints on the streams made it slower and are not used.
+// UNI: every off-diagonal entry of the operator has the same value `uni_a` (an unweighted graph Laplacian,
+// BASELINE configs 2 and 4: L = D - A).  The values are then not read at all - 4 instead of 12 bytes per
+// stored entry: y_i = a * sum_slots x[col] + deff_i * x_i, where deff_i collects what the slots with col == i
+// (the diagonal entry and the padding, which gathers x_i itself) should have contributed beyond a * x_i.
+template <bool UNI>
 __global__ void __launch_bounds__(kThreads)
 spmv_sell_dot_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __restrict__ col,
                      const double* __restrict__ val, const int32_t* __restrict__ row_of,
                      const double* __restrict__ x, const double* __restrict__ scale,
                      double* __restrict__ y, int64_t nchunks, double* __restrict__ partials,
                      const double* __restrict__ xg, int32_t M, int span, const FinTail fin,
-                     const int32_t* __restrict__ span_list, int nlist, const int* __restrict__ flag) {
+                     const int32_t* __restrict__ span_list, int nlist, const int* __restrict__ flag,
+                     const double* __restrict__ deff, double uni_a) {
     pdl_prologue();
     if (flag && *flag == 0) return;
     __shared__ double red[kWarps];
@@ -111,19 +118,24 @@ spmv_sell_dot_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __res
                 for (int u = 0; u < U; ++u) {
                     const bool on = k + u < width;
                     cc[u] = on ? ld_stream_i32(pc + (k + u) * 32) : 0;
-                    vv[u] = on ? ld_stream1(pv + (k + u) * 32) : 0.0;
+                    if (!UNI) vv[u] = on ? ld_stream1(pv + (k + u) * 32) : 0.0;
                 }
                 double xx[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) xx[u] = (k + u < width) ? __ldg((cc[u] < M ? x : xgs) + cc[u]) : 0.0;
 #pragma unroll
-                for (int u = 0; u < U; ++u) sum = fma(vv[u], xx[u], sum);
+                for (int u = 0; u < U; ++u) {
+                    if (UNI) sum += xx[u];
+                    else sum = fma(vv[u], xx[u], sum);
+                }
             }
             const int32_t row = __ldg(row_of + c * 32 + lane);
             if (row >= 0) {
+                const double xr = __ldg(x + row);
+                if (UNI) sum = fma(uni_a, sum, __ldg(deff + row) * xr);
                 const double yi = s * sum;
                 y[row] = yi;
-                acc = fma(yi, s * __ldg(x + row), acc);
+                acc = fma(yi, s * xr, acc);
             }
         }
     }
@@ -175,14 +187,91 @@ int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double*
     const int span = balanced_span(ctx, sl.nchunks, sl.sigma);
     const int64_t nspans = (sl.nchunks + span - 1) / span;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nspans, std::min<int64_t>((int64_t)ctx->sms * 16, kMaxPartials)));
-    LZ_CUDA(launch_k(spmv_sell_dot_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, sl.chunk_off, sl.col,
-                     sl.val, sl.row_of, x, scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, span, ft,
-                     (const int32_t*)nullptr, 0, flag_dev));
+    if (sl.uniform)
+        LZ_CUDA(launch_k(spmv_sell_dot_kernel<true>, dim3(grid), dim3(kThreads), 0, ctx->stream, sl.chunk_off, sl.col,
+                         sl.val, sl.row_of, x, scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, span, ft,
+                         (const int32_t*)nullptr, 0, flag_dev, (const double*)sl.deff, sl.uni_a));
+    else
+        LZ_CUDA(launch_k(spmv_sell_dot_kernel<false>, dim3(grid), dim3(kThreads), 0, ctx->stream, sl.chunk_off, sl.col,
+                         sl.val, sl.row_of, x, scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, span, ft,
+                         (const int32_t*)nullptr, 0, flag_dev, (const double*)nullptr, 0.0));
     if (nparts) *nparts = grid;
     return LZ_OK;
 }
 
 static int upload(void** dev, const void* host, size_t bytes, cudaStream_t s);
+
+// ---- value-free form for operators whose off-diagonal entries are all equal ----------------------------
+// One warp per chunk: deff[row] = sum over the slots with col == row of (val - a); any other slot whose value
+// is not exactly `a` clears the flag.
+__global__ void __launch_bounds__(kThreads)
+sell_uniform_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __restrict__ col,
+                    const double* __restrict__ val, const int32_t* __restrict__ row_of, int64_t nchunks, double a,
+                    double* __restrict__ deff, int* __restrict__ mismatch) {
+    const int64_t c = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    if (c >= nchunks) return;
+    const int lane = threadIdx.x & 31;
+    const int32_t row = row_of[c * 32 + lane];
+    const int64_t o0 = chunk_off[c];
+    const int width = (int)((chunk_off[c + 1] - o0) >> 5);
+    double d = 0.0;
+    int bad = 0;
+    for (int k = 0; k < width; ++k) {
+        const int64_t at = o0 + (int64_t)k * 32 + lane;
+        const double v = val[at];
+        if (row >= 0 && col[at] == row) d += v - a;
+        else if (row >= 0 && v != a) bad = 1;
+    }
+    if (row >= 0) deff[row] = d;
+    if (bad) *mismatch = 1;
+}
+
+// Decide whether the operator qualifies (LZ_SELL_UNIFORM=0 turns the form off) and build deff.
+int sell_detect_uniform(lz_op* op) {
+    static const bool off = []() { const char* e = getenv("LZ_SELL_UNIFORM"); return e && e[0] == '0'; }();
+    lz_ctx* ctx = op->ctx;
+    lz_sell& sl = op->sell;
+    if (off || op->kind != LZ_OP_SELL || sl.nchunks == 0 || sl.nnz_stored == 0) return LZ_OK;
+    // candidate value: the first off-diagonal entry among the first chunks
+    const int64_t probe_chunks = std::min<int64_t>(sl.nchunks, 4);
+    std::vector<int64_t> off4((size_t)probe_chunks + 1);
+    LZ_CUDA(cudaMemcpyAsync(off4.data(), sl.chunk_off, off4.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int64_t cnt = off4[(size_t)probe_chunks];
+    if (cnt <= 0) return LZ_OK;
+    std::vector<int32_t> hc((size_t)cnt), hr((size_t)probe_chunks * 32);
+    std::vector<double> hv((size_t)cnt);
+    LZ_CUDA(cudaMemcpyAsync(hc.data(), sl.col, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaMemcpyAsync(hv.data(), sl.val, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaMemcpyAsync(hr.data(), sl.row_of, hr.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    bool found = false;
+    double a = 0.0;
+    for (int64_t c = 0; c < probe_chunks && !found; ++c)
+        for (int64_t at = off4[(size_t)c]; at < off4[(size_t)c + 1] && !found; ++at) {
+            const int32_t row = hr[(size_t)(c * 32 + (at - off4[(size_t)c]) % 32)];
+            if (row >= 0 && hc[(size_t)at] != row) { a = hv[(size_t)at]; found = true; }
+        }
+    if (!found || a == 0.0) return LZ_OK;
+    double* deff = nullptr;
+    LZ_CUDA(cudaMalloc((void**)&deff, (size_t)op->M * 8));
+    int* flag = reinterpret_cast<int*>(ctx->scratch + 24);
+    LZ_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    const unsigned cgrid = (unsigned)((sl.nchunks + kWarps - 1) / kWarps);
+    sell_uniform_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(sl.chunk_off, sl.col, sl.val, sl.row_of, sl.nchunks, a, deff, flag);
+    int bad = 1;
+    cudaError_t e = cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess || bad) {
+        cudaFree(deff);
+        if (e != cudaSuccess) { set_error("sell_detect_uniform: %s", cudaGetErrorString(e)); return LZ_ERR_CUDA; }
+        return LZ_OK;
+    }
+    sl.deff = deff;
+    sl.uni_a = a;
+    sl.uniform = 1;
+    return LZ_OK;
+}
 
 // ---- row shards: interior / boundary spans ---------------------------------------------------------
 // A span (one sorting window of sigma rows = sigma/32 chunks) is "boundary" when any entry stored in it
@@ -268,9 +357,14 @@ int launch_spmv_part(lz_op* op, int part, const double* x, const double* scale_d
         if (ft.op.kind != FIN_NONE) { ft.op.extra = partials; ft.op.nextra = sl.np_int; }
     }
     // an empty list still launches one CTA: its partial is 0 and its tail runs the bookkeeping / the exchange
-    LZ_CUDA(launch_k(spmv_sell_dot_kernel, dim3(grid), dim3(kThreads), 0, stream, sl.chunk_off, sl.col, sl.val,
-                     sl.row_of, x, scale_dev, y, sl.nchunks, pout, op->xghost, (int32_t)op->M, span, ft,
-                     list, nlist, flag_dev));
+    if (sl.uniform)
+        LZ_CUDA(launch_k(spmv_sell_dot_kernel<true>, dim3(grid), dim3(kThreads), 0, stream, sl.chunk_off, sl.col, sl.val,
+                         sl.row_of, x, scale_dev, y, sl.nchunks, pout, op->xghost, (int32_t)op->M, span, ft,
+                         list, nlist, flag_dev, (const double*)sl.deff, sl.uni_a));
+    else
+        LZ_CUDA(launch_k(spmv_sell_dot_kernel<false>, dim3(grid), dim3(kThreads), 0, stream, sl.chunk_off, sl.col, sl.val,
+                         sl.row_of, x, scale_dev, y, sl.nchunks, pout, op->xghost, (int32_t)op->M, span, ft,
+                         list, nlist, flag_dev, (const double*)nullptr, 0.0));
     if (nparts) *nparts = (part == 1) ? grid : sl.np_int + grid;
     return LZ_OK;
 }

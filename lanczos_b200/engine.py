@@ -12,13 +12,15 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _capi
-from ._capi import (LZ_BC_DIRICHLET, LZ_BC_PERIODIC, LZ_FMT_CSR, LZ_FMT_SELL, LZ_REORTH_FULL,
+from ._capi import (LZ_BC_DIRICHLET, LZ_BC_PERIODIC, LZ_FMT_CSR, LZ_FMT_SELL, LZ_FMT_SELL_VALUES, LZ_REORTH_FULL,
                     LZ_REORTH_NONE, LZ_REORTH_SELECTIVE, LanczosBreakdown, RunInfo, RunOpts)
 
 _REORTH = {"none": LZ_REORTH_NONE, "full": LZ_REORTH_FULL, "selective": LZ_REORTH_SELECTIVE,
            None: LZ_REORTH_NONE, False: LZ_REORTH_NONE, True: LZ_REORTH_FULL}
 
 
+# "sell": SELL-32-sigma, value-free when every off-diagonal entry is equal; "sell_values": always with the values
+FORMATS = {"csr": LZ_FMT_CSR, "sell": LZ_FMT_SELL, "sell_values": LZ_FMT_SELL_VALUES}
 STEP_KERNEL = {"auto": 0, "two_pass": 1, "fused": 2, "recompute": 3, 0: 0, 1: 1, 2: 2, 3: 3}
 STEP_KERNEL_NAME = {1: "two_pass", 2: "fused", 3: "recompute", 4: "persistent"}
 
@@ -200,7 +202,7 @@ class DeviceOperator:
         data = np.ascontiguousarray(A.data, dtype=np.float64)
         if fmt == "auto":
             fmt = "sell"
-        f = {"csr": LZ_FMT_CSR, "sell": LZ_FMT_SELL}[fmt]
+        f = FORMATS[fmt]
         h = C.c_void_p()
         _capi.check(ctx.lib.lz_op_csr_create(
             ctx.handle, A.shape[0], A.nnz, indptr.ctypes.data_as(C.c_void_p),
@@ -223,7 +225,7 @@ class DeviceOperator:
                 raise ValueError("from_device_csr: the arrays live on another device than the context")
         if fmt == "auto":
             fmt = "sell"
-        f = {"csr": LZ_FMT_CSR, "sell": LZ_FMT_SELL}[fmt]
+        f = FORMATS[fmt]
         h = C.c_void_p()
         torch.cuda.current_stream(ctx.device).synchronize()      # the arrays were produced on torch's stream
         _capi.check(ctx.lib.lz_op_csr_create_dev(
@@ -236,6 +238,12 @@ class DeviceOperator:
         t, s = C.c_int64(), C.c_int64()
         _capi.check(self.ctx.lib.lz_op_nnz(self.handle, C.byref(t), C.byref(s)))
         return t.value, s.value
+
+    def value_free(self) -> bool:
+        """True when the operator is applied from its column indices alone (all off-diagonal entries equal)."""
+        v = C.c_int32()
+        _capi.check(self.ctx.lib.lz_op_value_free(self.handle, C.byref(v)))
+        return bool(v.value)
 
     def apply(self, x, y=None):
         """y = H x for CUDA tensors (enqueued on the context's stream)."""

@@ -353,7 +353,7 @@ class _TeamBase:
         torch = engine._torch()
         H, plan = self.H, self.plan
         if self.sparse:
-            f = {"csr": _capi.LZ_FMT_CSR, "sell": _capi.LZ_FMT_SELL, "auto": _capi.LZ_FMT_SELL}[self.fmt]
+            f = dict(engine.FORMATS, auto=_capi.LZ_FMT_SELL)[self.fmt]
             for s in self.shards:
                 s.op_handle = plan.make_op(self.lib, s.ctx, s.rank, f, self.sigma)
             return
@@ -554,6 +554,11 @@ class _TeamBase:
             xhx, hxhx, ys = self.apply_dots(xs, ys)
             out[i] = xhx ** 2 / hxhx if hxhx > 0.0 else 0.0
         return out
+
+    def value_free_local(self) -> bool:
+        v = C.c_int32()
+        _capi.check(self.lib.lz_op_value_free(self.shards[0].op_handle, C.byref(v)))
+        return bool(v.value)
 
     def nnz_local(self):
         """(true, stored) entries of the first local shard of a sparse operator."""

@@ -1016,3 +1016,41 @@ def test_persistent_kernel_reports_breakdown(lz):
     with pytest.raises(lz.LanczosBreakdown) as e:
         L.execute_Lanczos(40, seed=1, breakdown_tol=1e-10, persistent=True)
     assert 0 < e.value.steps_done < 40
+
+
+def test_value_free_sell_for_unweighted_graph_laplacians(lz):
+    """SELL operators whose off-diagonal entries are all equal (L = D - A of an unweighted graph: BASELINE configs 2
+    and 4) are applied from their column indices alone (4 instead of 12 bytes per stored entry); weighted operators,
+    and fmt="sell_values", keep the general kernel.  Same y, same exported matrix, same alpha/beta."""
+    import torch
+    from lanczos_b200 import engine
+    ctx = engine.Context.default()
+    G = orc.delaunay_graph_laplacian(7003, seed=2)                      # ragged rows, odd row count, padding in every chunk
+    x = np.random.RandomState(0).uniform(-1, 1, G.shape[0])
+    ops = {f: engine.DeviceOperator.from_scipy(ctx, G, fmt=f) for f in ("sell", "sell_values", "csr")}
+    assert ops["sell"].value_free() and not ops["sell_values"].value_free() and not ops["csr"].value_free()
+    ref = G * x
+    for f, op in ops.items():
+        y = op.apply_host(x)
+        assert np.max(np.abs(y - ref)) <= 4e-15 * np.max(np.abs(ref)), f
+        assert (op.export_csr() != G).nnz == 0, f
+    # -2 on every edge (a scaled Laplacian) is uniform too; a weighted one is not; a diagonal-free adjacency matrix is
+    assert engine.DeviceOperator.from_scipy(ctx, sp.csr_matrix(2.0 * G), fmt="sell").value_free()
+    W = sp.csr_matrix(G.copy())
+    W.data = W.data * (1.0 + 0.01 * np.arange(W.nnz))
+    wop = engine.DeviceOperator.from_scipy(ctx, W, fmt="sell")
+    assert not wop.value_free()
+    assert np.max(np.abs(wop.apply_host(x) - W * x)) <= 4e-15 * np.max(np.abs(W * x))
+    A = sp.csr_matrix(sp.diags(G.diagonal()) - G)                       # adjacency: no stored diagonal, entries +1
+    A.eliminate_zeros()
+    aop = engine.DeviceOperator.from_scipy(ctx, A, fmt="sell")
+    assert aop.value_free() and np.max(np.abs(aop.apply_host(x) - A * x)) <= 4e-15 * np.max(np.abs(A * x))
+    # device-resident CSR arrays (the config-4 path) and the loop
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.torch_device).to(dt)     # noqa: E731
+    dop = engine.DeviceOperator.from_device_csr(ctx, t(G.indptr, torch.int32), t(G.indices, torch.int32), t(G.data, torch.float64))
+    assert dop.value_free() and np.max(np.abs(dop.apply_host(x) - ref)) <= 4e-15 * np.max(np.abs(ref))
+    refl = orc.lanczos(G, 30, seed=5)
+    for f in ("sell", "sell_values"):
+        L = lz.IrrLanczos(G)
+        L.execute_LanczosOld(30, seed=5, fmt=f)
+        assert rel(np.diag(L.H_eff), refl["alpha"]) < TOL_AB and rel(np.diag(L.H_eff, 1), refl["beta"]) < TOL_AB
