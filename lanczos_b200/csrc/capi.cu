@@ -24,7 +24,7 @@ const char* get_error() { return g_err; }
 // not safe with this library's loads: a dependent grid's CTAs - and with them the L1 invalidation that normally
 // separates two kernels - may start while the primary is still writing, and data the primary produced is then
 // read through the non-coherent path (ld.global.nc / __ldg), which griddepcontrol.wait does not cover.  Seen as
-// wrong alpha from step 2-3 on in row-sharded two-pass runs (tools/dbg1.py), never with the attribute off.
+// wrong alpha from step 2-3 on in row-sharded two-pass runs (tools/pdl_race_check.py with LZ_PDL=1), never with the attribute off.
 }  // namespace lz
 void lz_ctx_drop_graphs(lz_ctx* c);     // lanczos.cu
 namespace lz {

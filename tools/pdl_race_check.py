@@ -1,3 +1,6 @@
+"""Development aid: row-sharded two-pass / recompute runs on one GPU, repeated, against the single-shard result.
+With LZ_PDL=1 (programmatic dependent launch on) the two-pass runs go wrong from step 2-3 on, nondeterministically;
+with the attribute off (the default) every line ends in `first bad []`.  See pdl_enabled() in csrc/capi.cu."""
 import sys, numpy as np
 sys.path.insert(0, '/root/repo')
 import lanczos_b200 as lz
