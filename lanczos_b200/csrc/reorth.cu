@@ -646,10 +646,137 @@ ritz_lift_gemm_kernel(const double* __restrict__ V, int64_t ldv, int n, int64_t 
     }
 }
 
+// K5 on the fp64 tensor cores: the same tiling and cp.async ring as ritz_lift_gemm_kernel, the inner product as
+// mma.sync.m8n8k4.f64 - D (8 Ritz vectors x 8 columns) += A (8 x 4: S^T) . B (4 x 8: basis rows x columns).  A warp
+// owns 32 Ritz vectors x 64 columns = 4 x 8 accumulator tiles; per pipeline step (four basis rows = one k-step) it
+// loads 4 A and 8 B fragments (one double per lane each, from rows padded by 4 doubles so that the 16 lanes of a
+// half-warp hit 16 different 8-byte banks) and issues 32 DMMAs: 44 instructions where the FMA form needs 152.
+constexpr int kMmaSsLd = kGemmOut + 4;        // padded row strides (doubles)
+constexpr int kMmaRingLd = kGemmTile + 4;
+
+__device__ __forceinline__ void dmma8x8x4(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+ritz_lift_mma_kernel(const double* __restrict__ V, int64_t ldv, int n, int64_t M, const double* __restrict__ S,
+                     int lds, int ncols, double* Y, int64_t ldy, int accumulate, int64_t ntiles) {
+    extern __shared__ __align__(128) double gsm[];
+    double* ss = gsm;                                            // [nr4][kMmaSsLd], zero beyond n rows / ncols columns
+    double* ring = gsm + (size_t)kGemmRowsSmem * kMmaSsLd;       // [kGemmRing][kMmaRingLd]
+    const int nr4 = (n + kGemmRowsPerStep - 1) / kGemmRowsPerStep * kGemmRowsPerStep;
+    for (int q = threadIdx.x; q < nr4 * kGemmOut; q += kThreads) {
+        const int r = q / kGemmOut, c = q % kGemmOut;
+        ss[r * kMmaSsLd + c] = (r < n && c < ncols) ? S[(int64_t)c * lds + r] : 0.0;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = 32 * (warp & 1), m0 = 64 * (warp >> 1);
+    const int gid = lane >> 2, tig = lane & 3;
+    const int steps_per_tile = nr4 / kGemmRowsPerStep;
+    const int my_tiles = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const int64_t nsteps = (int64_t)my_tiles * steps_per_tile;
+    // producer: thread t copies 16-byte chunk (t & 127) of rows (t >> 7) and (t >> 7) + 2 of every step
+    const int chunk = threadIdx.x & 127, rsub = threadIdx.x >> 7;
+    int64_t pstep = 0;
+    int pst = 0;
+    int64_t ptile = blockIdx.x;
+    auto issue_step = [&]() {
+        if (pstep < nsteps) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int rr = rsub + 2 * u;
+                const int r = pst * kGemmRowsPerStep + rr;
+                const int64_t col = ptile * kGemmTile + 2 * chunk;
+                const int64_t left = M - col;
+                const int bytes = (r < n) ? (left >= 2 ? 16 : (left == 1 ? 8 : 0)) : 0;
+                const double* src = bytes ? V + (int64_t)r * ldv + col : V;
+                cp_async16_zfill(ring + (size_t)((pstep & (kGemmDepth - 1)) * kGemmRowsPerStep + rr) * kMmaRingLd + 2 * chunk, src, bytes);
+            }
+        }
+        ++pstep;
+        if (++pst == steps_per_tile) { pst = 0; ptile += gridDim.x; }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll 1
+    for (int s = 0; s < kGemmDepth - 1; ++s) issue_step();
+    double acc[4][8][2];
+    int st = 0;
+    int64_t tile = blockIdx.x;
+#pragma unroll 1
+    for (int64_t step = 0; step < nsteps; ++step) {
+        issue_step();
+        asm volatile("cp.async.wait_group %0;" :: "n"(kGemmDepth - 1) : "memory");
+        __syncthreads();
+        const int64_t colbase = tile * kGemmTile + m0 + 2 * tig;         // + 8 * mj: this lane's two output columns
+        if (st == 0) {
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                for (int mj = 0; mj < 8; ++mj) {
+                    acc[ci][mj][0] = acc[ci][mj][1] = 0.0;
+                    const int c = c0 + 8 * ci + gid;
+                    const int64_t col = colbase + 8 * mj;
+                    if (accumulate && c < ncols) {
+                        double* py = Y + (int64_t)c * ldy + col;
+                        if (col + 1 < M) { const double2 y = ld_stream2_rw(py); acc[ci][mj][0] = y.x; acc[ci][mj][1] = y.y; }
+                        else if (col < M) acc[ci][mj][0] = py[0];
+                    }
+                }
+        }
+        const double* rows = ring + (size_t)((step & (kGemmDepth - 1)) * kGemmRowsPerStep + tig) * kMmaRingLd + m0 + gid;
+        const double* sr = ss + (size_t)(st * kGemmRowsPerStep + tig) * kMmaSsLd + c0 + gid;
+        double a[4], b[8];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) a[ci] = sr[8 * ci];
+#pragma unroll
+        for (int mj = 0; mj < 8; ++mj) b[mj] = rows[8 * mj];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+            for (int mj = 0; mj < 8; ++mj) dmma8x8x4(acc[ci][mj], a[ci], b[mj]);
+        if (++st == steps_per_tile) {
+            st = 0;
+            tile += gridDim.x;
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                for (int mj = 0; mj < 8; ++mj) {
+                    const int c = c0 + 8 * ci + gid;
+                    const int64_t col = colbase + 8 * mj;
+                    if (c < ncols) {
+                        double* py = Y + (int64_t)c * ldy + col;
+                        if (col + 1 < M) st_stream2(py, make_double2(acc[ci][mj][0], acc[ci][mj][1]));
+                        else if (col < M) py[0] = acc[ci][mj][0];
+                    }
+                }
+        }
+        __syncthreads();
+    }
+}
+
 int launch_ritz_lift(lz_ctx* ctx, const double* V, int64_t ldv, int n, int64_t M,
                      const double* S_dev, int k, double* Y, int64_t ldy) {
     const int vec_ok = ((((uintptr_t)V | (uintptr_t)Y) & 15) == 0) && ((ldv & 1) == 0) && ((ldy & 1) == 0);
     static const bool gemm_off = []() { const char* e = getenv("LZ_K5_GEMM"); return e && e[0] == '0'; }();
+    static const bool mma_off = []() { const char* e = getenv("LZ_K5_MMA"); return e && e[0] == '0'; }();
+    if (vec_ok && !gemm_off && !mma_off) {
+        const size_t smem = ((size_t)kGemmRowsSmem * kMmaSsLd + (size_t)kGemmRing * kMmaRingLd) * 8;
+        LZ_CUDA(cudaFuncSetAttribute((const void*)ritz_lift_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t ntiles = (M + kGemmTile - 1) / kGemmTile;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->sms));
+        for (int c0 = 0; c0 < k; c0 += kGemmOut) {
+            const int nc = std::min(kGemmOut, k - c0);
+            for (int w0 = 0; w0 < n; w0 += kGemmRowsSmem) {
+                const int wn = std::min(kGemmRowsSmem, n - w0);
+                ritz_lift_mma_kernel<<<grid, kThreads, smem, ctx->stream>>>(
+                    V + (int64_t)w0 * ldv, ldv, wn, M, S_dev + (int64_t)c0 * n + w0, n, nc,
+                    Y + (int64_t)c0 * ldy, ldy, w0 > 0, ntiles);
+                LZ_CUDA(cudaGetLastError());
+            }
+        }
+        return LZ_OK;
+    }
     if (vec_ok && !gemm_off) {
         const size_t smem = ((size_t)kGemmRowsSmem * kGemmOut + (size_t)kGemmRing * kGemmTile) * 8;
         LZ_CUDA(cudaFuncSetAttribute((const void*)ritz_lift_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
