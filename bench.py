@@ -731,7 +731,10 @@ def main():
              "achieved_gbs": moved_gbs if plain else None,
              "frac_of_measured_peak": moved_gbs / peak if plain else None,
              "frac_of_8TBs_nominal": moved_gbs / 8000.0 if plain else None,
-             "note": step_note + "; null when Gram-Schmidt sweeps ran"}
+             "burst_achieved_gbs": step_bytes / (burst_ms / K) / 1e6 if plain else None,
+             "burst_frac_of_measured_peak": step_bytes / (burst_ms / K) / 1e6 / peak if plain else None,
+             "note": step_note + "; sustained over the whole timed region, burst_* = the fastest single K-step solve "
+                                 "(both include the pre-step, amortised over K); null when Gram-Schmidt sweeps ran"}
     if is_stencil:
         # BASELINE's target (>= 70 % of the HBM roofline for the fused step at 512^3) is stated for the two-pass
         # step of SURVEY 8d, 48*N bytes: the same step time expressed in that accounting
