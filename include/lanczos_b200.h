@@ -149,6 +149,10 @@ int lz_op_nnz(const lz_op* op, int64_t* nnz_true, int64_t* nnz_stored);
 /* *value_free = 1 when the operator is applied from its column indices alone (LZ_FMT_SELL, all off-diagonal
  * entries equal): 4 instead of 12 bytes of HBM traffic per stored entry. */
 int lz_op_value_free(const lz_op* op, int32_t* value_free);
+/* *granules = 0, or - when the operator is applied in the windowed SELL form (per sorting window the entries of x
+ * it refers to are staged in shared memory, the stored column indices are 16-bit offsets into that stage) - the
+ * largest number of 32-entry granules of x one window stages.  LZ_SELL_WINDOW=0 in the environment disables the form. */
+int lz_op_windowed(const lz_op* op, int32_t* granules);
 
 /* y = H x on the device (`H*V[j]`, Lanczos.py:108,116).  Enqueues only. */
 int lz_op_apply(lz_op* op, const double* x_dev, double* y_dev);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "lz_op_rows": (C.c_int, [_vp, _P(_i64)]),
     "lz_op_nnz": (C.c_int, [_vp, _P(_i64), _P(_i64)]),
     "lz_op_value_free": (C.c_int, [_vp, _P(_i32)]),
+    "lz_op_windowed": (C.c_int, [_vp, _P(_i32)]),
     "lz_op_apply": (C.c_int, [_vp, _vp, _vp]),
     "lz_op_export_csr": (C.c_int, [_vp, _P(_i64), _vp, _vp, _vp]),
     "lz_op_destroy": (C.c_int, [_vp]),

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblanczos_b200.so")
 SYNTH_LIB = os.path.join(HERE, "liblz_synth.so")          # synthetic benchmark inputs (include/lz_synth.h)
 SYNTH_SOURCES = ["synth_rgg.cu"]
-SOURCES = ["capi.cu", "stencil.cu", "stencil27.cu", "vecops.cu", "reorth.cu", "spmv.cu", "fused.cu", "lanczos.cu", "potential.cu", "kba.cu", "small.cu"]
+SOURCES = ["capi.cu", "stencil.cu", "stencil27.cu", "vecops.cu", "reorth.cu", "spmv.cu", "sellw.cu", "fused.cu", "lanczos.cu", "potential.cu", "kba.cu", "small.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",

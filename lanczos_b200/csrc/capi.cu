@@ -252,6 +252,7 @@ int lz_op_csr_create_dev(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, con
     op->ncols = ncols;
     st = sell_classify_spans(op);
     if (st == LZ_OK && fmt == LZ_FMT_SELL) st = sell_detect_uniform(op);
+    if (st == LZ_OK) st = sellw_build(op);
     if (st != LZ_OK) { lz_op_destroy(op); return st; }
     *out = op;
     return LZ_OK;
@@ -278,6 +279,7 @@ static int csr_create_impl(lz_ctx* ctx, int64_t M, int64_t ncols, int64_t nnz, c
     op->ncols = ncols;
     st = sell_classify_spans(op);              // row shards: interior / boundary spans for the overlapped apply
     if (st == LZ_OK && fmt == LZ_FMT_SELL) st = sell_detect_uniform(op);   // unweighted graph Laplacians: value-free kernel
+    if (st == LZ_OK) st = sellw_build(op);     // locality-ordered matrices: x staged in shared memory, 16-bit indices
     if (st != LZ_OK) { lz_op_destroy(op); return st; }
     *out = op;
     return LZ_OK;
@@ -312,6 +314,12 @@ int lz_op_value_free(const lz_op* op, int32_t* value_free) {
     return LZ_OK;
 }
 
+int lz_op_windowed(const lz_op* op, int32_t* granules) {
+    LZ_REQUIRE(op && granules, "lz_op_windowed: null argument");
+    *granules = (op->kind == LZ_OP_SELL && op->sell.windowed) ? op->sell.win_maxg : 0;
+    return LZ_OK;
+}
+
 int lz_op_apply(lz_op* op, const double* x_dev, double* y_dev) {
     LZ_REQUIRE(op && x_dev && y_dev, "lz_op_apply: null argument");
     LZ_REQUIRE(x_dev != y_dev, "lz_op_apply: in-place apply is not supported");
@@ -334,6 +342,12 @@ int lz_op_destroy(lz_op* op) {
     if (op->sell.deff) cudaFree(op->sell.deff);
     if (op->sell.spans_int) cudaFree(op->sell.spans_int);
     if (op->sell.spans_bnd) cudaFree(op->sell.spans_bnd);
+    if (op->sell.win_gran_off) cudaFree(op->sell.win_gran_off);
+    if (op->sell.win_gran) cudaFree(op->sell.win_gran);
+    if (op->sell.win_lcol) cudaFree(op->sell.win_lcol);
+    if (op->sell.win_lrow) cudaFree(op->sell.win_lrow);
+    if (op->sell.win_off8) cudaFree(op->sell.win_off8);
+    if (op->sell.win_deff) cudaFree(op->sell.win_deff);
     delete op;
     return LZ_OK;
 }

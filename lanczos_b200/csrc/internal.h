@@ -74,6 +74,21 @@ struct lz_sell {
     int32_t* spans_bnd = nullptr;  // device, n_bnd span indices, ascending
     int n_int = 0, n_bnd = 0;
     int np_int = 0;                // CTAs (= partials) of the last interior launch
+    // windowed form (sellw.cu): per sorting window the sorted list of 32-entry granules of x it refers to, and
+    // 16-bit local indices (granule rank * 32 + col % 32) for every stored entry
+    int windowed = 0;              // 1: every window; 2: row shard, only the interior windows have lists
+    int win_span = 0;              // chunks per window (= sigma / 32)
+    int64_t win_count = 0;         // windows
+    int win_maxg = 0;              // largest granule list
+    int64_t win_total = 0;         // granules over all windows
+    size_t win_smem = 0;           // stage size of the kernel (win_maxg * 256 B)
+    int32_t* win_gran_off = nullptr;   // device, win_count + 1
+    int32_t* win_gran = nullptr;       // device, win_total
+    void* win_lcol = nullptr;          // device, 16-bit stage indices in blocks of [32 lanes][8 entries]
+    int64_t* win_off8 = nullptr;       // device, nchunks + 1: first block of each chunk
+    int64_t win_blocks = 0;
+    void* win_lrow = nullptr;          // device, nchunks*32 x uint32: row inside its window | stage index of x[row] << 16
+    double* win_deff = nullptr;        // device, nchunks*32: deff in (chunk, lane) order (value-free form)
 };
 
 struct lz_op {
@@ -114,6 +129,11 @@ int launch_apply_dot(lz_op* op, const double* x, const double* scale_dev, double
 bool spmv_split_supported(const lz_op* op);
 int sell_classify_spans(lz_op* op);
 int sell_detect_uniform(lz_op* op);
+int sellw_build(lz_op* op);
+int scan_i64(int64_t* a_dev, int64_t n, cudaStream_t q);     // exclusive prefix in place (set-up only)
+int launch_spmv_windowed(lz_op* op, const int32_t* win_list, int nlist, const double* x, const double* scale_dev,
+                         double* y, double* partials, int* grid_out, const int* flag_dev, const FinTail& ft,
+                         cudaStream_t stream);
 int launch_spmv_part(lz_op* op, int part, const double* x, const double* scale_dev, double* y, double* partials,
                      int* nparts, const int* flag_dev, const FinTail* fin, cudaStream_t stream);
 

@@ -182,6 +182,12 @@ int launch_spmv_dot(lz_op* op, const double* x, const double* scale_dev, double*
         return LZ_OK;
     }
     const lz_sell& sl = op->sell;
+    if (sl.windowed == 1) {
+        int grid = 0;
+        LZ_CHECK(launch_spmv_windowed(op, nullptr, 0, x, scale_dev, y, partials, &grid, flag_dev, ft, ctx->stream));
+        if (nparts) *nparts = grid;
+        return LZ_OK;
+    }
     // spans: one sorting window each; shorter (down to one chunk per warp) when the operator is too
     // small to give every resident CTA a few spans
     const int span = balanced_span(ctx, sl.nchunks, sl.sigma);
@@ -357,6 +363,13 @@ int launch_spmv_part(lz_op* op, int part, const double* x, const double* scale_d
         if (ft.op.kind != FIN_NONE) { ft.op.extra = partials; ft.op.nextra = sl.np_int; }
     }
     // an empty list still launches one CTA: its partial is 0 and its tail runs the bookkeeping / the exchange
+    if (part == 1 && sl.windowed) {
+        int wgrid = 0;
+        LZ_CHECK(launch_spmv_windowed(op, list, nlist, x, scale_dev, y, pout, &wgrid, flag_dev, ft, stream));
+        sl.np_int = wgrid;
+        if (nparts) *nparts = wgrid;
+        return LZ_OK;
+    }
     if (sl.uniform)
         LZ_CUDA(launch_k(spmv_sell_dot_kernel<true>, dim3(grid), dim3(kThreads), 0, stream, sl.chunk_off, sl.col, sl.val,
                          sl.row_of, x, scale_dev, y, sl.nchunks, pout, op->xghost, (int32_t)op->M, span, ft,
@@ -588,6 +601,12 @@ scan_i64_kernel(int64_t* __restrict__ a, int64_t n) {
     __syncthreads();
     int64_t run = s_tot[t];
     for (int64_t i = b; i < e; ++i) { const int64_t v = a[i]; a[i] = run; run += v; }
+}
+
+int scan_i64(int64_t* a_dev, int64_t n, cudaStream_t q) {
+    scan_i64_kernel<<<1, 1024, 0, q>>>(a_dev, n);
+    LZ_CUDA(cudaGetLastError());
+    return LZ_OK;
 }
 
 int build_from_device(lz_op* op, int64_t M, int64_t ncols, int64_t nnz, const int32_t* indptr,

@@ -245,6 +245,13 @@ class DeviceOperator:
         _capi.check(self.ctx.lib.lz_op_value_free(self.handle, C.byref(v)))
         return bool(v.value)
 
+    def windowed(self) -> int:
+        """0, or the largest number of 32-entry granules of x one sorting window stages in shared memory when the
+        operator runs in the windowed SELL form (16-bit column offsets; csrc/sellw.cu)."""
+        v = C.c_int32()
+        _capi.check(self.ctx.lib.lz_op_windowed(self.handle, C.byref(v)))
+        return int(v.value)
+
     def apply(self, x, y=None):
         """y = H x for CUDA tensors (enqueued on the context's stream)."""
         torch = _torch()

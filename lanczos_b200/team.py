@@ -560,6 +560,12 @@ class _TeamBase:
         _capi.check(self.lib.lz_op_value_free(self.shards[0].op_handle, C.byref(v)))
         return bool(v.value)
 
+    def windowed_local(self) -> int:
+        """Largest per-window stage (granules of 32 entries) of the first local shard, 0 = plain SELL kernel."""
+        v = C.c_int32()
+        _capi.check(self.lib.lz_op_windowed(self.shards[0].op_handle, C.byref(v)))
+        return int(v.value)
+
     def nnz_local(self):
         """(true, stored) entries of the first local shard of a sparse operator."""
         t, s = C.c_int64(), C.c_int64()

@@ -325,6 +325,21 @@ def delaunay_graph_laplacian(npts, seed=0):
     return Lm
 
 
+def banded_graph_laplacian(M, far=(9000,), seed=0, keep=0.7):
+    """Unweighted graph Laplacian of a locality-ordered graph: vertex i is joined to i +- 1..4, i +- 97..100 and
+    i +- (f .. f+2) for f in `far`, every candidate edge kept with probability `keep` (ragged rows)."""
+    rng = np.random.RandomState(seed)
+    offs = [1, 2, 3, 4, 97, 98, 99, 100] + [f + k for f in far for k in range(3)]
+    rows, cols = [], []
+    for d in offs:
+        i = np.nonzero(rng.random_sample(M - d) < keep)[0]
+        rows += [i, i + d]
+        cols += [i + d, i]
+    r, c = np.concatenate(rows), np.concatenate(cols)
+    A = sp.csr_matrix((np.ones(r.size), (r, c)), shape=(M, M))
+    return sp.csr_matrix(sp.diags(np.asarray(A.sum(axis=1)).ravel()) - A)
+
+
 def rgg_graph_laplacian(npts, mean_degree=13.0, seed=0, dim=3):
     """Graph Laplacian of a random geometric graph in the unit cube (BASELINE config 4,
     scaled down for tests): radius chosen for the requested mean degree, vertices in

@@ -1054,3 +1054,49 @@ def test_value_free_sell_for_unweighted_graph_laplacians(lz):
         L = lz.IrrLanczos(G)
         L.execute_LanczosOld(30, seed=5, fmt=f)
         assert rel(np.diag(L.H_eff), refl["alpha"]) < TOL_AB and rel(np.diag(L.H_eff, 1), refl["beta"]) < TOL_AB
+
+
+def test_windowed_sell_form(lz, monkeypatch):
+    """csrc/sellw.cu: when the columns every sorting window refers to fit a shared-memory stage, x is staged there
+    and the stored column indices are 16-bit offsets.  Same summation order per row as the plain SELL kernel, so y
+    is bit-identical to it - value-free and weighted operators, ragged rows, a last window that is not full; an
+    operator whose windows do not fit keeps the plain kernel; the loop gives the oracle's alpha/beta."""
+    from lanczos_b200 import engine
+    ctx = engine.Context.default()
+    M = 40_037
+    G = orc.banded_graph_laplacian(M, seed=3)
+    W = sp.csr_matrix(G.copy())
+    W.data = W.data * (1.0 + 0.01 * (np.arange(W.nnz) % 89))
+    x = np.random.RandomState(0).uniform(-1, 1, M)
+    monkeypatch.setenv("LZ_SELL_WINDOW", "0")
+    plain = {k: engine.DeviceOperator.from_scipy(ctx, A, fmt="sell") for k, A in (("G", G), ("W", W))}
+    assert plain["G"].windowed() == 0 and plain["G"].value_free()
+    monkeypatch.setenv("LZ_SELL_WINDOW", "1")
+    monkeypatch.setenv("LZ_SELL_WINDOW_MIN", "1")
+    for k, A in (("G", G), ("W", W)):
+        op = engine.DeviceOperator.from_scipy(ctx, A, fmt="sell")
+        assert 0 < op.windowed() <= 448, op.windowed()
+        assert op.value_free() == (k == "G")
+        y = op.apply_host(x)
+        assert np.array_equal(y, plain[k].apply_host(x)), k
+        assert np.max(np.abs(y - A * x)) <= 4e-15 * np.max(np.abs(A * x))
+        assert (op.export_csr() != A).nnz == 0
+    # smaller sorting windows (8 chunks: half of the kernel's warps idle) and one that is no multiple of 8 chunks
+    for sigma in (256, 96):
+        op = engine.DeviceOperator.from_scipy(ctx, G, fmt="sell", sigma=sigma)
+        assert op.windowed() > 0
+        assert np.max(np.abs(op.apply_host(x) - G * x)) <= 4e-15 * np.max(np.abs(G * x))
+    # too many distinct runs of columns per window: the plain kernel stays
+    far = orc.banded_graph_laplacian(M, far=(5000, 9000, 14000, 20000, 27000), seed=3)
+    fop = engine.DeviceOperator.from_scipy(ctx, far, fmt="sell")
+    assert fop.windowed() == 0
+    assert np.max(np.abs(fop.apply_host(x) - far * x)) <= 4e-15 * np.max(np.abs(far * x))
+    # the loop (alpha from the windowed kernel's partial sums, bookkeeping tail run by its first 8 warps)
+    ref = orc.lanczos(G, 30, seed=5)
+    L = lz.IrrLanczos(G)
+    L.execute_LanczosOld(30, seed=5)
+    assert L._device_op.windowed() > 0
+    assert rel(np.diag(L.H_eff), ref["alpha"]) < TOL_AB and rel(np.diag(L.H_eff, 1), ref["beta"]) < TOL_AB
+    first = L.H_eff.copy()
+    L.execute_LanczosOld(30, seed=5)
+    assert np.array_equal(first, L.H_eff)

@@ -349,3 +349,29 @@ def test_sparse_shards_overlap_interior_apply_with_exchange(lz, world, reorth, p
     if reorth == "selective":
         ref = orc.lanczos(H, n, seed=3)
         assert rel(np.diag(T[True])[:12], ref["alpha"][:12]) < 1e-11
+
+
+@pytest.mark.parametrize("world,reorth", [(2, "selective"), (3, "none")])
+def test_sparse_shards_windowed_interior(lz, monkeypatch, world, reorth):
+    """Row shards in the windowed SELL form (csrc/sellw.cu): the interior windows run from the shared-memory stage
+    with 16-bit offsets, the windows with ghost columns stay with the plain kernel in pieces."""
+    from lanczos_b200.team import LocalTeamLanczos
+    H = orc.banded_graph_laplacian(60_011, far=(3000,), seed=9)
+    n = 30
+    kw = dict(reorth=reorth, cgs_passes=2, select_tol=1e-12 if reorth == "selective" else 0.0)
+    monkeypatch.setenv("LZ_SELL_WINDOW", "0")
+    plain = LocalTeamLanczos(H, world, fmt="sell", sigma=256)
+    plain.execute_LanczosOld(n, seed=3, **kw)
+    assert plain.windowed_local() == 0
+    monkeypatch.setenv("LZ_SELL_WINDOW", "1")
+    monkeypatch.setenv("LZ_SELL_WINDOW_MIN", "1")
+    for ov in (True, False):
+        team = LocalTeamLanczos(H, world, fmt="sell", sigma=256)
+        team.execute_LanczosOld(n, seed=3, overlap=ov, **kw)
+        assert team.windowed_local() > 0 and team.result.overlap == ov
+        tol = 1e-12 if reorth != "none" else 1e-9
+        assert rel(np.diag(team.H_eff), np.diag(plain.H_eff)) < tol
+        assert rel(np.diag(team.H_eff, 1), np.diag(plain.H_eff, 1)) < tol
+        T = team.H_eff.copy()
+        team.execute_LanczosOld(n, seed=3, overlap=ov, **kw)
+        assert np.array_equal(T, team.H_eff)

@@ -225,3 +225,15 @@ def test_vendored_reference_matches_golden():
         L.execute_Lanczos(20, seed=99, use_cuda=False)
     ref = orc.lanczos(H, 20, seed=99)
     assert np.array_equal(np.diag(L.H_eff), ref["alpha"]) and np.array_equal(np.diag(L.H_eff, 1), ref["beta"])
+
+
+def test_banded_graph_laplacian_generator():
+    """Test matrix of the windowed SELL form: symmetric, zero row sums, -1 off the diagonal, columns only in the
+    stated bands around the diagonal."""
+    L = orc.banded_graph_laplacian(5000, far=(900,), seed=1)
+    assert (L != L.T).nnz == 0
+    assert np.max(np.abs(L @ np.ones(5000))) == 0.0
+    C = L.tocoo()
+    d = np.abs(C.row - C.col)
+    assert set(np.unique(C.data[d > 0])) == {-1.0}
+    assert set(np.unique(d)) <= {0, 1, 2, 3, 4, 97, 98, 99, 100, 900, 901, 902}
