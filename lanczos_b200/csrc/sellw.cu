@@ -39,7 +39,7 @@ constexpr size_t kWinSmemMax = 232448 - 1024;   // opt-in dynamic shared memory 
 
 __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
     uint4 v;
-    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 
@@ -52,6 +52,7 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 // barrier's phase completes when all have and every byte has landed).  x 16-byte aligned: thread t issues the bulk
 // copy of granule t.  Otherwise (a basis row of odd length): warp q copies granules q, q + 32, ... with 8-byte
 // asynchronous copies.  The granule that straddles M, and ghost columns of a row shard, are copied by hand.
+template <int NT>
 __device__ __forceinline__ void stage_window(double* buf, uint32_t bar, const double* __restrict__ x,
                                              const double* __restrict__ xg, const int32_t* __restrict__ gran,
                                              int32_t g0, int ng, int32_t M, int32_t ncols, bool al16) {
@@ -59,7 +60,7 @@ __device__ __forceinline__ void stage_window(double* buf, uint32_t bar, const do
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) buf[ng * 32] = 0.0;             // the slot the padding indices point at
     if (al16) {
-        for (int gi = threadIdx.x; gi < ng; gi += kWinThreads) {
+        for (int gi = threadIdx.x; gi < ng; gi += NT) {
             const int32_t base = __ldg(gran + g0 + gi) * 32;
             double* dst = buf + gi * 32;
             if (base + 32 <= M) {
@@ -75,9 +76,9 @@ __device__ __forceinline__ void stage_window(double* buf, uint32_t bar, const do
         mbar_arrive(bar);
         return;
     }
-    const int mine_at = warp + kWinWarps * lane;
+    const int mine_at = warp + (NT / 32) * lane;
     const int32_t mine = mine_at < ng ? __ldg(gran + g0 + mine_at) : 0;
-    for (int it = 0, gi = warp; gi < ng; ++it, gi += kWinWarps) {
+    for (int it = 0, gi = warp; gi < ng; ++it, gi += NT / 32) {
         const int32_t base = __shfl_sync(0xffffffffu, mine, it) * 32;
         double* dst = buf + gi * 32;
         if (base + 32 <= M) {
@@ -93,24 +94,42 @@ __device__ __forceinline__ void stage_window(double* buf, uint32_t bar, const do
 // One chunk of 32 rows: what it reads from global memory is requested first (chunk_issue), consumed later
 // (chunk_finish), so that a warp has the loads of two chunks in flight.
 struct ChunkRegs {
+    int c;                                                // chunk, -1: none
     uint4 q0, q1;                                         // the first 16 stage indices of the lane's row
-    const uint4* p;                                       // the lane's first block
+    int b0;                                               // first block
     int nb;                                               // blocks of 8 entries
     uint32_t rr;                                          // row inside the window | stage index of x[row] << 16
     double dd;
 };
 
+// where a chunk's index blocks are: loaded one window ahead of the indices themselves, which depend on it
+struct ChunkMeta {
+    int c;                                                // chunk, -1: none
+    int b0, nb;                                           // its blocks [b0, b0 + nb)
+};
+
+__device__ __forceinline__ ChunkMeta chunk_meta(int64_t c, int64_t c_end, const int64_t* __restrict__ off8) {
+    ChunkMeta m;
+    m.c = c < c_end ? (int)c : -1;
+    m.b0 = m.c >= 0 ? (int)__ldg(off8 + c) : 0;
+    m.nb = m.c >= 0 ? (int)__ldg(off8 + c + 1) - m.b0 : 0;
+    return m;
+}
+
 template <bool UNI>
-__device__ __forceinline__ void chunk_issue(ChunkRegs& r, int64_t c, const uint4* __restrict__ lc8,
-                                            const int64_t* __restrict__ off8, const uint32_t* __restrict__ lrow,
-                                            const double* __restrict__ deff_p, int lane) {
-    const int64_t b0 = __ldg(off8 + c);
-    r.nb = (int)(__ldg(off8 + c + 1) - b0);
-    r.p = lc8 + b0 * 32 + lane;
+__device__ __forceinline__ void chunk_issue(ChunkRegs& r, const ChunkMeta& m, const uint4* __restrict__ lc8,
+                                            const uint32_t* __restrict__ lrow, const double* __restrict__ deff_p,
+                                            int lane) {
+    r.c = m.c;
+    if (m.c < 0) return;
+    const int64_t c = m.c;
+    r.b0 = m.b0;
+    r.nb = m.nb;
+    const uint4* p = lc8 + (int64_t)m.b0 * 32 + lane;
     r.rr = __ldg(lrow + c * 32 + lane);
     r.dd = UNI ? __ldg(deff_p + c * 32 + lane) : 0.0;
-    r.q0 = r.nb > 0 ? ld_stream_u4(r.p) : make_uint4(0, 0, 0, 0);
-    r.q1 = r.nb > 1 ? ld_stream_u4(r.p + 32) : make_uint4(0, 0, 0, 0);
+    r.q0 = r.nb > 0 ? ld_stream_u4(p) : make_uint4(0, 0, 0, 0);
+    r.q1 = r.nb > 1 ? ld_stream_u4(p + 32) : make_uint4(0, 0, 0, 0);
 }
 
 // 8 entries: sum += [v *] stage[index], in entry order (the low half of a word is the earlier entry)
@@ -136,9 +155,11 @@ __device__ __forceinline__ void add8(double& sum, const uint4 q, const double* s
 }
 
 template <bool UNI>
-__device__ __forceinline__ void chunk_finish(const ChunkRegs& r, int64_t c, const double* sx, double* sy,
-                                             const int64_t* __restrict__ chunk_off, const double* __restrict__ val,
+__device__ __forceinline__ void chunk_finish(const ChunkRegs& r, const double* sx, double* sy,
+                                             const uint4* __restrict__ lc8, const int64_t* __restrict__ chunk_off, const double* __restrict__ val,
                                              double s, double uni_a, int lane, double& acc) {
+    if (r.c < 0) return;
+    const int64_t c = r.c;
     double sum = 0.0;
     const double* pv = nullptr;
     int width = 0;
@@ -149,7 +170,8 @@ __device__ __forceinline__ void chunk_finish(const ChunkRegs& r, int64_t c, cons
     }
     if (r.nb > 0) add8<UNI>(sum, r.q0, sx, pv, width);
     if (r.nb > 1) add8<UNI>(sum, r.q1, sx, pv + 8 * 32, width - 8);
-    for (int b = 2; b < r.nb; ++b) add8<UNI>(sum, ld_stream_u4(r.p + b * 32), sx, pv + b * 8 * 32, width - 8 * b);
+    for (int b = 2; b < r.nb; ++b)
+        add8<UNI>(sum, ld_stream_u4(lc8 + ((int64_t)r.b0 + b) * 32 + lane), sx, pv + b * 8 * 32, width - 8 * b);
     if (r.rr != 0xffffffffu) {
         const double xr = sx[r.rr >> 16];
         if (UNI) sum = fma(uni_a, sum, r.dd * xr);
@@ -171,7 +193,7 @@ spmv_sellw_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __rest
                       double* __restrict__ partials, const double* __restrict__ xg, int32_t M, int32_t ncols, int span,
                       const FinTail fin, const int32_t* __restrict__ win_list, int nlist, int64_t nwin,
                       const int* __restrict__ flag, const double* __restrict__ deff_p, double uni_a,
-                      const int32_t* __restrict__ gran_off, const int32_t* __restrict__ gran, int stage_doubles) {
+                      const int32_t* __restrict__ gran_off, const int32_t* __restrict__ gran, int stage_doubles, int dbg) {
     pdl_prologue();
     if (flag && *flag == 0) return;
     extern __shared__ __align__(128) double sx[];
@@ -182,7 +204,7 @@ spmv_sellw_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __rest
     const double s = scale ? __ldg(scale) : 1.0;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const bool al16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const bool al16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && !(dbg & 4);
     const int64_t nitems = win_list ? (int64_t)nlist : nwin;
     const uint32_t bar0 = smem_addr(&bars[0]), bar1 = smem_addr(&bars[1]);
     if (threadIdx.x == 0) {
@@ -193,38 +215,55 @@ spmv_sellw_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __rest
     __syncthreads();
     double acc = 0.0;
     auto window_of = [&](int64_t si) { return win_list ? (int64_t)__ldg(win_list + si) : si; };
+    // A warp's chunks of a window are w * span + warp + 32 k.  The first two (all of them when sigma = 2048) run one
+    // window ahead: their block ranges are fetched while the previous window is computed, their indices as soon as
+    // it is done - before the barrier, the write-out of y and the wait for the stage.
     int64_t si = blockIdx.x;
+    ChunkRegs a, b;
+    a.c = b.c = -1;
     if (si < nitems) {
         const int64_t w = window_of(si);
         const int32_t g0 = __ldg(gran_off + w);
-        stage_window(sx, bar0, x, xg, gran, g0, __ldg(gran_off + w + 1) - g0, M, ncols, al16);
+        stage_window<kWinThreads>(sx, bar0, x, xg, gran, g0, (dbg & 1) ? 0 : __ldg(gran_off + w + 1) - g0, M, ncols, al16);
+        const int64_t c_end = min(nchunks, (w + 1) * span);
+        chunk_issue<UNI>(a, chunk_meta(w * span + warp, c_end, off8), lc8, lrow, deff_p, lane);
+        chunk_issue<UNI>(b, chunk_meta(w * span + warp + kWinWarps, c_end, off8), lc8, lrow, deff_p, lane);
     }
     for (int it = 0; si < nitems; si += gridDim.x, ++it) {
         const int64_t w = window_of(si);
         const int64_t sn = si + gridDim.x;
+        ChunkMeta ma, mb;
+        ma.c = mb.c = -1;
         if (sn < nitems) {                                // next window into the other stage (free since the barrier below)
             const int64_t wn = window_of(sn);
             const int32_t g0 = __ldg(gran_off + wn);
-            stage_window(sx + ((it + 1) & 1) * stage_doubles, (it & 1) ? bar0 : bar1, x, xg, gran, g0,
-                         __ldg(gran_off + wn + 1) - g0, M, ncols, al16);
+            stage_window<kWinThreads>(sx + ((it + 1) & 1) * stage_doubles, (it & 1) ? bar0 : bar1, x, xg, gran, g0,
+                         (dbg & 1) ? 0 : __ldg(gran_off + wn + 1) - g0, M, ncols, al16);
+            const int64_t cn_end = min(nchunks, (wn + 1) * span);
+            ma = chunk_meta(wn * span + warp, cn_end, off8);
+            mb = chunk_meta(wn * span + warp + kWinWarps, cn_end, off8);
         }
         mbar_wait((it & 1) ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
         const double* cur = sx + (it & 1) * stage_doubles;
         double* sy = sy0 + (it & 1) * sigma;
+        if (!(dbg & 2)) {
+        chunk_finish<UNI>(a, cur, sy, lc8, chunk_off, val, s, uni_a, lane, acc);
+        chunk_finish<UNI>(b, cur, sy, lc8, chunk_off, val, s, uni_a, lane, acc);
+        }
         const int64_t c_end = min(nchunks, (w + 1) * span);
-        for (int64_t c = w * span + warp; c < c_end; c += 2 * kWinWarps) {
-            ChunkRegs a, b;
-            const bool two = c + kWinWarps < c_end;
-            chunk_issue<UNI>(a, c, lc8, off8, lrow, deff_p, lane);
-            if (two) chunk_issue<UNI>(b, c + kWinWarps, lc8, off8, lrow, deff_p, lane);
-            chunk_finish<UNI>(a, c, cur, sy, chunk_off, val, s, uni_a, lane, acc);
-            if (two) chunk_finish<UNI>(b, c + kWinWarps, cur, sy, chunk_off, val, s, uni_a, lane, acc);
+        for (int64_t c = w * span + warp + 2 * kWinWarps; c < c_end; c += kWinWarps) {     // sigma > 2048
+            chunk_issue<UNI>(a, chunk_meta(c, c_end, off8), lc8, lrow, deff_p, lane);
+            chunk_finish<UNI>(a, cur, sy, lc8, chunk_off, val, s, uni_a, lane, acc);
+        }
+        if (!(dbg & 8)) {
+        chunk_issue<UNI>(a, ma, lc8, lrow, deff_p, lane);
+        chunk_issue<UNI>(b, mb, lc8, lrow, deff_p, lane);
         }
         __syncthreads();                                  // sy is complete; this stage may be overwritten from now on
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ... by bulk copies (async proxy) as well
+        if (!(dbg & 32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ... by bulk copies (async proxy) as well
         const int64_t r0 = w * sigma;
         const int rows = (int)min((int64_t)sigma, (int64_t)M - r0);
-        for (int t = threadIdx.x; t < rows; t += kWinThreads) y[r0 + t] = sy[t];
+        if (!(dbg & 16)) for (int t = threadIdx.x; t < rows; t += kWinThreads) y[r0 + t] = sy[t];
     }
     // CTA sum in warp order; the bookkeeping tail is written for kThreads threads, so the upper warps leave first
     acc = warp_sum(acc);
@@ -235,6 +274,92 @@ spmv_sellw_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __rest
         double t = 0.0;
 #pragma unroll
         for (int q = 0; q < kWinWarps; ++q) t += red[q];
+        partials[blockIdx.x] = t;
+    }
+    fin_tail(fin, partials, red);
+}
+
+// The same with two CTAs of 16 warps per SM, each with ONE stage of x and one buffer for y: a CTA's phases (stage
+// the window, fetch the indices, gather out of shared memory, write y) follow each other, and the two CTAs of an
+// SM fill each other's waits.  Needs (granules * 256 + sigma * 8) bytes twice per SM.
+constexpr int kWin2Threads = 512;
+constexpr int kWin2Warps = kWin2Threads / 32;
+
+template <bool UNI>
+__global__ void __launch_bounds__(kWin2Threads, 2)
+spmv_sellw2_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __restrict__ lc8,
+                       const int64_t* __restrict__ off8, const double* __restrict__ val,
+                       const uint32_t* __restrict__ lrow, const double* __restrict__ x,
+                       const double* __restrict__ scale, double* __restrict__ y, int64_t nchunks,
+                       double* __restrict__ partials, const double* __restrict__ xg, int32_t M, int32_t ncols, int span,
+                       const FinTail fin, const int32_t* __restrict__ win_list, int nlist, int64_t nwin,
+                       const int* __restrict__ flag, const double* __restrict__ deff_p, double uni_a,
+                       const int32_t* __restrict__ gran_off, const int32_t* __restrict__ gran, int stage_doubles) {
+    pdl_prologue();
+    if (flag && *flag == 0) return;
+    extern __shared__ __align__(128) double sx[];
+    __shared__ double red[kWin2Warps];
+    __shared__ __align__(8) unsigned long long bars[1];
+    const int sigma = span * 32;
+    double* const sy = sx + stage_doubles;
+    const double s = scale ? __ldg(scale) : 1.0;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const bool al16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const int64_t nitems = win_list ? (int64_t)nlist : nwin;
+    const uint32_t bar = smem_addr(&bars[0]);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, kWin2Threads);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    double acc = 0.0;
+    auto window_of = [&](int64_t si) { return win_list ? (int64_t)__ldg(win_list + si) : si; };
+    // the window after this one: its id and granule range are fetched an iteration ahead
+    int64_t si = blockIdx.x;
+    int64_t w = si < nitems ? window_of(si) : 0;
+    int32_t g0 = si < nitems ? __ldg(gran_off + w) : 0;
+    int32_t g1 = si < nitems ? __ldg(gran_off + w + 1) : 0;
+    for (int it = 0; si < nitems; si += gridDim.x, ++it) {
+        stage_window<kWin2Threads>(sx, bar, x, xg, gran, g0, g1 - g0, M, ncols, al16);
+        const int64_t c_end = min(nchunks, (w + 1) * span);
+        int64_t c = w * span + warp;
+        ChunkRegs a, b;
+        chunk_issue<UNI>(a, chunk_meta(c, c_end, off8), lc8, lrow, deff_p, lane);
+        chunk_issue<UNI>(b, chunk_meta(c + kWin2Warps, c_end, off8), lc8, lrow, deff_p, lane);
+        const int64_t w_cur = w;
+        const int64_t sn = si + gridDim.x;
+        if (sn < nitems) {
+            w = window_of(sn);
+            g0 = __ldg(gran_off + w);
+            g1 = __ldg(gran_off + w + 1);
+        }
+        mbar_wait(bar, (uint32_t)it & 1u);
+        for (;;) {
+            c += 2 * kWin2Warps;
+            const ChunkMeta ma = chunk_meta(c, c_end, off8), mb = chunk_meta(c + kWin2Warps, c_end, off8);
+            chunk_finish<UNI>(a, sx, sy, lc8, chunk_off, val, s, uni_a, lane, acc);
+            chunk_finish<UNI>(b, sx, sy, lc8, chunk_off, val, s, uni_a, lane, acc);
+            if (ma.c < 0) break;
+            chunk_issue<UNI>(a, ma, lc8, lrow, deff_p, lane);
+            chunk_issue<UNI>(b, mb, lc8, lrow, deff_p, lane);
+        }
+        __syncthreads();                                  // sy is complete, the stage is free
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const int64_t r0 = w_cur * sigma;
+        const int rows = (int)min((int64_t)sigma, (int64_t)M - r0);
+        for (int t = threadIdx.x; t < rows; t += kWin2Threads) y[r0 + t] = sy[t];
+        // the next write to sy follows the wait for the next stage, whose barrier needs every thread's arrival -
+        // made after this write-out
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (warp >= kWarps) return;
+    if (threadIdx.x == 0 && partials) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < kWin2Warps; ++q) t += red[q];
         partials[blockIdx.x] = t;
     }
     fin_tail(fin, partials, red);
@@ -410,6 +535,8 @@ int sellw_build(lz_op* op) {
     }
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(spmv_sellw_dot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmemMax);
     if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(spmv_sellw_dot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmemMax);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(spmv_sellw2_dot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kWinSmemMax / 2));
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(spmv_sellw2_dot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kWinSmemMax / 2));
     if (e2 != cudaSuccess) {
         cudaGetLastError();
         if (gran) cudaFree(gran);
@@ -445,20 +572,39 @@ int launch_spmv_windowed(lz_op* op, const int32_t* win_list, int nlist, const do
     lz_ctx* ctx = op->ctx;
     const lz_sell& sl = op->sell;
     const int64_t nitems = win_list ? (int64_t)nlist : sl.win_count;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nitems, (int64_t)ctx->sms));
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nitems, (int64_t)ctx->sms));
     const int stage_doubles = sl.win_maxg * 32 + 2;
-    if (sl.uniform)
+    const char* dbg_env = getenv("LZ_SELLW_DEBUG");
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
+    const char* var_env = getenv("LZ_SELLW_VARIANT");
+    const size_t smem2 = ((size_t)stage_doubles + (size_t)sl.sigma) * sizeof(double);
+    const bool two_ctas = smem2 <= kWinSmemMax / 2 - 1024 && !(var_env && var_env[0] == '1');
+    if (two_ctas) {
+        grid = (int)std::max<int64_t>(1, std::min<int64_t>(nitems, (int64_t)ctx->sms * 2));
+        if (sl.uniform)
+            LZ_CUDA(launch_k(spmv_sellw2_dot_kernel<true>, dim3(grid), dim3(kWin2Threads), smem2, stream, sl.chunk_off,
+                             (const uint4*)sl.win_lcol, (const int64_t*)sl.win_off8, sl.val, (const uint32_t*)sl.win_lrow, x,
+                             scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, (int32_t)op->ncols, sl.win_span, ft,
+                             win_list, nlist, sl.win_count, flag_dev, (const double*)sl.win_deff, sl.uni_a,
+                             (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles));
+        else
+            LZ_CUDA(launch_k(spmv_sellw2_dot_kernel<false>, dim3(grid), dim3(kWin2Threads), smem2, stream, sl.chunk_off,
+                             (const uint4*)sl.win_lcol, (const int64_t*)sl.win_off8, sl.val, (const uint32_t*)sl.win_lrow, x,
+                             scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, (int32_t)op->ncols, sl.win_span, ft,
+                             win_list, nlist, sl.win_count, flag_dev, (const double*)nullptr, 0.0,
+                             (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles));
+    } else if (sl.uniform)
         LZ_CUDA(launch_k(spmv_sellw_dot_kernel<true>, dim3(grid), dim3(kWinThreads), sl.win_smem, stream, sl.chunk_off,
                          (const uint4*)sl.win_lcol, (const int64_t*)sl.win_off8, sl.val, (const uint32_t*)sl.win_lrow, x,
                          scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, (int32_t)op->ncols, sl.win_span, ft,
                          win_list, nlist, sl.win_count, flag_dev, (const double*)sl.win_deff, sl.uni_a,
-                         (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles));
+                         (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles, dbg));
     else
         LZ_CUDA(launch_k(spmv_sellw_dot_kernel<false>, dim3(grid), dim3(kWinThreads), sl.win_smem, stream, sl.chunk_off,
                          (const uint4*)sl.win_lcol, (const int64_t*)sl.win_off8, sl.val, (const uint32_t*)sl.win_lrow, x,
                          scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, (int32_t)op->ncols, sl.win_span, ft,
                          win_list, nlist, sl.win_count, flag_dev, (const double*)nullptr, 0.0,
-                         (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles));
+                         (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles, dbg));
     if (grid_out) *grid_out = grid;
     return LZ_OK;
 }
