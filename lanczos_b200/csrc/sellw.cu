@@ -181,9 +181,11 @@ __device__ __forceinline__ void chunk_finish(const ChunkRegs& r, const double* s
     }
 }
 
-// One CTA of 32 warps per SM, windows dealt round-robin (neighbouring SMs work on neighbouring windows: what they
-// stage overlaps and comes out of L2).  Shared memory: two stages of x (each the largest granule set + the zero
-// slot), two buffers for the window's y.
+// Fallback for granule sets too large for two CTAs per SM (spmv_sellw2_dot_kernel below, the one that normally
+// runs): one CTA of 32 warps per SM, two stages of x (each the largest granule set + the zero slot) and two buffers
+// for the window's y; the copies of window i + 1 are in flight while window i is computed.  Measured on the
+// config-4 graph: 1.11 ms per apply against 0.98 ms for the two-CTA form (plain SELL kernel: 1.55 ms) - with one
+// CTA nothing fills the waits between the phases of a window.  LZ_SELLW_VARIANT=1 forces this form.
 template <bool UNI>
 __global__ void __launch_bounds__(kWinThreads, 1)
 spmv_sellw_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __restrict__ lc8,
@@ -193,7 +195,7 @@ spmv_sellw_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __rest
                       double* __restrict__ partials, const double* __restrict__ xg, int32_t M, int32_t ncols, int span,
                       const FinTail fin, const int32_t* __restrict__ win_list, int nlist, int64_t nwin,
                       const int* __restrict__ flag, const double* __restrict__ deff_p, double uni_a,
-                      const int32_t* __restrict__ gran_off, const int32_t* __restrict__ gran, int stage_doubles, int dbg) {
+                      const int32_t* __restrict__ gran_off, const int32_t* __restrict__ gran, int stage_doubles) {
     pdl_prologue();
     if (flag && *flag == 0) return;
     extern __shared__ __align__(128) double sx[];
@@ -204,7 +206,7 @@ spmv_sellw_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __rest
     const double s = scale ? __ldg(scale) : 1.0;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const bool al16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && !(dbg & 4);
+    const bool al16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     const int64_t nitems = win_list ? (int64_t)nlist : nwin;
     const uint32_t bar0 = smem_addr(&bars[0]), bar1 = smem_addr(&bars[1]);
     if (threadIdx.x == 0) {
@@ -215,55 +217,43 @@ spmv_sellw_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __rest
     __syncthreads();
     double acc = 0.0;
     auto window_of = [&](int64_t si) { return win_list ? (int64_t)__ldg(win_list + si) : si; };
-    // A warp's chunks of a window are w * span + warp + 32 k.  The first two (all of them when sigma = 2048) run one
-    // window ahead: their block ranges are fetched while the previous window is computed, their indices as soon as
-    // it is done - before the barrier, the write-out of y and the wait for the stage.
     int64_t si = blockIdx.x;
-    ChunkRegs a, b;
-    a.c = b.c = -1;
     if (si < nitems) {
         const int64_t w = window_of(si);
         const int32_t g0 = __ldg(gran_off + w);
-        stage_window<kWinThreads>(sx, bar0, x, xg, gran, g0, (dbg & 1) ? 0 : __ldg(gran_off + w + 1) - g0, M, ncols, al16);
-        const int64_t c_end = min(nchunks, (w + 1) * span);
-        chunk_issue<UNI>(a, chunk_meta(w * span + warp, c_end, off8), lc8, lrow, deff_p, lane);
-        chunk_issue<UNI>(b, chunk_meta(w * span + warp + kWinWarps, c_end, off8), lc8, lrow, deff_p, lane);
+        stage_window<kWinThreads>(sx, bar0, x, xg, gran, g0, __ldg(gran_off + w + 1) - g0, M, ncols, al16);
     }
     for (int it = 0; si < nitems; si += gridDim.x, ++it) {
         const int64_t w = window_of(si);
         const int64_t sn = si + gridDim.x;
-        ChunkMeta ma, mb;
-        ma.c = mb.c = -1;
         if (sn < nitems) {                                // next window into the other stage (free since the barrier below)
             const int64_t wn = window_of(sn);
             const int32_t g0 = __ldg(gran_off + wn);
             stage_window<kWinThreads>(sx + ((it + 1) & 1) * stage_doubles, (it & 1) ? bar0 : bar1, x, xg, gran, g0,
-                         (dbg & 1) ? 0 : __ldg(gran_off + wn + 1) - g0, M, ncols, al16);
-            const int64_t cn_end = min(nchunks, (wn + 1) * span);
-            ma = chunk_meta(wn * span + warp, cn_end, off8);
-            mb = chunk_meta(wn * span + warp + kWinWarps, cn_end, off8);
+                                      __ldg(gran_off + wn + 1) - g0, M, ncols, al16);
         }
+        const int64_t c_end = min(nchunks, (w + 1) * span);
+        int64_t c = w * span + warp;
+        ChunkRegs a, b;
+        chunk_issue<UNI>(a, chunk_meta(c, c_end, off8), lc8, lrow, deff_p, lane);
+        chunk_issue<UNI>(b, chunk_meta(c + kWinWarps, c_end, off8), lc8, lrow, deff_p, lane);
         mbar_wait((it & 1) ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
         const double* cur = sx + (it & 1) * stage_doubles;
         double* sy = sy0 + (it & 1) * sigma;
-        if (!(dbg & 2)) {
-        chunk_finish<UNI>(a, cur, sy, lc8, chunk_off, val, s, uni_a, lane, acc);
-        chunk_finish<UNI>(b, cur, sy, lc8, chunk_off, val, s, uni_a, lane, acc);
-        }
-        const int64_t c_end = min(nchunks, (w + 1) * span);
-        for (int64_t c = w * span + warp + 2 * kWinWarps; c < c_end; c += kWinWarps) {     // sigma > 2048
-            chunk_issue<UNI>(a, chunk_meta(c, c_end, off8), lc8, lrow, deff_p, lane);
+        for (;;) {
+            c += 2 * kWinWarps;
+            const ChunkMeta ma = chunk_meta(c, c_end, off8), mb = chunk_meta(c + kWinWarps, c_end, off8);
             chunk_finish<UNI>(a, cur, sy, lc8, chunk_off, val, s, uni_a, lane, acc);
-        }
-        if (!(dbg & 8)) {
-        chunk_issue<UNI>(a, ma, lc8, lrow, deff_p, lane);
-        chunk_issue<UNI>(b, mb, lc8, lrow, deff_p, lane);
+            chunk_finish<UNI>(b, cur, sy, lc8, chunk_off, val, s, uni_a, lane, acc);
+            if (ma.c < 0) break;
+            chunk_issue<UNI>(a, ma, lc8, lrow, deff_p, lane);
+            chunk_issue<UNI>(b, mb, lc8, lrow, deff_p, lane);
         }
         __syncthreads();                                  // sy is complete; this stage may be overwritten from now on
-        if (!(dbg & 32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ... by bulk copies (async proxy) as well
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ... by bulk copies (async proxy) as well
         const int64_t r0 = w * sigma;
         const int rows = (int)min((int64_t)sigma, (int64_t)M - r0);
-        if (!(dbg & 16)) for (int t = threadIdx.x; t < rows; t += kWinThreads) y[r0 + t] = sy[t];
+        for (int t = threadIdx.x; t < rows; t += kWinThreads) y[r0 + t] = sy[t];
     }
     // CTA sum in warp order; the bookkeeping tail is written for kThreads threads, so the upper warps leave first
     acc = warp_sum(acc);
@@ -279,9 +269,10 @@ spmv_sellw_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __rest
     fin_tail(fin, partials, red);
 }
 
-// The same with two CTAs of 16 warps per SM, each with ONE stage of x and one buffer for y: a CTA's phases (stage
-// the window, fetch the indices, gather out of shared memory, write y) follow each other, and the two CTAs of an
-// SM fill each other's waits.  Needs (granules * 256 + sigma * 8) bytes twice per SM.
+// Two CTAs of 16 warps per SM, each with ONE stage of x and one buffer for y: a CTA's phases (stage the window,
+// fetch the indices, gather out of shared memory, write y) follow each other, and the two CTAs of an SM fill each
+// other's waits.  Windows are dealt round-robin over the CTAs (neighbouring CTAs work on neighbouring windows: what
+// they stage overlaps and comes out of L2).  Needs (granules * 256 + sigma * 8) bytes twice per SM.
 constexpr int kWin2Threads = 512;
 constexpr int kWin2Warps = kWin2Threads / 32;
 
@@ -574,8 +565,6 @@ int launch_spmv_windowed(lz_op* op, const int32_t* win_list, int nlist, const do
     const int64_t nitems = win_list ? (int64_t)nlist : sl.win_count;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nitems, (int64_t)ctx->sms));
     const int stage_doubles = sl.win_maxg * 32 + 2;
-    const char* dbg_env = getenv("LZ_SELLW_DEBUG");
-    const int dbg = dbg_env ? atoi(dbg_env) : 0;
     const char* var_env = getenv("LZ_SELLW_VARIANT");
     const size_t smem2 = ((size_t)stage_doubles + (size_t)sl.sigma) * sizeof(double);
     const bool two_ctas = smem2 <= kWinSmemMax / 2 - 1024 && !(var_env && var_env[0] == '1');
@@ -598,13 +587,13 @@ int launch_spmv_windowed(lz_op* op, const int32_t* win_list, int nlist, const do
                          (const uint4*)sl.win_lcol, (const int64_t*)sl.win_off8, sl.val, (const uint32_t*)sl.win_lrow, x,
                          scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, (int32_t)op->ncols, sl.win_span, ft,
                          win_list, nlist, sl.win_count, flag_dev, (const double*)sl.win_deff, sl.uni_a,
-                         (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles, dbg));
+                         (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles));
     else
         LZ_CUDA(launch_k(spmv_sellw_dot_kernel<false>, dim3(grid), dim3(kWinThreads), sl.win_smem, stream, sl.chunk_off,
                          (const uint4*)sl.win_lcol, (const int64_t*)sl.win_off8, sl.val, (const uint32_t*)sl.win_lrow, x,
                          scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, (int32_t)op->ncols, sl.win_span, ft,
                          win_list, nlist, sl.win_count, flag_dev, (const double*)nullptr, 0.0,
-                         (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles, dbg));
+                         (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles));
     if (grid_out) *grid_out = grid;
     return LZ_OK;
 }

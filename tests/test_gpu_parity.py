@@ -1077,9 +1077,19 @@ def test_windowed_sell_form(lz, monkeypatch):
         op = engine.DeviceOperator.from_scipy(ctx, A, fmt="sell")
         assert 0 < op.windowed() <= 448, op.windowed()
         assert op.value_free() == (k == "G")
-        y = op.apply_host(x)
-        assert np.array_equal(y, plain[k].apply_host(x)), k
-        assert np.max(np.abs(y - A * x)) <= 4e-15 * np.max(np.abs(A * x))
+        for variant in ("0", "1"):          # two CTAs per SM with one stage each / one CTA with two stages (the fallback)
+            monkeypatch.setenv("LZ_SELLW_VARIANT", variant)
+            y = op.apply_host(x)
+            assert np.array_equal(y, plain[k].apply_host(x)), (k, variant)
+            assert np.max(np.abs(y - A * x)) <= 4e-15 * np.max(np.abs(A * x))
+            # a vector that is only 8-byte aligned (odd rows of a basis with an odd row length): no bulk copies
+            import torch
+            buf = torch.zeros(M + 1, dtype=torch.float64, device=ctx.torch_device)
+            buf[1:] = torch.from_numpy(x).to(ctx.torch_device)
+            assert buf[1:].data_ptr() % 16 == 8
+            y8 = op.apply(buf[1:]).cpu().numpy()
+            assert np.array_equal(y8, y), (k, variant)
+        monkeypatch.setenv("LZ_SELLW_VARIANT", "0")
         assert (op.export_csr() != A).nnz == 0
     # smaller sorting windows (8 chunks: half of the kernel's warps idle) and one that is no multiple of 8 chunks
     for sigma in (256, 96):
@@ -1093,10 +1103,12 @@ def test_windowed_sell_form(lz, monkeypatch):
     assert np.max(np.abs(fop.apply_host(x) - far * x)) <= 4e-15 * np.max(np.abs(far * x))
     # the loop (alpha from the windowed kernel's partial sums, bookkeeping tail run by its first 8 warps)
     ref = orc.lanczos(G, 30, seed=5)
-    L = lz.IrrLanczos(G)
-    L.execute_LanczosOld(30, seed=5)
-    assert L._device_op.windowed() > 0
-    assert rel(np.diag(L.H_eff), ref["alpha"]) < TOL_AB and rel(np.diag(L.H_eff, 1), ref["beta"]) < TOL_AB
-    first = L.H_eff.copy()
-    L.execute_LanczosOld(30, seed=5)
-    assert np.array_equal(first, L.H_eff)
+    for variant in ("0", "1"):
+        monkeypatch.setenv("LZ_SELLW_VARIANT", variant)
+        L = lz.IrrLanczos(G)
+        L.execute_LanczosOld(30, seed=5)
+        assert L._device_op.windowed() > 0
+        assert rel(np.diag(L.H_eff), ref["alpha"]) < TOL_AB and rel(np.diag(L.H_eff, 1), ref["beta"]) < TOL_AB
+        first = L.H_eff.copy()
+        L.execute_LanczosOld(30, seed=5)
+        assert np.array_equal(first, L.H_eff)
