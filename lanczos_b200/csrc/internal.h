@@ -87,6 +87,7 @@ struct lz_sell {
     void* win_lcol = nullptr;          // device, 16-bit stage indices in blocks of [32 lanes][8 entries]
     int64_t* win_off8 = nullptr;       // device, nchunks + 1: first block of each chunk
     int64_t win_blocks = 0;
+    int win_banked = 0;                // entries of a row stored in the bank-aware order (value-free form)
     void* win_lrow = nullptr;          // device, nchunks*32 x uint32: row inside its window | stage index of x[row] << 16
     double* win_deff = nullptr;        // device, nchunks*32: deff in (chunk, lane) order (value-free form)
 };

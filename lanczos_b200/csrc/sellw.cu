@@ -456,6 +456,102 @@ sellw_setup_kernel(const int64_t* __restrict__ chunk_off, const int32_t* __restr
     }
 }
 
+// Bank-aware order of a row's entries (value-free form only: the stored values of a weighted operator stay in the
+// SELL order).  A gather of 16 lanes x 8 bytes is one pass through shared memory when the 16 addresses fall into 16
+// different 8-byte banks (stage index mod 16); with the entries in column order it takes ~3.1 passes (random
+// banks).  Per half-chunk (16 rows, S = 8 or 16 slots): slot by slot, a maximum bipartite matching lanes -> banks
+// (augmenting paths) over the entries not placed yet picks one entry per lane with pairwise different banks; a
+// lane that stays unmatched takes the zero slot if it can still afford to (S minus its row length spare slots),
+// else its entry from the least loaded bank.  Simulated on random banks: 1.6 passes per slot.  One thread per
+// half-chunk; rows longer than 16 entries keep their order.  The sums of a row are then added in a different
+// (fixed) order than in the plain kernel: y differs from it by rounding.
+__global__ void __launch_bounds__(kThreads)
+sellw_bank_kernel(const int64_t* __restrict__ off8, const int32_t* __restrict__ gran_off, int64_t nchunks, int span,
+                  uint16_t* __restrict__ lc8) {
+    const int64_t h = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t c = h >> 1;
+    if (c >= nchunks) return;
+    const int half = (int)(h & 1);
+    const int64_t w = c / span;
+    const int ng = gran_off[w + 1] - gran_off[w];
+    if (ng == 0) return;                                   // a window that stays with the plain kernel
+    const uint16_t zero_slot = (uint16_t)(ng * 32);
+    const int64_t b0 = off8[c];
+    const int nb = (int)(off8[c + 1] - b0);
+    if (nb < 1 || nb > 2) return;
+    const int S = nb * 8;
+    uint16_t ent[16][16];
+    int cnt[16];
+    auto at = [&](int l, int k) -> uint16_t& { return lc8[((b0 + (k >> 3)) * 32 + (half * 16 + l)) * 8 + (k & 7)]; };
+    for (int l = 0; l < 16; ++l) {
+        int n = 0;
+        for (int k = 0; k < S; ++k) {
+            const uint16_t v = at(l, k);
+            if (v != zero_slot) ent[l][n++] = v;
+        }
+        cnt[l] = n;
+    }
+    for (int k = 0; k < S; ++k) {
+        uint32_t avail[16];
+        int owner[16];
+        for (int l = 0; l < 16; ++l) {
+            uint32_t m = 0;
+            for (int i = 0; i < cnt[l]; ++i) m |= 1u << (ent[l][i] & 15);
+            avail[l] = m;
+            owner[l] = -1;
+        }
+        for (int l0 = 0; l0 < 16; ++l0) {
+            if (cnt[l0] == 0) continue;
+            int st_l[17], st_b[17];
+            uint32_t st_m[17];
+            uint32_t visited = 0;
+            int depth = 0;
+            st_l[0] = l0;
+            st_m[0] = avail[l0];
+            while (depth >= 0) {
+                const uint32_t m = st_m[depth] & ~visited;
+                if (!m) { --depth; continue; }
+                const int b = __ffs(m) - 1;
+                visited |= 1u << b;
+                st_m[depth] = m & ~(1u << b);
+                st_b[depth] = b;
+                if (owner[b] < 0) {
+                    for (int d = depth; d >= 0; --d) owner[st_b[d]] = st_l[d];
+                    break;
+                }
+                if (depth + 1 < 17) {
+                    ++depth;
+                    st_l[depth] = owner[b];
+                    st_m[depth] = avail[owner[b]];
+                }
+            }
+        }
+        int bank_of[16], load[16];
+        for (int l = 0; l < 16; ++l) { bank_of[l] = -1; load[l] = 0; }
+        for (int b = 0; b < 16; ++b)
+            if (owner[b] >= 0) { bank_of[owner[b]] = b; load[b] = 1; }
+        for (int l = 0; l < 16; ++l) {
+            int pick = -1;
+            if (bank_of[l] >= 0) {
+                for (int i = 0; i < cnt[l]; ++i)
+                    if ((ent[l][i] & 15) == bank_of[l]) { pick = i; break; }
+            } else if (cnt[l] >= S - k) {                  // no spare slot left: the entry from the least loaded bank
+                int best = 1 << 30;
+                for (int i = 0; i < cnt[l]; ++i)
+                    if (load[ent[l][i] & 15] < best) { best = load[ent[l][i] & 15]; pick = i; }
+                if (pick >= 0) ++load[ent[l][pick] & 15];
+            }
+            uint16_t v = zero_slot;
+            if (pick >= 0) {
+                v = ent[l][pick];
+                ent[l][pick] = ent[l][cnt[l] - 1];
+                --cnt[l];
+            }
+            at(l, k) = v;
+        }
+    }
+}
+
 int sellw_build(lz_op* op) {
     // read per call: LZ_SELL_WINDOW=0 keeps the plain kernel, LZ_SELL_WINDOW_MIN overrides the smallest number of
     // windows the form is built for (tests build small operators)
@@ -521,6 +617,11 @@ int sellw_build(lz_op* op) {
     if (e2 == cudaSuccess) {
         sellw_setup_kernel<false><<<(unsigned)nwin, kThreads, 0, q>>>(sl.chunk_off, sl.col, sl.row_of, sl.deff, sl.nchunks, span,
                                                                     nullptr, gcount, gran, off8, lc8, lrow, deff_p);
+        const char* env_banks = getenv("LZ_SELLW_BANKS");
+        if (sl.uniform && !(env_banks && env_banks[0] == '0')) {
+            sellw_bank_kernel<<<(unsigned)((2 * sl.nchunks + kThreads - 1) / kThreads), kThreads, 0, q>>>(off8, gcount, sl.nchunks, span, lc8);
+            sl.win_banked = 1;
+        }
         e2 = cudaStreamSynchronize(q);
         if (e2 == cudaSuccess) e2 = cudaGetLastError();
     }

@@ -1073,6 +1073,15 @@ def test_windowed_sell_form(lz, monkeypatch):
     assert plain["G"].windowed() == 0 and plain["G"].value_free()
     monkeypatch.setenv("LZ_SELL_WINDOW", "1")
     monkeypatch.setenv("LZ_SELL_WINDOW_MIN", "1")
+    # value-free operators store a row's entries in a bank-aware order (fewer shared-memory conflicts): same sums
+    # up to rounding, in a fixed order
+    bop = engine.DeviceOperator.from_scipy(ctx, G, fmt="sell")
+    assert bop.windowed() > 0 and bop.value_free()
+    yb = bop.apply_host(x)
+    assert np.max(np.abs(yb - G * x)) <= 4e-15 * np.max(np.abs(G * x))
+    assert np.array_equal(yb, bop.apply_host(x))
+    assert (bop.export_csr() != G).nnz == 0
+    monkeypatch.setenv("LZ_SELLW_BANKS", "0")             # entries in column order: bit-identical to the plain kernel
     for k, A in (("G", G), ("W", W)):
         op = engine.DeviceOperator.from_scipy(ctx, A, fmt="sell")
         assert 0 < op.windowed() <= 448, op.windowed()
@@ -1091,6 +1100,7 @@ def test_windowed_sell_form(lz, monkeypatch):
             assert np.array_equal(y8, y), (k, variant)
         monkeypatch.setenv("LZ_SELLW_VARIANT", "0")
         assert (op.export_csr() != A).nnz == 0
+    monkeypatch.delenv("LZ_SELLW_BANKS")
     # smaller sorting windows (8 chunks: half of the kernel's warps idle) and one that is no multiple of 8 chunks
     for sigma in (256, 96):
         op = engine.DeviceOperator.from_scipy(ctx, G, fmt="sell", sigma=sigma)
