@@ -651,7 +651,7 @@ def main():
         # windowed form (csrc/sellw.cu): 16-bit offsets into a shared-memory stage of x, 2 B less per entry
         windowed = solver.windowed_local() if world > 1 else solver._device_op.windowed()
         idx_bytes = 2.0 if windowed else 4.0
-        apply_bytes = (idx_bytes * nnz_true + 24.0 * N) if value_free else ((8.0 + idx_bytes) * nnz_true + 16.0 * N)
+        apply_bytes = (idx_bytes * nnz_true + 24.0 * N) if value_free else (12.0 * nnz_true + 16.0 * N)
     per_kernel = {}
     # K3 reads w, v_j, v_{j-1}, writes r; KB (recompute) reads v_j, v_{j-1}, writes r and applies H again
     update_bytes = 24.0 * N if recompute else 32.0 * N
@@ -806,7 +806,7 @@ def main():
         line["config"]["spmv_bytes"] = (f"{ib}*nnz + 24*N: every off-diagonal entry of the operator is equal, so the kernel reads column "
                                         f"indices only{' (16-bit offsets into the staged window of x)' if windowed else ''} "
                                         "(SURVEY 8d's 12*nnz + 16*N would be %.3f GB per launch)" % ((12.0 * nnz_true + 16.0 * N) / 1e9)
-                                        ) if value_free else f"{8 + ib}*nnz + 16*N" + ("" if windowed else " (SURVEY 8d)")
+                                        ) if value_free else "12*nnz + 16*N (SURVEY 8d)"
         line["config"]["nnz_per_gpu"] = int(nnz_true)
         line["config"]["sell_stored_over_true"] = float(nnz_stored) / max(1, nnz_true)
     if rank == 0:

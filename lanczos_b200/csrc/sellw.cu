@@ -13,10 +13,12 @@
 //       2 instead of 4 bytes per stored entry from HBM, and no gather reaches L1.  The indices are stored in blocks
 //       of [32 lanes][8 entries], so a lane fetches 8 of them with one 16-byte load; a chunk's width is padded to a
 //       multiple of 8 with indices of a slot that holds 0.0;
-//   (3) x[row] comes out of the stage too (the set-up adds the rows' own granules), the diagonal coefficients of
-//       the value-free form are stored in (chunk, lane) order, and the window's y (consecutive rows) is collected
+//   (3) x[row] comes out of the stage too (the set-up adds the rows' own granules), the diagonal coefficients
+//       are stored in (chunk, lane) order, and the window's y (consecutive rows) is collected
 //       in shared memory and written out coalesced.
-// The per-row summation order is the one of spmv_sell_dot_kernel, so y is bit-identical to it.
+// Value-free operators only (every off-diagonal entry equal, spmv.cu: sell_detect_uniform): the kernel reads no
+// values.  With LZ_SELLW_BANKS=0 the per-row summation order is the one of spmv_sell_dot_kernel and y is
+// bit-identical to it; by default a row's entries are stored in a bank-aware order (sellw_bank_kernel).
 //
 // Built at operator creation when every window's granule set fits (sellw_build); otherwise the operator keeps the
 // plain kernel.  LZ_SELL_WINDOW=0 turns the form off.
@@ -116,7 +118,6 @@ __device__ __forceinline__ ChunkMeta chunk_meta(int64_t c, int64_t c_end, const 
     return m;
 }
 
-template <bool UNI>
 __device__ __forceinline__ void chunk_issue(ChunkRegs& r, const ChunkMeta& m, const uint4* __restrict__ lc8,
                                             const uint32_t* __restrict__ lrow, const double* __restrict__ deff_p,
                                             int lane) {
@@ -127,54 +128,32 @@ __device__ __forceinline__ void chunk_issue(ChunkRegs& r, const ChunkMeta& m, co
     r.nb = m.nb;
     const uint4* p = lc8 + (int64_t)m.b0 * 32 + lane;
     r.rr = __ldg(lrow + c * 32 + lane);
-    r.dd = UNI ? __ldg(deff_p + c * 32 + lane) : 0.0;
+    r.dd = __ldg(deff_p + c * 32 + lane);
     r.q0 = r.nb > 0 ? ld_stream_u4(p) : make_uint4(0, 0, 0, 0);
     r.q1 = r.nb > 1 ? ld_stream_u4(p + 32) : make_uint4(0, 0, 0, 0);
 }
 
-// 8 entries: sum += [v *] stage[index], in entry order (the low half of a word is the earlier entry)
-template <bool UNI>
-__device__ __forceinline__ void add8(double& sum, const uint4 q, const double* sx, const double* __restrict__ pv, int left) {
+// 8 entries: sum += stage[index], in entry order (the low half of a word is the earlier entry)
+__device__ __forceinline__ void add8(double& sum, const uint4 q, const double* sx) {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-    if (UNI) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            sum += sx[w[i] & 0xffffu];
-            sum += sx[w[i] >> 16];
-        }
-    } else {
-        double vv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) vv[j] = j < left ? ld_stream1(pv + j * 32) : 0.0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            sum = fma(vv[2 * i], sx[w[i] & 0xffffu], sum);
-            sum = fma(vv[2 * i + 1], sx[w[i] >> 16], sum);
-        }
+    for (int i = 0; i < 4; ++i) {
+        sum += sx[w[i] & 0xffffu];
+        sum += sx[w[i] >> 16];
     }
 }
 
-template <bool UNI>
 __device__ __forceinline__ void chunk_finish(const ChunkRegs& r, const double* sx, double* sy,
-                                             const uint4* __restrict__ lc8, const int64_t* __restrict__ chunk_off, const double* __restrict__ val,
-                                             double s, double uni_a, int lane, double& acc) {
+                                             const uint4* __restrict__ lc8, double s, double uni_a, int lane,
+                                             double& acc) {
     if (r.c < 0) return;
-    const int64_t c = r.c;
     double sum = 0.0;
-    const double* pv = nullptr;
-    int width = 0;
-    if (!UNI) {
-        const int64_t o0 = __ldg(chunk_off + c);
-        width = (int)((__ldg(chunk_off + c + 1) - o0) >> 5);
-        pv = val + o0 + lane;
-    }
-    if (r.nb > 0) add8<UNI>(sum, r.q0, sx, pv, width);
-    if (r.nb > 1) add8<UNI>(sum, r.q1, sx, pv + 8 * 32, width - 8);
-    for (int b = 2; b < r.nb; ++b)
-        add8<UNI>(sum, ld_stream_u4(lc8 + ((int64_t)r.b0 + b) * 32 + lane), sx, pv + b * 8 * 32, width - 8 * b);
+    if (r.nb > 0) add8(sum, r.q0, sx);
+    if (r.nb > 1) add8(sum, r.q1, sx);
+    for (int b = 2; b < r.nb; ++b) add8(sum, ld_stream_u4(lc8 + ((int64_t)r.b0 + b) * 32 + lane), sx);
     if (r.rr != 0xffffffffu) {
         const double xr = sx[r.rr >> 16];
-        if (UNI) sum = fma(uni_a, sum, r.dd * xr);
+        sum = fma(uni_a, sum, r.dd * xr);
         const double yi = s * sum;
         sy[r.rr & 0xffffu] = yi;
         acc = fma(yi, s * xr, acc);
@@ -186,10 +165,8 @@ __device__ __forceinline__ void chunk_finish(const ChunkRegs& r, const double* s
 // for the window's y; the copies of window i + 1 are in flight while window i is computed.  Measured on the
 // config-4 graph: 1.11 ms per apply against 0.98 ms for the two-CTA form (plain SELL kernel: 1.55 ms) - with one
 // CTA nothing fills the waits between the phases of a window.  LZ_SELLW_VARIANT=1 forces this form.
-template <bool UNI>
 __global__ void __launch_bounds__(kWinThreads, 1)
-spmv_sellw_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __restrict__ lc8,
-                      const int64_t* __restrict__ off8, const double* __restrict__ val,
+spmv_sellw_dot_kernel(const uint4* __restrict__ lc8, const int64_t* __restrict__ off8,
                       const uint32_t* __restrict__ lrow, const double* __restrict__ x,
                       const double* __restrict__ scale, double* __restrict__ y, int64_t nchunks,
                       double* __restrict__ partials, const double* __restrict__ xg, int32_t M, int32_t ncols, int span,
@@ -235,19 +212,19 @@ spmv_sellw_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __rest
         const int64_t c_end = min(nchunks, (w + 1) * span);
         int64_t c = w * span + warp;
         ChunkRegs a, b;
-        chunk_issue<UNI>(a, chunk_meta(c, c_end, off8), lc8, lrow, deff_p, lane);
-        chunk_issue<UNI>(b, chunk_meta(c + kWinWarps, c_end, off8), lc8, lrow, deff_p, lane);
+        chunk_issue(a, chunk_meta(c, c_end, off8), lc8, lrow, deff_p, lane);
+        chunk_issue(b, chunk_meta(c + kWinWarps, c_end, off8), lc8, lrow, deff_p, lane);
         mbar_wait((it & 1) ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
         const double* cur = sx + (it & 1) * stage_doubles;
         double* sy = sy0 + (it & 1) * sigma;
         for (;;) {
             c += 2 * kWinWarps;
             const ChunkMeta ma = chunk_meta(c, c_end, off8), mb = chunk_meta(c + kWinWarps, c_end, off8);
-            chunk_finish<UNI>(a, cur, sy, lc8, chunk_off, val, s, uni_a, lane, acc);
-            chunk_finish<UNI>(b, cur, sy, lc8, chunk_off, val, s, uni_a, lane, acc);
+            chunk_finish(a, cur, sy, lc8, s, uni_a, lane, acc);
+            chunk_finish(b, cur, sy, lc8, s, uni_a, lane, acc);
             if (ma.c < 0) break;
-            chunk_issue<UNI>(a, ma, lc8, lrow, deff_p, lane);
-            chunk_issue<UNI>(b, mb, lc8, lrow, deff_p, lane);
+            chunk_issue(a, ma, lc8, lrow, deff_p, lane);
+            chunk_issue(b, mb, lc8, lrow, deff_p, lane);
         }
         __syncthreads();                                  // sy is complete; this stage may be overwritten from now on
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ... by bulk copies (async proxy) as well
@@ -276,10 +253,8 @@ spmv_sellw_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __rest
 constexpr int kWin2Threads = 512;
 constexpr int kWin2Warps = kWin2Threads / 32;
 
-template <bool UNI>
 __global__ void __launch_bounds__(kWin2Threads, 2)
-spmv_sellw2_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __restrict__ lc8,
-                       const int64_t* __restrict__ off8, const double* __restrict__ val,
+spmv_sellw2_dot_kernel(const uint4* __restrict__ lc8, const int64_t* __restrict__ off8,
                        const uint32_t* __restrict__ lrow, const double* __restrict__ x,
                        const double* __restrict__ scale, double* __restrict__ y, int64_t nchunks,
                        double* __restrict__ partials, const double* __restrict__ xg, int32_t M, int32_t ncols, int span,
@@ -316,8 +291,8 @@ spmv_sellw2_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __res
         const int64_t c_end = min(nchunks, (w + 1) * span);
         int64_t c = w * span + warp;
         ChunkRegs a, b;
-        chunk_issue<UNI>(a, chunk_meta(c, c_end, off8), lc8, lrow, deff_p, lane);
-        chunk_issue<UNI>(b, chunk_meta(c + kWin2Warps, c_end, off8), lc8, lrow, deff_p, lane);
+        chunk_issue(a, chunk_meta(c, c_end, off8), lc8, lrow, deff_p, lane);
+        chunk_issue(b, chunk_meta(c + kWin2Warps, c_end, off8), lc8, lrow, deff_p, lane);
         const int64_t w_cur = w;
         const int64_t sn = si + gridDim.x;
         if (sn < nitems) {
@@ -329,11 +304,11 @@ spmv_sellw2_dot_kernel(const int64_t* __restrict__ chunk_off, const uint4* __res
         for (;;) {
             c += 2 * kWin2Warps;
             const ChunkMeta ma = chunk_meta(c, c_end, off8), mb = chunk_meta(c + kWin2Warps, c_end, off8);
-            chunk_finish<UNI>(a, sx, sy, lc8, chunk_off, val, s, uni_a, lane, acc);
-            chunk_finish<UNI>(b, sx, sy, lc8, chunk_off, val, s, uni_a, lane, acc);
+            chunk_finish(a, sx, sy, lc8, s, uni_a, lane, acc);
+            chunk_finish(b, sx, sy, lc8, s, uni_a, lane, acc);
             if (ma.c < 0) break;
-            chunk_issue<UNI>(a, ma, lc8, lrow, deff_p, lane);
-            chunk_issue<UNI>(b, mb, lc8, lrow, deff_p, lane);
+            chunk_issue(a, ma, lc8, lrow, deff_p, lane);
+            chunk_issue(b, mb, lc8, lrow, deff_p, lane);
         }
         __syncthreads();                                  // sy is complete, the stage is free
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -561,6 +536,9 @@ int sellw_build(lz_op* op) {
     lz_ctx* ctx = op->ctx;
     lz_sell& sl = op->sell;
     if (off || op->kind != LZ_OP_SELL || sl.nchunks == 0 || sl.nnz_stored == 0 || sl.sigma % 32 != 0 || sl.sigma > 8192) return LZ_OK;
+    // value-free operators only: with stored values the plain kernel already runs at 73 % of the copy peak on the
+    // config-4 graph (1.92 ms); this form with the values fetched in SELL order measured 2.08 ms
+    if (!sl.uniform) return LZ_OK;
     const int span = sl.sigma / 32;
     const int64_t nwin = (sl.nchunks + span - 1) / span;
     // a window per CTA only pays when there are enough of them to fill the machine a few times over
@@ -612,23 +590,21 @@ int sellw_build(lz_op* op) {
     if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&gran, (size_t)std::max<int64_t>(total, 4) * 4);
     if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&lc8, (size_t)std::max<int64_t>(blocks, 1) * 256 * 2);
     if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&lrow, (size_t)sl.nchunks * 32 * 4);
-    if (e2 == cudaSuccess && sl.uniform) e2 = cudaMalloc((void**)&deff_p, (size_t)sl.nchunks * 32 * 8);
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&deff_p, (size_t)sl.nchunks * 32 * 8);
     if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(gcount, h.data(), (size_t)(nwin + 1) * 4, cudaMemcpyHostToDevice, q);
     if (e2 == cudaSuccess) {
         sellw_setup_kernel<false><<<(unsigned)nwin, kThreads, 0, q>>>(sl.chunk_off, sl.col, sl.row_of, sl.deff, sl.nchunks, span,
                                                                     nullptr, gcount, gran, off8, lc8, lrow, deff_p);
         const char* env_banks = getenv("LZ_SELLW_BANKS");
-        if (sl.uniform && !(env_banks && env_banks[0] == '0')) {
+        if (!(env_banks && env_banks[0] == '0')) {
             sellw_bank_kernel<<<(unsigned)((2 * sl.nchunks + kThreads - 1) / kThreads), kThreads, 0, q>>>(off8, gcount, sl.nchunks, span, lc8);
             sl.win_banked = 1;
         }
         e2 = cudaStreamSynchronize(q);
         if (e2 == cudaSuccess) e2 = cudaGetLastError();
     }
-    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(spmv_sellw_dot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmemMax);
-    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(spmv_sellw_dot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmemMax);
-    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(spmv_sellw2_dot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kWinSmemMax / 2));
-    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(spmv_sellw2_dot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kWinSmemMax / 2));
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(spmv_sellw_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmemMax);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(spmv_sellw2_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kWinSmemMax / 2));
     if (e2 != cudaSuccess) {
         cudaGetLastError();
         if (gran) cudaFree(gran);
@@ -671,30 +647,18 @@ int launch_spmv_windowed(lz_op* op, const int32_t* win_list, int nlist, const do
     const bool two_ctas = smem2 <= kWinSmemMax / 2 - 1024 && !(var_env && var_env[0] == '1');
     if (two_ctas) {
         grid = (int)std::max<int64_t>(1, std::min<int64_t>(nitems, (int64_t)ctx->sms * 2));
-        if (sl.uniform)
-            LZ_CUDA(launch_k(spmv_sellw2_dot_kernel<true>, dim3(grid), dim3(kWin2Threads), smem2, stream, sl.chunk_off,
-                             (const uint4*)sl.win_lcol, (const int64_t*)sl.win_off8, sl.val, (const uint32_t*)sl.win_lrow, x,
-                             scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, (int32_t)op->ncols, sl.win_span, ft,
-                             win_list, nlist, sl.win_count, flag_dev, (const double*)sl.win_deff, sl.uni_a,
-                             (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles));
-        else
-            LZ_CUDA(launch_k(spmv_sellw2_dot_kernel<false>, dim3(grid), dim3(kWin2Threads), smem2, stream, sl.chunk_off,
-                             (const uint4*)sl.win_lcol, (const int64_t*)sl.win_off8, sl.val, (const uint32_t*)sl.win_lrow, x,
-                             scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, (int32_t)op->ncols, sl.win_span, ft,
-                             win_list, nlist, sl.win_count, flag_dev, (const double*)nullptr, 0.0,
-                             (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles));
-    } else if (sl.uniform)
-        LZ_CUDA(launch_k(spmv_sellw_dot_kernel<true>, dim3(grid), dim3(kWinThreads), sl.win_smem, stream, sl.chunk_off,
-                         (const uint4*)sl.win_lcol, (const int64_t*)sl.win_off8, sl.val, (const uint32_t*)sl.win_lrow, x,
-                         scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, (int32_t)op->ncols, sl.win_span, ft,
-                         win_list, nlist, sl.win_count, flag_dev, (const double*)sl.win_deff, sl.uni_a,
-                         (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles));
-    else
-        LZ_CUDA(launch_k(spmv_sellw_dot_kernel<false>, dim3(grid), dim3(kWinThreads), sl.win_smem, stream, sl.chunk_off,
-                         (const uint4*)sl.win_lcol, (const int64_t*)sl.win_off8, sl.val, (const uint32_t*)sl.win_lrow, x,
-                         scale_dev, y, sl.nchunks, partials, op->xghost, (int32_t)op->M, (int32_t)op->ncols, sl.win_span, ft,
-                         win_list, nlist, sl.win_count, flag_dev, (const double*)nullptr, 0.0,
-                         (const int32_t*)sl.win_gran_off, (const int32_t*)sl.win_gran, stage_doubles));
+        LZ_CUDA(launch_k(spmv_sellw2_dot_kernel, dim3(grid), dim3(kWin2Threads), smem2, stream, (const uint4*)sl.win_lcol,
+                         (const int64_t*)sl.win_off8, (const uint32_t*)sl.win_lrow, x, scale_dev, y, sl.nchunks, partials,
+                         op->xghost, (int32_t)op->M, (int32_t)op->ncols, sl.win_span, ft, win_list, nlist, sl.win_count,
+                         flag_dev, (const double*)sl.win_deff, sl.uni_a, (const int32_t*)sl.win_gran_off,
+                         (const int32_t*)sl.win_gran, stage_doubles));
+    } else {
+        LZ_CUDA(launch_k(spmv_sellw_dot_kernel, dim3(grid), dim3(kWinThreads), sl.win_smem, stream, (const uint4*)sl.win_lcol,
+                         (const int64_t*)sl.win_off8, (const uint32_t*)sl.win_lrow, x, scale_dev, y, sl.nchunks, partials,
+                         op->xghost, (int32_t)op->M, (int32_t)op->ncols, sl.win_span, ft, win_list, nlist, sl.win_count,
+                         flag_dev, (const double*)sl.win_deff, sl.uni_a, (const int32_t*)sl.win_gran_off,
+                         (const int32_t*)sl.win_gran, stage_doubles));
+    }
     if (grid_out) *grid_out = grid;
     return LZ_OK;
 }

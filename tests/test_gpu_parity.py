@@ -1057,50 +1057,50 @@ def test_value_free_sell_for_unweighted_graph_laplacians(lz):
 
 
 def test_windowed_sell_form(lz, monkeypatch):
-    """csrc/sellw.cu: when the columns every sorting window refers to fit a shared-memory stage, x is staged there
-    and the stored column indices are 16-bit offsets.  Same summation order per row as the plain SELL kernel, so y
-    is bit-identical to it - value-free and weighted operators, ragged rows, a last window that is not full; an
-    operator whose windows do not fit keeps the plain kernel; the loop gives the oracle's alpha/beta."""
+    """csrc/sellw.cu: when the columns every sorting window of a value-free operator refers to fit a shared-memory
+    stage, x is staged there and the stored column indices are 16-bit offsets.  With the entries in column order
+    (LZ_SELLW_BANKS=0) the summation order per row is the plain SELL kernel's and y is bit-identical to it; by
+    default a row's entries are stored in a bank-aware order (same sums up to rounding, fixed order).  Ragged rows,
+    a last window that is not full, vectors that are only 8-byte aligned, both kernel variants; weighted operators
+    and operators whose windows do not fit keep the plain kernel; the loop gives the oracle's alpha/beta."""
+    import torch
     from lanczos_b200 import engine
     ctx = engine.Context.default()
     M = 40_037
     G = orc.banded_graph_laplacian(M, seed=3)
-    W = sp.csr_matrix(G.copy())
-    W.data = W.data * (1.0 + 0.01 * (np.arange(W.nnz) % 89))
     x = np.random.RandomState(0).uniform(-1, 1, M)
     monkeypatch.setenv("LZ_SELL_WINDOW", "0")
-    plain = {k: engine.DeviceOperator.from_scipy(ctx, A, fmt="sell") for k, A in (("G", G), ("W", W))}
-    assert plain["G"].windowed() == 0 and plain["G"].value_free()
+    plain = engine.DeviceOperator.from_scipy(ctx, G, fmt="sell")
+    assert plain.windowed() == 0 and plain.value_free()
+    y_plain = plain.apply_host(x)
     monkeypatch.setenv("LZ_SELL_WINDOW", "1")
     monkeypatch.setenv("LZ_SELL_WINDOW_MIN", "1")
-    # value-free operators store a row's entries in a bank-aware order (fewer shared-memory conflicts): same sums
-    # up to rounding, in a fixed order
-    bop = engine.DeviceOperator.from_scipy(ctx, G, fmt="sell")
-    assert bop.windowed() > 0 and bop.value_free()
-    yb = bop.apply_host(x)
-    assert np.max(np.abs(yb - G * x)) <= 4e-15 * np.max(np.abs(G * x))
-    assert np.array_equal(yb, bop.apply_host(x))
-    assert (bop.export_csr() != G).nnz == 0
-    monkeypatch.setenv("LZ_SELLW_BANKS", "0")             # entries in column order: bit-identical to the plain kernel
-    for k, A in (("G", G), ("W", W)):
-        op = engine.DeviceOperator.from_scipy(ctx, A, fmt="sell")
-        assert 0 < op.windowed() <= 448, op.windowed()
-        assert op.value_free() == (k == "G")
+    buf = torch.zeros(M + 1, dtype=torch.float64, device=ctx.torch_device)      # odd rows of a basis with odd M
+    buf[1:] = torch.from_numpy(x).to(ctx.torch_device)
+    assert buf[1:].data_ptr() % 16 == 8
+    for banks in ("1", "0"):
+        monkeypatch.setenv("LZ_SELLW_BANKS", banks)
+        op = engine.DeviceOperator.from_scipy(ctx, G, fmt="sell")
+        assert 0 < op.windowed() <= 448 and op.value_free()
+        ys = []
         for variant in ("0", "1"):          # two CTAs per SM with one stage each / one CTA with two stages (the fallback)
             monkeypatch.setenv("LZ_SELLW_VARIANT", variant)
             y = op.apply_host(x)
-            assert np.array_equal(y, plain[k].apply_host(x)), (k, variant)
-            assert np.max(np.abs(y - A * x)) <= 4e-15 * np.max(np.abs(A * x))
-            # a vector that is only 8-byte aligned (odd rows of a basis with an odd row length): no bulk copies
-            import torch
-            buf = torch.zeros(M + 1, dtype=torch.float64, device=ctx.torch_device)
-            buf[1:] = torch.from_numpy(x).to(ctx.torch_device)
-            assert buf[1:].data_ptr() % 16 == 8
-            y8 = op.apply(buf[1:]).cpu().numpy()
-            assert np.array_equal(y8, y), (k, variant)
+            assert np.max(np.abs(y - G * x)) <= 4e-15 * np.max(np.abs(G * x)), (banks, variant)
+            if banks == "0":
+                assert np.array_equal(y, y_plain), variant
+            assert np.array_equal(op.apply(buf[1:]).cpu().numpy(), y), (banks, variant)      # no bulk copies
+            ys.append(y)
+        assert np.array_equal(ys[0], ys[1])
         monkeypatch.setenv("LZ_SELLW_VARIANT", "0")
-        assert (op.export_csr() != A).nnz == 0
+        assert (op.export_csr() != G).nnz == 0
     monkeypatch.delenv("LZ_SELLW_BANKS")
+    # a weighted operator keeps the plain kernel (with stored values it is already close to the HBM bound)
+    W = sp.csr_matrix(G.copy())
+    W.data = W.data * (1.0 + 0.01 * (np.arange(W.nnz) % 89))
+    wop = engine.DeviceOperator.from_scipy(ctx, W, fmt="sell")
+    assert wop.windowed() == 0 and not wop.value_free()
+    assert np.max(np.abs(wop.apply_host(x) - W * x)) <= 4e-15 * np.max(np.abs(W * x))
     # smaller sorting windows (8 chunks: half of the kernel's warps idle) and one that is no multiple of 8 chunks
     for sigma in (256, 96):
         op = engine.DeviceOperator.from_scipy(ctx, G, fmt="sell", sigma=sigma)
