@@ -78,14 +78,15 @@ struct GridSync {
         if (threadIdx.x == 0) {
             target += gridDim.x;
             epoch += 1;
-            __threadfence();
-            const unsigned int old = atomicAdd(ctr, 1u);
+            // release + acquire at gpu scope: the writes of this CTA (ordered before this thread by the barrier above) are visible to
+            // whoever acquires the epoch; cheaper than a full fence on either side of a relaxed atomic
+            unsigned int old;
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
             if (old == target - 1) {
                 asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(ctr + 32), "r"(epoch) : "memory");
             } else {
                 while (ld_acq_u32(ctr + 32) < epoch) {}
             }
-            __threadfence();
         }
         __syncthreads();
     }
@@ -154,6 +155,7 @@ small_lanczos_kernel(const SmallArgs a) {
     __shared__ double sbc[2];
     __shared__ double vs[kSmallEpt * kThreads];          // the CTA's slice of V[j] (for the row dots)
     extern __shared__ double scoef[];                    // [n + 1] sweep coefficients
+    __shared__ double sseg[8 * kThreads];                // partial coefficient sums of the CTA runs
     GridSync gs{a.bar};
     int parity = 0;
     const int64_t T = (int64_t)gridDim.x * kThreads;
@@ -193,16 +195,137 @@ small_lanczos_kernel(const SmallArgs a) {
         for (int k = 0; k < kSmallEpt; ++k) r[k] = v[k];
     }
 
+    // slice dots of the vector held in `vs` against rows 0 .. nrows-1 -> dpart[cta][i]; four rows in flight per warp:
+    // the loads (L2, ~0.5 us away) of a group are issued before any is used
+    auto slice_dots = [&](int nrows) {
+        for (int i0 = warp; i0 < nrows; i0 += 4 * kWarps) {
+            double d[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int k = 0; k < ept; ++k) {
+                double x[4][kWarps];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * kWarps;
+                    const double* vi = a.V + (int64_t)min(i, nrows - 1) * a.ldv;
+#pragma unroll
+                    for (int m = 0; m < kWarps; ++m) {
+                        const int64_t e = (int64_t)blockIdx.x * kThreads + lane + 32 * m + k * T;
+                        x[u][m] = (e < a.M) ? ld_cg(vi + e) : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int m = 0; m < kWarps; ++m) d[u] = fma(vs[k * kThreads + lane + 32 * m], x[u][m], d[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kWarps;
+                const double t = warp_sum(d[u]);
+                if (lane == 0 && i < nrows) a.dpart[(size_t)blockIdx.x * a.ldp + i] = t;
+            }
+        }
+    };
+    // scoef[i] = inv * sum over the CTAs of dpart[cta][i], CTAs in order.  The CTAs are cut into nseg runs so that all
+    // 256 threads load (thread = (run, row)); a run is summed in order with up to 32 loads in flight, then the runs
+    // are added in order.
+    auto coefficients = [&](int nrows, double inv) {
+        const int G = (int)gridDim.x;
+        for (int i0 = 0; i0 < nrows; i0 += kThreads) {
+            const int R = min(nrows - i0, kThreads);
+            const int nseg = max(1, min(kThreads / R, 8));
+            const int per = (G + nseg - 1) / nseg;
+            const int seg = threadIdx.x / R, i = i0 + threadIdx.x % R;
+            double sacc = 0.0;
+            if (seg < nseg) {
+                const int c0 = seg * per, c1 = min(G, c0 + per);
+                int cta = c0;
+                for (; cta + 32 <= c1; cta += 32) {
+                    double x[32];
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) x[u] = ld_cg(a.dpart + (size_t)(cta + u) * a.ldp + i);
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) sacc += x[u];
+                }
+                for (; cta + 8 <= c1; cta += 8) {
+                    double x[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) x[u] = ld_cg(a.dpart + (size_t)(cta + u) * a.ldp + i);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) sacc += x[u];
+                }
+                for (; cta < c1; ++cta) sacc += ld_cg(a.dpart + (size_t)cta * a.ldp + i);
+                sseg[seg * kThreads + (i - i0)] = sacc;
+            }
+            __syncthreads();
+            if ((int)threadIdx.x < R) {
+                double t = 0.0;
+                for (int q = 0; q < nseg; ++q) t += sseg[q * kThreads + threadIdx.x];
+                scoef[i0 + threadIdx.x] = inv * t;
+            }
+            __syncthreads();
+        }
+    };
+    // v = cself * v - sum_i scoef[i] V[i] on the thread's own elements; 32 rows of every element in flight,
+    // subtracted in row order
+    auto subtract_rows = [&](int nrows, double cself) {
+        double t[kSmallEpt];
+#pragma unroll
+        for (int k = 0; k < kSmallEpt; ++k) t[k] = cself * v[k];
+        int i = 0;
+        for (; i + 32 <= nrows; i += 32) {
+#pragma unroll
+            for (int k = 0; k < kSmallEpt; ++k) {
+                if (!on[k]) continue;
+                const double* col = a.V + el[k];
+                double x[32];
+#pragma unroll
+                for (int u = 0; u < 32; ++u) x[u] = ld_cg(col + (int64_t)(i + u) * a.ldv);
+#pragma unroll
+                for (int u = 0; u < 32; ++u) t[k] = fma(-scoef[i + u], x[u], t[k]);
+            }
+        }
+        for (; i + 8 <= nrows; i += 8) {
+#pragma unroll
+            for (int k = 0; k < kSmallEpt; ++k) {
+                if (!on[k]) continue;
+                const double* col = a.V + el[k];
+                double x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = ld_cg(col + (int64_t)(i + u) * a.ldv);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[k] = fma(-scoef[i + u], x[u], t[k]);
+            }
+        }
+        for (; i < nrows; ++i) {
+#pragma unroll
+            for (int k = 0; k < kSmallEpt; ++k)
+                if (on[k]) t[k] = fma(-scoef[i], ld_cg(a.V + el[k] + (int64_t)i * a.ldv), t[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kSmallEpt; ++k) if (on[k]) v[k] = t[k];
+    };
+
     for (int j = 0; j < a.n; ++j) {
         double* row = a.V + (int64_t)j * a.ldv;
-        // ---- beta_j = |r|, V[j] = r / beta_j ------------------------------------------------------
-        double beta;
+        const bool sweep = a.reorth_full && (j > 0 || a.ref);
+        const int nrows = j;                                  // rows before j; the self term is handled separately
+        // ---- beta_j = |r|, V[j] = r / beta_j; with a sweep, its first pass shares the barrier: the slice dots are
+        //      taken with r (V[i].r, divided by beta afterwards) and published together with the partial of |r|^2
+        double beta, sumsq = 0.0;
+        const bool fused_first = sweep && !(j == 0 && !a.ref);
         if (j == 0 && !a.ref) beta = nrm0;
         else {
             acc = 0.0;
 #pragma unroll
             for (int k = 0; k < kSmallEpt; ++k) acc = fma(r[k], r[k], acc);
-            beta = sqrt(grid_sum(acc, a, gs, parity, sred, sbc));
+            if (fused_first && nrows > 0) {
+#pragma unroll
+                for (int k = 0; k < kSmallEpt; ++k) vs[k * kThreads + threadIdx.x] = r[k];
+                __syncthreads();
+                slice_dots(nrows);
+            }
+            sumsq = grid_sum(acc, a, gs, parity, sred, sbc);   // (its barrier also publishes dpart)
+            beta = sqrt(sumsq);
         }
         if (g == 0) {
             a.beta[j] = beta;
@@ -210,69 +333,36 @@ small_lanczos_kernel(const SmallArgs a) {
             const bool ok = isfinite(beta) && beta > a.tol_rel * mag && beta > 0.0;
             if (!ok && a.flags[0] < 0) a.flags[0] = j;
         }
+        const double inv_beta = (beta > 0.0) ? 1.0 / beta : 0.0;
 #pragma unroll
         for (int k = 0; k < kSmallEpt; ++k) { vprev[k] = v[k]; v[k] = (beta > 0.0) ? r[k] / beta : 0.0; }
         // ---- Gram-Schmidt sweeps against the rows before (and, in the reference's form, including) row j --
-        const bool sweep = a.reorth_full && (j > 0 || a.ref);
         if (sweep) {
             for (int p = 0; p < a.passes; ++p) {
                 const int ref_form = (a.ref && p == 0 && !a.gpu_sweep) ? 1 : 0;
-                const int nrows = j;                      // rows before j; the self term is handled below
                 if (nrows == 0 && !ref_form) continue;
-                // the CTA's slice of V[j] into shared memory, then warp w takes rows w, w + 8, ...
-#pragma unroll
-                for (int k = 0; k < kSmallEpt; ++k) vs[k * kThreads + threadIdx.x] = v[k];
-                __syncthreads();
-                for (int i = warp; i < nrows; i += kWarps) {
-                    const double* vi = a.V + (int64_t)i * a.ldv;
-                    double d = 0.0;
-                    for (int k = 0; k < ept; ++k) {
-#pragma unroll
-                        for (int m = 0; m < kWarps; ++m) {
-                            const int t = lane + 32 * m;
-                            const int64_t e = (int64_t)blockIdx.x * kThreads + t + k * T;
-                            if (e < a.M) d = fma(vs[k * kThreads + t], ld_cg(vi + e), d);
-                        }
-                    }
-                    d = warp_sum(d);
-                    if (lane == 0) a.dpart[(size_t)blockIdx.x * a.ldp + i] = d;
-                }
-                double self = 0.0;
-                if (ref_form) {                           // (2 - |v|^2): the reference's sum includes row j itself
-                    double q = 0.0;
-#pragma unroll
-                    for (int k = 0; k < kSmallEpt; ++k) q = fma(v[k], v[k], q);
-                    self = grid_sum(q, a, gs, parity, sred, sbc);      // (its barrier also publishes dpart)
+                double self = 0.0, inv = 1.0;
+                if (p == 0 && fused_first) {
+                    // |V[j]|^2 = |r|^2 / beta^2 (1 to rounding; the reference sums the squares of the normalised row)
+                    self = (beta > 0.0) ? sumsq / (beta * beta) : 0.0;
+                    inv = inv_beta;
                 } else {
-                    gs.sync();
-                }
-                // coefficient of row i = sum over the CTAs of its partials: a warp per row, lane l adds CTAs
-                // l, l + 32, ... in order, then the shuffle tree - a fixed order, and the loads are in flight together
-                for (int i = warp; i < nrows; i += kWarps) {
-                    double s = 0.0;
-                    for (int cta = lane; cta < (int)gridDim.x; cta += 32) s += ld_cg(a.dpart + (size_t)cta * a.ldp + i);
-                    s = warp_sum(s);
-                    if (lane == 0) scoef[i] = s;
-                }
-                __syncthreads();
-                const double cself = ref_form ? 2.0 - self : 1.0;
+                    // the CTA's slice of V[j] into shared memory, then warp w takes rows w, w + 8, ...
 #pragma unroll
-                for (int k = 0; k < kSmallEpt; ++k) {
-                    if (on[k]) {
-                        double t = cself * v[k];
-                        const double* col = a.V + el[k];
-                        int i = 0;
-                        for (; i + 8 <= nrows; i += 8) {                 // eight rows in flight, subtracted in row order
-                            double x[8];
+                    for (int k = 0; k < kSmallEpt; ++k) vs[k * kThreads + threadIdx.x] = v[k];
+                    __syncthreads();
+                    slice_dots(nrows);
+                    if (ref_form) {                           // (2 - |v|^2): the reference's sum includes row j itself
+                        double q = 0.0;
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) x[u] = ld_cg(col + (int64_t)(i + u) * a.ldv);
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) t = fma(-scoef[i + u], x[u], t);
-                        }
-                        for (; i < nrows; ++i) t = fma(-scoef[i], ld_cg(col + (int64_t)i * a.ldv), t);
-                        v[k] = t;
+                        for (int k = 0; k < kSmallEpt; ++k) q = fma(v[k], v[k], q);
+                        self = grid_sum(q, a, gs, parity, sred, sbc);      // (its barrier also publishes dpart)
+                    } else {
+                        gs.sync();
                     }
                 }
+                coefficients(nrows, inv);
+                subtract_rows(nrows, ref_form ? 2.0 - self : 1.0);
                 __syncthreads();                          // scoef / vs are reused by the next pass
                 if (p + 1 < a.passes) gs.sync();          // dpart is rewritten by the next pass
             }
