@@ -104,7 +104,7 @@ struct ChunkRegs {
     double dd;
 };
 
-// where a chunk's index blocks are: loaded one window ahead of the indices themselves, which depend on it
+// where a chunk's index blocks are (fetched a pair of chunks ahead of the indices themselves, which depend on it)
 struct ChunkMeta {
     int c;                                                // chunk, -1: none
     int b0, nb;                                           // its blocks [b0, b0 + nb)
