@@ -402,6 +402,11 @@ int launch_small_solve(lz_ctx* ctx, lz_op* op, const double* v0_dev, int32_t n, 
     const lz_stencil& st = op->st;
     const int passes = opts->cgs_passes <= 0 ? 1 : opts->cgs_passes;
     int grid = (int)std::min<int64_t>(ctx->sms, (op->M + kThreads - 1) / kThreads);
+    // LZ_SMALL_GRID: fewer CTAs make the grid barriers cheaper and every phase longer (tuning knob)
+    if (const char* e = getenv("LZ_SMALL_GRID")) {
+        const int64_t least = (op->M + (int64_t)kThreads * kSmallEpt - 1) / ((int64_t)kThreads * kSmallEpt);
+        grid = (int)std::max<int64_t>(least, std::min<int64_t>(grid, atoi(e)));
+    }
     grid = std::max(grid, 1);
     const size_t nd = (size_t)n + 2;
     const int ldp = (int)((nd + 7) & ~(size_t)7);
